@@ -1,0 +1,132 @@
+/*
+ * trt_b200.h — C ABI of libtrt_b200.so, the B200 (sm_100a) implementation of TerminalRayTracer's
+ * per-pixel render path.  Plain C: pointers, ints and sizes only; no CUDA or torch types.
+ *
+ * The reference has no plugin / FFI layer; its "operator interface" for this path is the set of
+ * plain C functions its main() calls (TRT.c = /root/reference/TerminalRayTracer.c):
+ *
+ *      reference call site                      replacement exported here
+ *      ---------------------------------------  -------------------------------------------------
+ *      initialize_screenbuffer()   TRT.c:1241   trt_init()               (device context + staging)
+ *      load_skybox(&sky, name)     TRT.c:1244   trt_load_skybox() then trt_upload_skybox()
+ *      project_scene(&scene,&scr)  TRT.c:1339   trt_project_scene()      (same signature, same pixels)
+ *      buffered_draw_screen(&scr)  TRT.c:1342   trt_buffered_draw_screen() / trt_draw_screen()
+ *      1339 + 1342 together                     trt_render_ansi()        (fused: one D2H, one fwrite)
+ *      free_skybox(&sky)           TRT.c:1369   trt_free_skybox(), trt_shutdown()
+ *
+ * Error behaviour follows the reference (TRT.c:318-322 …): the drop-in calls cannot fail from
+ * the caller's point of view; a CUDA failure prints "file:line: message" to stderr and exit(1)s.
+ * There is NO CPU fallback: without a usable CUDA device trt_init() exits.
+ * Threading follows the reference too: one caller thread, not re-entrant.
+ *
+ * INTEGRATION.md shows the edit a maintainer makes to the reference's main() to bind these.
+ */
+#ifndef TRT_B200_H
+#define TRT_B200_H
+
+#include <stddef.h>
+#include "trt_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRT_DEMO_SPHERES 6
+#define TRT_MAX_LIGHTS 16        /* per kind; the demo scene uses 1 + 1 (TRT.c:1278-1287) */
+#define TRT_MAX_CONST_SPHERES 1024 /* geometry kept in __constant__; larger scenes fall back to global memory */
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+/* Bind this process to CUDA device `device` (one process per GPU; under torchrun pass LOCAL_RANK).
+ * Creates the library's stream and staging buffers.  Exits if no CUDA device is usable. */
+int trt_init(int device);
+void trt_shutdown(void);
+/* 1 if trt_init() has succeeded in this process */
+int trt_is_initialized(void);
+/* the library's CUDA stream as an opaque pointer (cudaStream_t), so plumbing code (torch) can order against it */
+void *trt_stream(void);
+
+/* ---- skybox ingest (replaces the pointer chase through Scene.skybox, TRT.c:782-788) ----------- */
+/* Copies the six dim*dim RGB planes to the device (each padded with dim+1 black texels, see
+ * trt_host.c).  Must be called before the first render and whenever the skybox changes.
+ * The caller's planes are not retained. */
+int trt_upload_skybox(const trt_Skybox *skybox);
+
+/* ---- drop-ins ------------------------------------------------------------------------------ */
+/* project_scene (TRT.c:966): fills screen->pixels[row*width+col] with the same FP64 RGB the
+ * reference computes, bit for bit.  scene->skybox is ignored in favour of the uploaded skybox
+ * only as far as the texel storage goes (dim must match). */
+void trt_project_scene(const trt_Scene *scene, trt_Screen *screen);
+
+/* buffered_draw_screen (TRT.c:1142) without the fwrite: writes the 9+(25W+1)H bytes of the
+ * terminal stream for `screen` to `out` and returns the byte count. */
+size_t trt_draw_screen(const trt_Screen *screen, char *out);
+
+/* exact drop-in for buffered_draw_screen: encodes on the GPU and fwrite()s the stream to stdout */
+void trt_buffered_draw_screen(const trt_Screen *screen);
+
+/* fused path: render w x h and encode on the device, copy only the byte stream back.
+ * `out` needs TRT_STREAM_BYTES(w,h) bytes; returns the byte count (0 if cap is too small). */
+size_t trt_render_ansi(const trt_Scene *scene, int width, int height, char *out, size_t cap);
+
+/* ---- device-resident pieces (row bands; used by the multi-GPU plumbing and by bench.py) ------- */
+/* Upload scene (spheres, ground, lights, camera) for subsequent *_device calls. */
+int trt_set_scene(const trt_Scene *scene);
+
+/* Render rows [row0,row1) of a width x height frame into d_pixels (device pointer to
+ * (row1-row0)*width*3 doubles, band-local row-major).  Asynchronous on trt_stream(). */
+int trt_render_rows_device(int width, int height, int row0, int row1, double *d_pixels);
+
+/* Encode `rows` rows of `width` pixels from d_pixels into d_bytes: rows*(25*width+1) bytes,
+ * starting at d_bytes + byte_offset (any alignment).  Asynchronous on trt_stream(). */
+int trt_encode_rows_device(const double *d_pixels, int width, int rows, char *d_bytes, size_t byte_offset);
+
+/* Fast-path variants: the render kernel writes one quantised cell (r,g,b,0) = (int)(c*255) per pixel
+ * (4 bytes instead of 24) and the encoder reads those; the bytes produced are identical. */
+int trt_render_rows_quant_device(int width, int height, int row0, int row1, unsigned char *d_quant);
+int trt_encode_rows_quant_device(const unsigned char *d_quant, int width, int rows, char *d_bytes, size_t byte_offset);
+
+/* Write the 6-byte home sequence at d_stream[0..5] and the 3 NUL bytes after the last row of a
+ * width x height stream (TRT.c:1102, 1104, 1130). */
+int trt_stream_frame_device(char *d_stream, int width, int height);
+
+/* Same render as trt_render_rows_device, additionally accumulating the work counters of the
+ * algorithmic flop model into counters[TRT_NUM_COUNTERS] (host array). Synchronous. */
+#define TRT_NUM_COUNTERS 32
+int trt_count_rows_device(int width, int height, int row0, int row1, double *d_pixels, long long *counters);
+/* F(frame) of SURVEY.md §8(d) from such a counter array */
+double trt_model_flops(const long long *counters);
+
+/* device memory helpers for plain-C callers (thin wrappers over cudaMalloc / cudaMemcpy) */
+void *trt_device_alloc(size_t bytes);
+void trt_device_free(void *p);
+void *trt_host_alloc_pinned(size_t bytes);
+void trt_host_free_pinned(void *p);
+int trt_copy_to_host(void *dst, const void *d_src, size_t bytes);
+int trt_copy_to_device(void *d_dst, const void *src, size_t bytes);
+int trt_synchronize(void);
+
+/* timing of the last trt_project_scene / trt_render_ansi call, CUDA events on trt_stream(), ms */
+float trt_last_render_ms(void);
+float trt_last_encode_ms(void);
+
+/* ---- measured ALU peaks (dependent-free FMA loops on every SM; TFLOP/s) ---------------------- */
+double trt_measure_fp32_tflops(void);
+double trt_measure_fp64_tflops(void);
+
+/* ---- host-side helpers (trt_host.c; no CUDA) -------------------------------------------------- */
+void trt_init_camera(trt_Camera *camera, int width, int height);                     /* TRT.c:299 */
+void trt_orbit_camera(trt_Camera *camera, double t);                                 /* TRT.c:1327-1336 */
+void trt_subpixel_offsets(double dx[TRT_RAYS_PER_PIXEL], double dy[TRT_RAYS_PER_PIXEL]); /* TRT.c:992-993 */
+void trt_demo_scene(trt_Scene *scene, trt_Sphere spheres[TRT_DEMO_SPHERES], trt_DirectionalLight *dl, trt_PointLight *pl,
+                    int width, int height);                                          /* TRT.c:1256-1306 */
+int trt_stress_scene(trt_Scene *scene, trt_Sphere *spheres, int count, trt_DirectionalLight *dl, trt_PointLight *pl,
+                     int width, int height);                                         /* SURVEY §8d config 3 */
+void trt_read_ppm(const char *filename, trt_Color **colors_ptr, int *width, int *height); /* TRT.c:309 */
+void trt_load_skybox(trt_Skybox *skybox, const char *skybox_name);                   /* TRT.c:388 (cwd/skybox/<name>) */
+void trt_load_skybox_dir(trt_Skybox *skybox, const char *dir);
+void trt_free_skybox(trt_Skybox *skybox);                                            /* TRT.c:430 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRT_B200_H */

@@ -1,0 +1,481 @@
+// trt_api.cu — the C ABI of libtrt_b200.so (include/trt_b200.h): device context, scene/skybox upload,
+// the drop-in entry points and the device-resident band API.  Host C calls land here; nothing in this
+// file computes pixels on the CPU — if CUDA is unusable the library exits (no CPU fallback by design,
+// mirroring the reference's printf+exit(1) error style, TRT.c:318-322).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include "trt_internal.h"
+
+using namespace trt;
+
+namespace {
+
+void die_if(cudaError_t e, const char *file, int line)
+{
+    if (e != cudaSuccess) {
+        fprintf(stderr, "%s:%d: CUDA error: %s\n", file, line, cudaGetErrorString(e));
+        exit(1);
+    }
+}
+#define CK(x) die_if((x), __FILE__, __LINE__)
+
+struct Buffer {
+    void *p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes)
+    {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFree(p));
+        CK(cudaMalloc(&p, bytes));
+        cap = bytes;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinnedBuffer {
+    void *p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes)
+    {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFreeHost(p));
+        CK(cudaMallocHost(&p, bytes));
+        cap = bytes;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Context {
+    bool ready = false;
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float last_render_ms = 0.f, last_encode_ms = 0.f;
+    // scene
+    DevScene scene;
+    bool have_scene = false;
+    bool const_geom = true;
+    Buffer sphere_geom, sphere_mat;
+    // skybox
+    Buffer sky;
+    int sky_dim = -1, sky_face_stride = 0;
+    // work
+    Buffer tile_counter, counters;
+    Buffer pixels, quant, bytes;
+    PinnedBuffer stage;
+} g;
+
+void require_init(const char *who)
+{
+    if (!g.ready) {
+        fprintf(stderr, "libtrt_b200: %s called before trt_init()\n", who);
+        exit(1);
+    }
+}
+
+// unit(-direction) exactly as apply_lighting does it (TRT.c:903-904, 439-450); this TU's host code is
+// compiled without FMA contraction (x86-64 baseline), so the bits equal the reference's.
+void negated_unit(const trt_Vector &dir, double out[3])
+{
+    volatile double x = dir.x * -1.0, y = dir.y * -1.0, z = dir.z * -1.0;
+    volatile double xx = x * x, yy = y * y, zz = z * z;
+    volatile double s = xx + yy;
+    s = s + zz;
+    double len = sqrt(s);
+    if (len > 0.0001) {
+        out[0] = x / len;
+        out[1] = y / len;
+        out[2] = z / len;
+    } else {
+        out[0] = x;
+        out[1] = y;
+        out[2] = z;
+    }
+}
+
+void set_material(DevMaterial &m, const trt_Material &src)
+{
+    m.color[0] = src.color.x;
+    m.color[1] = src.color.y;
+    m.color[2] = src.color.z;
+    m.reflectivity = src.reflectivity;
+}
+
+void upload_scene(const trt_Scene *scene)
+{
+    if (scene->num_directional_lights > TRT_MAX_LIGHTS || scene->num_point_lights > TRT_MAX_LIGHTS ||
+        scene->num_directional_lights < 0 || scene->num_point_lights < 0 || scene->num_spheres < 0) {
+        fprintf(stderr, "libtrt_b200: unsupported scene (at most %d lights of each kind)\n", TRT_MAX_LIGHTS);
+        exit(1);
+    }
+    DevScene &s = g.scene;
+    const trt_Camera &c = scene->camera;
+    s.bx[0] = c.frame.basis.x.x; s.bx[1] = c.frame.basis.x.y; s.bx[2] = c.frame.basis.x.z;
+    s.by[0] = c.frame.basis.y.x; s.by[1] = c.frame.basis.y.y; s.by[2] = c.frame.basis.y.z;
+    s.bz[0] = c.frame.basis.z.x; s.bz[1] = c.frame.basis.z.y; s.bz[2] = c.frame.basis.z.z;
+    s.eye[0] = c.frame.origin.x; s.eye[1] = c.frame.origin.y; s.eye[2] = c.frame.origin.z;
+    s.screen_distance = c.screen_distance;
+    s.screen_width = c.screen_width;
+    s.screen_height = c.screen_height;
+    s.ground_point[0] = scene->ground.point.x; s.ground_point[1] = scene->ground.point.y; s.ground_point[2] = scene->ground.point.z;
+    s.ground_normal[0] = scene->ground.normal.x; s.ground_normal[1] = scene->ground.normal.y; s.ground_normal[2] = scene->ground.normal.z;
+    set_material(s.ground_even, scene->ground.even_material);
+    set_material(s.ground_odd, scene->ground.odd_material);
+    s.num_dir = scene->num_directional_lights;
+    s.num_point = scene->num_point_lights;
+    for (int i = 0; i < s.num_dir; i++) {
+        negated_unit(scene->directional_lights[i].direction, s.dir[i].L);
+        s.dir[i].color[0] = scene->directional_lights[i].color.x;
+        s.dir[i].color[1] = scene->directional_lights[i].color.y;
+        s.dir[i].color[2] = scene->directional_lights[i].color.z;
+    }
+    for (int i = 0; i < s.num_point; i++) {
+        const trt_PointLight &p = scene->point_lights[i];
+        s.point[i].pos[0] = p.position.x; s.point[i].pos[1] = p.position.y; s.point[i].pos[2] = p.position.z;
+        s.point[i].color[0] = p.color.x; s.point[i].color[1] = p.color.y; s.point[i].color[2] = p.color.z;
+        s.point[i].intensity = p.intensity;
+    }
+    s.num_spheres = scene->num_spheres;
+    g.const_geom = s.num_spheres <= TRT_MAX_CONST_SPHERES;
+    s.spheres_in_const = g.const_geom ? 1 : 0;
+    s.sky_dim = g.sky_dim;
+    s.sky_face_stride = g.sky_face_stride;
+    trt_subpixel_offsets(s.sub_dx, s.sub_dy);
+
+    const int n = s.num_spheres;
+    std::vector<double4> geom((size_t)(n > 0 ? n : 1));
+    std::vector<DevMaterial> mats((size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) {
+        const trt_Sphere &sp = scene->spheres[i];
+        volatile double r2 = sp.radius * sp.radius;   // TRT.c:648, a single rounded product
+        geom[i] = make_double4(sp.center.x, sp.center.y, sp.center.z, r2);
+        set_material(mats[i], sp.material);
+    }
+    g.sphere_geom.reserve(sizeof(double4) * geom.size());
+    g.sphere_mat.reserve(sizeof(DevMaterial) * mats.size());
+    // The vectors above die at the end of this function, so these copies must complete before it
+    // returns: plain (staged) cudaMemcpyAsync from pageable memory is synchronous w.r.t. the host buffer.
+    CK(cudaMemcpyAsync(g.sphere_geom.p, geom.data(), sizeof(double4) * geom.size(), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.sphere_mat.p, mats.data(), sizeof(DevMaterial) * mats.size(), cudaMemcpyHostToDevice, g.stream));
+    upload_scene_constants(s, geom.data(), n, g.stream);
+    CK(cudaStreamSynchronize(g.stream));
+    g.have_scene = true;
+}
+
+RenderParams make_params(int width, int height, int row0, int row1, double *d_pixels, uchar4 *d_quant, bool count)
+{
+    if (!g.have_scene) {
+        fprintf(stderr, "libtrt_b200: render requested before a scene was set\n");
+        exit(1);
+    }
+    if (g.sky_dim <= 0) {
+        fprintf(stderr, "libtrt_b200: render requested before trt_upload_skybox()\n");
+        exit(1);
+    }
+    RenderParams p;
+    p.width = width;
+    p.height = height;
+    p.row0 = row0;
+    p.row1 = row1;
+    p.pixels = d_pixels;
+    p.quant = d_quant;
+    p.sphere_geom = (const double4 *)g.sphere_geom.p;
+    p.sphere_mat = (const DevMaterial *)g.sphere_mat.p;
+    p.sky = (const uchar4 *)g.sky.p;
+    p.tile_counter = (unsigned int *)g.tile_counter.p;
+    p.counters = count ? (unsigned long long *)g.counters.p : nullptr;
+    return p;
+}
+
+} // namespace
+
+extern "C" {
+
+int trt_init(int device)
+{
+    if (g.ready) return 0;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        fprintf(stderr, "libtrt_b200: no usable CUDA device (%s); this library has no CPU fallback\n",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        exit(1);
+    }
+    if (device < 0 || device >= n) {
+        fprintf(stderr, "libtrt_b200: device %d out of range (0..%d)\n", device, n - 1);
+        exit(1);
+    }
+    CK(cudaSetDevice(device));
+    g.device = device;
+    CK(cudaDeviceGetAttribute(&g.num_sms, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    for (auto &ev : g.ev) CK(cudaEventCreate(&ev));
+    g.tile_counter.reserve(256);
+    g.counters.reserve(sizeof(unsigned long long) * TRT_NUM_COUNTERS);
+    g.ready = true;
+    return 0;
+}
+
+void trt_shutdown(void)
+{
+    if (!g.ready) return;
+    cudaStreamSynchronize(g.stream);
+    g.sphere_geom.release();
+    g.sphere_mat.release();
+    g.sky.release();
+    g.tile_counter.release();
+    g.counters.release();
+    g.pixels.release();
+    g.quant.release();
+    g.bytes.release();
+    g.stage.release();
+    for (auto &ev : g.ev) {
+        if (ev) cudaEventDestroy(ev);
+        ev = nullptr;
+    }
+    cudaStreamDestroy(g.stream);
+    g.stream = nullptr;
+    g.have_scene = false;
+    g.sky_dim = -1;
+    g.ready = false;
+}
+
+int trt_is_initialized(void) { return g.ready ? 1 : 0; }
+void *trt_stream(void) { return (void *)g.stream; }
+
+int trt_upload_skybox(const trt_Skybox *skybox)
+{
+    require_init("trt_upload_skybox");
+    const int dim = skybox->dim;
+    if (dim <= 0) {
+        fprintf(stderr, "libtrt_b200: skybox has no faces loaded (dim=%d)\n", dim);
+        exit(1);
+    }
+    // RGBA8 repack: one aligned 4-byte load per lookup instead of three byte loads.  Each face keeps
+    // dim+1 black texels after its payload: the reference's index can run that far (TRT.c:778-788).
+    const size_t payload = (size_t)dim * (size_t)dim;
+    const size_t stride = payload + (size_t)dim + 1;
+    std::vector<uchar4> packed(stride * 6, make_uchar4(0, 0, 0, 0));
+    for (int f = 0; f < 6; f++) {
+        const trt_Color *src = skybox->colors[f];
+        uchar4 *dst = packed.data() + stride * (size_t)f;
+        for (size_t i = 0; i < payload; i++) dst[i] = make_uchar4(src[i].r, src[i].g, src[i].b, 0);
+    }
+    g.sky.reserve(sizeof(uchar4) * packed.size());
+    CK(cudaMemcpyAsync(g.sky.p, packed.data(), sizeof(uchar4) * packed.size(), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    g.sky_dim = dim;
+    g.sky_face_stride = (int)stride;
+    if (g.have_scene) {
+        g.scene.sky_dim = dim;
+        g.scene.sky_face_stride = (int)stride;
+    }
+    return 0;
+}
+
+int trt_set_scene(const trt_Scene *scene)
+{
+    require_init("trt_set_scene");
+    upload_scene(scene);
+    return 0;
+}
+
+int trt_render_rows_device(int width, int height, int row0, int row1, double *d_pixels)
+{
+    require_init("trt_render_rows_device");
+    RenderParams p = make_params(width, height, row0, row1, d_pixels, nullptr, false);
+    launch_render(p, false, g.const_geom, g.num_sms, g.stream);
+    return 0;
+}
+
+int trt_render_rows_quant_device(int width, int height, int row0, int row1, unsigned char *d_quant)
+{
+    require_init("trt_render_rows_quant_device");
+    RenderParams p = make_params(width, height, row0, row1, nullptr, (uchar4 *)d_quant, false);
+    launch_render(p, false, g.const_geom, g.num_sms, g.stream);
+    return 0;
+}
+
+int trt_encode_rows_device(const double *d_pixels, int width, int rows, char *d_bytes, size_t byte_offset)
+{
+    require_init("trt_encode_rows_device");
+    launch_encode_f64(d_pixels, width, rows, d_bytes, byte_offset, g.stream);
+    return 0;
+}
+
+int trt_encode_rows_quant_device(const unsigned char *d_quant, int width, int rows, char *d_bytes, size_t byte_offset)
+{
+    require_init("trt_encode_rows_quant_device");
+    launch_encode_quant((const uchar4 *)d_quant, width, rows, d_bytes, byte_offset, g.stream);
+    return 0;
+}
+
+int trt_stream_frame_device(char *d_stream, int width, int height)
+{
+    require_init("trt_stream_frame_device");
+    launch_stream_frame(d_stream, width, height, g.stream);
+    return 0;
+}
+
+int trt_count_rows_device(int width, int height, int row0, int row1, double *d_pixels, long long *counters)
+{
+    require_init("trt_count_rows_device");
+    CK(cudaMemsetAsync(g.counters.p, 0, sizeof(unsigned long long) * TRT_NUM_COUNTERS, g.stream));
+    RenderParams p = make_params(width, height, row0, row1, d_pixels, nullptr, true);
+    launch_render(p, true, g.const_geom, g.num_sms, g.stream);
+    CK(cudaMemcpyAsync(counters, g.counters.p, sizeof(unsigned long long) * TRT_NUM_COUNTERS, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+double trt_model_flops(const long long *c)
+{
+    // as-written adds/muls/divs/sqrts of the reference per counted event
+    return 25.0 * c[CTR_SPHERE_TESTS] + 5.0 * c[CTR_SPHERE_DISC_OK] + 14.0 * c[CTR_SPHERE_T0_POS] + 3.0 * c[CTR_SPHERE_CLOSEST] +
+           5.0 * c[CTR_PLANE_TESTS] + 9.0 * c[CTR_PLANE_DENOM_OK] + 14.0 * c[CTR_PLANE_T_POS] + 1.0 * c[CTR_PLANE_CLOSEST] +
+           90.0 * c[CTR_SKY_LOOKUPS] + 27.0 * c[CTR_TRACE_HITS] + 55.0 * c[CTR_LIGHTING_CALLS] + 34.0 * c[CTR_BOUNCE_ITERS] +
+           68.0 * c[CTR_SAMPLES] + 4.0 * c[CTR_PIXELS];
+}
+
+// ---- drop-ins ---------------------------------------------------------------------------------------
+
+void trt_project_scene(const trt_Scene *scene, trt_Screen *screen)
+{
+    require_init("trt_project_scene");
+    const int w = screen->width, h = screen->height;
+    if (w <= 0 || h <= 0) return;
+    upload_scene(scene);
+    const size_t bytes = sizeof(double) * 3 * (size_t)w * (size_t)h;
+    g.pixels.reserve(bytes);
+    RenderParams p = make_params(w, h, 0, h, (double *)g.pixels.p, nullptr, false);
+    CK(cudaEventRecord(g.ev[0], g.stream));
+    launch_render(p, false, g.const_geom, g.num_sms, g.stream);
+    CK(cudaEventRecord(g.ev[1], g.stream));
+    CK(cudaMemcpyAsync(screen->pixels, g.pixels.p, bytes, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaEventElapsedTime(&g.last_render_ms, g.ev[0], g.ev[1]));
+}
+
+size_t trt_draw_screen(const trt_Screen *screen, char *out)
+{
+    require_init("trt_draw_screen");
+    const int w = screen->width, h = screen->height;
+    const size_t total = TRT_STREAM_BYTES(w, h);
+    const size_t px_bytes = sizeof(double) * 3 * (size_t)w * (size_t)h;
+    g.pixels.reserve(px_bytes ? px_bytes : 8);
+    g.bytes.reserve(total + 16);
+    if (px_bytes) CK(cudaMemcpyAsync(g.pixels.p, screen->pixels, px_bytes, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaEventRecord(g.ev[2], g.stream));
+    launch_stream_frame((char *)g.bytes.p, w, h, g.stream);
+    launch_encode_f64((const double *)g.pixels.p, w, h, (char *)g.bytes.p, TRT_HOME_BYTES, g.stream);
+    CK(cudaEventRecord(g.ev[3], g.stream));
+    CK(cudaMemcpyAsync(out, g.bytes.p, total, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaEventElapsedTime(&g.last_encode_ms, g.ev[2], g.ev[3]));
+    return total;
+}
+
+void trt_buffered_draw_screen(const trt_Screen *screen)
+{
+    require_init("trt_buffered_draw_screen");
+    const size_t total = TRT_STREAM_BYTES(screen->width, screen->height);
+    g.stage.reserve(total);
+    trt_draw_screen(screen, (char *)g.stage.p);
+    fwrite(g.stage.p, sizeof(char), total, stdout); // TRT.c:1171
+}
+
+size_t trt_render_ansi(const trt_Scene *scene, int width, int height, char *out, size_t cap)
+{
+    require_init("trt_render_ansi");
+    const size_t total = TRT_STREAM_BYTES(width, height);
+    if (cap < total || width <= 0 || height <= 0) return 0;
+    upload_scene(scene);
+    g.quant.reserve(sizeof(uchar4) * (size_t)width * (size_t)height);
+    g.bytes.reserve(total + 16);
+    RenderParams p = make_params(width, height, 0, height, nullptr, (uchar4 *)g.quant.p, false);
+    CK(cudaEventRecord(g.ev[0], g.stream));
+    launch_render(p, false, g.const_geom, g.num_sms, g.stream);
+    CK(cudaEventRecord(g.ev[1], g.stream));
+    launch_stream_frame((char *)g.bytes.p, width, height, g.stream);
+    launch_encode_quant((const uchar4 *)g.quant.p, width, height, (char *)g.bytes.p, TRT_HOME_BYTES, g.stream);
+    CK(cudaEventRecord(g.ev[3], g.stream));
+    CK(cudaMemcpyAsync(out, g.bytes.p, total, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaEventElapsedTime(&g.last_render_ms, g.ev[0], g.ev[1]));
+    CK(cudaEventElapsedTime(&g.last_encode_ms, g.ev[1], g.ev[3]));
+    return total;
+}
+
+// ---- small helpers for plain-C callers -----------------------------------------------------------------
+
+void *trt_device_alloc(size_t bytes)
+{
+    require_init("trt_device_alloc");
+    void *p = nullptr;
+    CK(cudaMalloc(&p, bytes ? bytes : 1));
+    return p;
+}
+void trt_device_free(void *p)
+{
+    if (p) CK(cudaFree(p));
+}
+void *trt_host_alloc_pinned(size_t bytes)
+{
+    require_init("trt_host_alloc_pinned");
+    void *p = nullptr;
+    CK(cudaMallocHost(&p, bytes ? bytes : 1));
+    return p;
+}
+void trt_host_free_pinned(void *p)
+{
+    if (p) CK(cudaFreeHost(p));
+}
+int trt_copy_to_host(void *dst, const void *d_src, size_t bytes)
+{
+    require_init("trt_copy_to_host");
+    CK(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+int trt_copy_to_device(void *d_dst, const void *src, size_t bytes)
+{
+    require_init("trt_copy_to_device");
+    CK(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+int trt_synchronize(void)
+{
+    require_init("trt_synchronize");
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+float trt_last_render_ms(void) { return g.last_render_ms; }
+float trt_last_encode_ms(void) { return g.last_encode_ms; }
+
+double trt_measure_fp32_tflops(void)
+{
+    require_init("trt_measure_fp32_tflops");
+    return measure_fp32_tflops(g.stream);
+}
+double trt_measure_fp64_tflops(void)
+{
+    require_init("trt_measure_fp64_tflops");
+    return measure_fp64_tflops(g.stream);
+}
+
+} // extern "C"

@@ -1,0 +1,24 @@
+// trt_internal.h — C++ glue between the translation units of libtrt_b200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include "trt_device.cuh"
+
+namespace trt {
+
+// trt_render.cu (owns the __constant__ scene)
+void upload_scene_constants(const DevScene &scene, const double4 *geom, int count, cudaStream_t stream);
+void launch_render(const RenderParams &p, bool count, bool const_geom, int num_sms, cudaStream_t stream);
+int render_ctas_per_sm();
+
+// trt_encode.cu
+// Encode `rows` rows of `width` cells into out_base[byte_offset ...); source is either the FP64
+// framebuffer (3 doubles per pixel) or the quantised cells written by the render kernel.
+void launch_encode_f64(const double *pixels, int width, int rows, char *out_base, size_t byte_offset, cudaStream_t stream);
+void launch_encode_quant(const uchar4 *quant, int width, int rows, char *out_base, size_t byte_offset, cudaStream_t stream);
+void launch_stream_frame(char *stream_base, int width, int height, cudaStream_t stream);
+
+// trt_peak.cu
+double measure_fp32_tflops(cudaStream_t stream);
+double measure_fp64_tflops(cudaStream_t stream);
+
+} // namespace trt

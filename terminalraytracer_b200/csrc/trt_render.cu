@@ -1,0 +1,450 @@
+// trt_render.cu — K1: the per-pixel render loop of the reference as one persistent sm_100a kernel.
+//
+// Replaces project_scene (TRT.c:966-1069) and everything it calls: trace_ray (793-889),
+// ray_intersects_sphere (638-672), ray_intersects_plane (677-695), get_skybox_color (700-789),
+// apply_lighting (894-963), reflect_vector (627-633).  TRT.c = /root/reference/TerminalRayTracer.c.
+//
+// Exactness contract: every value that reaches a pixel is computed with the reference's IEEE-double
+// operations in the reference's order (this TU is compiled with -fmad=false), so the framebuffer is
+// bit-identical to the reference's.  What is NOT reproduced is work that cannot influence a pixel:
+//   * the skybox lookup the reference performs when a SHADOW ray misses (TRT.c:907, 937 -> 858-867),
+//   * the reflect/normalise the reference performs after a sample has already hit the sky (1054-1055),
+//   * the `view` vector (1029) and the specularity field (118), both never read.
+//
+// Execution model (why it looks nothing like the reference's call tree):
+//   * persistent CTAs, one per SM slot; each WARP pulls 8x4-pixel tiles from a global atomic counter,
+//     lane = pixel, so the 32 rays of a warp are spatially coherent;
+//   * every lane runs ONE loop whose body starts with the closest-hit query (the sphere loop is ~half
+//     of all work) and then advances a small per-lane state machine: primary/bounce ray -> one shadow
+//     ray per light -> shade/reflect -> next bounce or next sample.  Primary, bounce and shadow rays of
+//     different lanes therefore share the same sphere-loop instructions instead of serialising three
+//     inlined copies of trace_ray, and a lane that finishes a sample immediately starts its next one;
+//   * the scene sits in __constant__ memory (warp-uniform index in the sphere loop -> one broadcast
+//     LDC per operand); the skybox is an RGBA8 repack read through the read-only path and stays
+//     L2-resident; the k/255.0 colour table is in shared memory.
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include "trt_device.cuh"
+#include "trt_internal.h"
+
+namespace trt {
+
+__constant__ DevScene c_scene;
+__constant__ double4 c_sphere_geom[TRT_MAX_CONST_SPHERES]; // (cx, cy, cz, r*r)
+
+constexpr int TILE_W = 8;
+constexpr int TILE_H = 4;
+constexpr int WARPS_PER_CTA = 4;
+constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+
+enum Phase : int { PH_MAIN = 0, PH_SHADOW = 1 };
+
+// (cx,cy,cz,r*r) of sphere i through the read-only path (scenes too large for __constant__)
+__device__ __forceinline__ double4 ldg_geom(const double4 *geom, int i)
+{
+    const double2 *p = reinterpret_cast<const double2 *>(geom + i);
+    const double2 lo = __ldg(p), hi = __ldg(p + 1);
+    return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+
+template <bool COUNT>
+struct Tally {
+    unsigned long long *g;
+    __device__ __forceinline__ void add(int id) const
+    {
+        if (COUNT) atomicAdd(&g[id], 1ull);
+    }
+};
+
+// ---- get_skybox_color, TRT.c:700-789 -----------------------------------------------------------------
+// Returns the linear texel index inside the chosen face and the face itself.  The dot products with
+// the axis table reduce exactly (x*1.0 + y*0.0 + z*0.0 == x for finite inputs), so the face argmax,
+// the projection and the (u,v) extraction below are the reference's values, not approximations.
+__device__ __forceinline__ int sky_texel_index(const d3 &direction, int dim, int &face)
+{
+    d3 dir = unit(direction);
+    // argmax over (+x,-x,+y,-y,+z,-z), strict >, first wins, start at -1.0 (TRT.c:703-713)
+    double best_t = -1.0;
+    int best = -1;
+    const double cand[6] = {dir.x, -dir.x, dir.y, -dir.y, dir.z, -dir.z};
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+        if (cand[f] > best_t) {
+            best_t = cand[f];
+            best = f;
+        }
+    }
+    // scale_by == best_t (sum of dir (*) axis), TRT.c:717-719
+    const double s = 1.0 / best_t;
+    const double px = dir.x * s, py = dir.y * s, pz = dir.z * s;
+    // orthogonal component * 0.5, then dots with axes (best+2)%6 and (best+4)%6 (TRT.c:720-727)
+    double u, v;
+    switch (best) {
+    case 0: u = py * 0.5; v = pz * 0.5; break;
+    case 1: u = -(py * 0.5); v = -(pz * 0.5); break;
+    case 2: u = pz * 0.5; v = px * 0.5; break;
+    case 3: u = -(pz * 0.5); v = -(px * 0.5); break;
+    case 4: u = px * 0.5; v = py * 0.5; break;
+    default: u = -(px * 0.5); v = -(py * 0.5); break;
+    }
+    if (best & 1) u *= -1.0;                     // :730
+    if (best <= 1) { double t = u; u = v; v = -t; }          // :735
+    else if (best <= 3) { double t = u; u = -v; v = t; }     // :742-755
+    else if (best == 4) { u *= -1.0; v *= -1.0; }            // :756
+    u = clampd(u, -0.5, 0.5);
+    v = clampd(v, -0.5, 0.5);
+    const int ui = x86_int((u + 0.5) * dim);
+    const int vi = x86_int((v + 0.5) * dim);
+    face = best;
+    return ui + vi * dim;
+}
+
+// ---- closest-hit query, the geometric half of trace_ray (TRT.c:805-853) -------------------------------
+// obj: 0 none, 1 sphere, 2 ground.  hit = un-pushed intersection point of the closest object.
+template <bool COUNT, bool CONST_GEOM>
+__device__ __forceinline__ void closest_hit(const RenderParams &P, const d3 &o, const d3 &d, int &obj, int &index,
+                                            d3 &hit, const Tally<COUNT> &tally)
+{
+    double closest = INFINITY;
+    obj = 0;
+    index = -1;
+    const double a = dot(d, d);                  // TRT.c:646, loop-invariant
+    const double two_a = 2.0 * a;
+    const double four_a = 4.0 * a;
+    const int n = c_scene.num_spheres;
+    for (int i = 0; i < n; i++) {
+        double4 g;
+        if (CONST_GEOM) g = c_sphere_geom[i];
+        else g = ldg_geom(P.sphere_geom, i);
+        tally.add(CTR_SPHERE_TESTS);
+        const d3 oc = mk3(o.x - g.x, o.y - g.y, o.z - g.z);
+        const double b = 2.0 * dot(oc, d);
+        const double c = dot(oc, oc) - g.w;      // g.w = radius*radius, evaluated on the host in double
+        const double disc = b * b - four_a * c;  // (4.0*a)*c, scaling by 4 is exact
+        if (!(disc < 0.0)) {                     // TRT.c:651
+            tally.add(CTR_SPHERE_DISC_OK);
+            const double t0 = (-b - sqrt(disc)) / two_a;
+            if (t0 > 0.0) {
+                tally.add(CTR_SPHERE_T0_POS);
+                const d3 p = mk3(o.x + t0 * d.x, o.y + t0 * d.y, o.z + t0 * d.z);
+                const d3 back = o - p;
+                const double d2 = dot(back, back);
+                if (d2 < closest) {
+                    tally.add(CTR_SPHERE_CLOSEST);
+                    closest = d2;
+                    obj = 1;
+                    index = i;
+                    hit = p;
+                }
+            }
+        }
+    }
+    // ground, TRT.c:677-695 and 831-853
+    tally.add(CTR_PLANE_TESTS);
+    const d3 gn = mk3(c_scene.ground_normal[0], c_scene.ground_normal[1], c_scene.ground_normal[2]);
+    const double denom = dot(d, gn);
+    if (fabs(denom) > 0.00001) {
+        tally.add(CTR_PLANE_DENOM_OK);
+        const d3 to_plane = mk3(c_scene.ground_point[0] - o.x, c_scene.ground_point[1] - o.y, c_scene.ground_point[2] - o.z);
+        const double t = dot(to_plane, gn) / denom;
+        if (t > 0.00001) {
+            tally.add(CTR_PLANE_T_POS);
+            const d3 p = mk3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
+            const d3 back = o - p;
+            const double d2 = dot(back, back);
+            if (d2 < closest) {
+                tally.add(CTR_PLANE_CLOSEST);
+                obj = 2;
+                // checker parity, TRT.c:850
+                index = x86_int(floor(p.x) + floor(p.z)) & 1;
+                hit = p;
+            }
+        }
+    }
+}
+
+// hit point pushed back toward the ray origin by EPSILON, TRT.c:871-874
+__device__ __forceinline__ d3 push_back(const d3 &o, const d3 &hit)
+{
+    d3 back = unit(o - hit);
+    back = back * TRT_EPSILON;
+    return hit + back;
+}
+
+template <bool COUNT, bool CONST_GEOM>
+__global__ void __launch_bounds__(CTA_THREADS) k_render(const RenderParams P)
+{
+    __shared__ double s_byte_to_unit[256]; // k/255.0, the division of TRT.c:866 done once per CTA
+    __shared__ unsigned int s_tile[WARPS_PER_CTA];
+    for (int k = threadIdx.x; k < 256; k += CTA_THREADS) s_byte_to_unit[k] = (double)k / 255.0;
+    __syncthreads();
+
+    const Tally<COUNT> tally{P.counters};
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int band_rows = P.row1 - P.row0;
+    const int tiles_x = (P.width + TILE_W - 1) / TILE_W;
+    const int tiles_y = (band_rows + TILE_H - 1) / TILE_H;
+    const unsigned int num_tiles = (unsigned int)(tiles_x * tiles_y);
+
+    const d3 bx = mk3(c_scene.bx[0], c_scene.bx[1], c_scene.bx[2]);
+    const d3 by = mk3(c_scene.by[0], c_scene.by[1], c_scene.by[2]);
+    const d3 bz = mk3(c_scene.bz[0], c_scene.bz[1], c_scene.bz[2]);
+    const d3 eye = mk3(c_scene.eye[0], c_scene.eye[1], c_scene.eye[2]);
+    const double sw = c_scene.screen_width, sh = c_scene.screen_height;
+    const double pixel_w = sw / P.width;   // TRT.c:981
+    const double pixel_h = sh / P.height;  // TRT.c:982
+    const double sz = -c_scene.screen_distance;
+    const int num_dir = c_scene.num_dir;
+    const int num_lights = num_dir + c_scene.num_point;
+
+    for (;;) {
+        if (lane == 0) s_tile[warp] = atomicAdd(P.tile_counter, 1u);
+        __syncwarp();
+        const unsigned int tile = s_tile[warp];
+        __syncwarp();
+        if (tile >= num_tiles) break;
+        const int ty = (int)(tile / (unsigned)tiles_x), tx = (int)(tile % (unsigned)tiles_x);
+        const int col = tx * TILE_W + (lane & (TILE_W - 1));
+        const int brow = ty * TILE_H + (lane >> 3); // band-local row
+        const int row = P.row0 + brow;
+        if (col >= P.width || brow >= band_rows) continue; // lane idles for this tile
+        tally.add(CTR_PIXELS);
+
+        // per-pixel part of the primary ray, TRT.c:987-988
+        const double sx0 = (((double)col / (double)P.width) * sw - sw / 2.0);
+        const double sy0 = -(((double)row / (double)P.height) * sh - sh / 2.0);
+
+        d3 average = mk3(0.0, 0.0, 0.0);
+        // ---- per-lane state machine -----------------------------------------------------------
+        int k = 0;            // sample index (ray_num)
+        int phase = PH_MAIN;
+        int bounces = 0;
+        int light = 0;        // index of the light whose shadow ray is in flight
+        int surf_obj = 0, surf_index = 0;  // what the main ray hit
+        double weight = 1.0, weight_sum = 0.0, light_d2 = 0.0, intensity = 0.0;
+        d3 o, d, d_main, nrm, lit, sample;
+        bool new_sample = true;
+
+        while (k < TRT_RAYS_PER_PIXEL) {
+            if (new_sample) {
+                // primary ray of sample k, TRT.c:987-1016
+                tally.add(CTR_SAMPLES);
+                const double sx = sx0 + c_scene.sub_dx[k] * pixel_w;
+                const double sy = sy0 + c_scene.sub_dy[k] * pixel_h;
+                const d3 wx = bx * sx, wy = by * sy, wz = bz * sz;
+                d3 sp = mk3(0.0, 0.0, 0.0);
+                sp = sp + wx;
+                sp = sp + wy;
+                sp = sp + wz;
+                sp = sp - eye;              // TRT.c:1005 (origin subtracted from an untranslated vector)
+                d = unit(sp);
+                o = eye;
+                sample = mk3(0.0, 0.0, 0.0);
+                bounces = 0;
+                weight = 1.0;
+                weight_sum = 0.0;
+                phase = PH_MAIN;
+                new_sample = false;
+            }
+
+            // ---- the shared part: closest hit of the current ray -----------------------------
+            int obj, index;
+            d3 hit;
+            tally.add(CTR_TRACE_CALLS);
+            if (phase == PH_MAIN) tally.add(CTR_BOUNCE_ITERS);
+            closest_hit<COUNT, CONST_GEOM>(P, o, d, obj, index, hit, tally);
+            if (obj != 0) tally.add(CTR_TRACE_HITS);
+            else { tally.add(CTR_SKY_LOOKUPS); if (phase != PH_MAIN) tally.add(CTR_SKY_SKIPPED); }
+
+            bool shade_done = false; // true when `lit` holds the final surface colour of the main hit
+            if (phase == PH_MAIN) {
+                if (obj == 0) {
+                    // sky: TRT.c:858-867, then the tail of the bounce loop 1034-1051 with weight -> 0
+                    int face;
+                    const int texel = sky_texel_index(d, c_scene.sky_dim, face);
+                    const uchar4 t = __ldg(&P.sky[(size_t)face * (size_t)c_scene.sky_face_stride + (size_t)texel]);
+                    d3 c = mk3(s_byte_to_unit[t.x], s_byte_to_unit[t.y], s_byte_to_unit[t.z]);
+                    weight_sum += weight;
+                    c = c * weight;
+                    sample = sample + c;
+                    // sample finished
+                    if (COUNT) atomicAdd(&P.counters[CTR_BOUNCE_HIST0 + bounces], 1ull);
+                    sample = sample * (1.0 / weight_sum);   // TRT.c:1061
+                    average = average + sample;             // TRT.c:1063
+                    k++;
+                    new_sample = true;
+                    continue;
+                }
+                // surface hit: remember it, start the light loop (apply_lighting, TRT.c:894-963)
+                tally.add(CTR_LIGHTING_CALLS);
+                surf_obj = obj;
+                surf_index = index;
+                d3 n;
+                if (obj == 1) {
+                    double4 g;
+                    if (CONST_GEOM) g = c_sphere_geom[index];
+                    else g = ldg_geom(P.sphere_geom, index);
+                    n = mk3(hit.x - g.x, hit.y - g.y, hit.z - g.z);   // TRT.c:824
+                } else {
+                    n = mk3(c_scene.ground_normal[0], c_scene.ground_normal[1], c_scene.ground_normal[2]);
+                }
+                const d3 at = push_back(o, hit);
+                nrm = unit(n);                                       // TRT.c:878
+                d_main = d;
+                o = at;
+                lit = mk3(0.0, 0.0, 0.0);
+                light = 0;
+                if (num_lights == 0) shade_done = true;
+                else phase = PH_SHADOW;
+            } else {
+                // ---- a shadow ray came back: add this light's contribution ------------------
+                d3 mcol;
+                {
+                    const DevMaterial *m = (surf_obj == 1) ? &P.sphere_mat[surf_index]
+                                                           : (surf_index ? &c_scene.ground_odd : &c_scene.ground_even);
+                    mcol = mk3(m->color[0], m->color[1], m->color[2]);
+                }
+                if (light < num_dir) {
+                    if (obj == 0) {                                   // TRT.c:908-921
+                        const DevLightDir &Ld = c_scene.dir[light];
+                        const double f = fmin(dot(nrm, d), 1.0);
+                        d3 diffuse = mk3(Ld.color[0] * f, Ld.color[1] * f, Ld.color[2] * f);
+                        diffuse = hadamard(diffuse, mcol);
+                        lit = lit + diffuse;
+                    }
+                } else {
+                    bool open = (obj == 0);
+                    if (!open) {                                      // TRT.c:939-942
+                        const d3 blocker = push_back(o, hit);
+                        const d3 to_blocker = blocker - o;
+                        open = light_d2 < dot(to_blocker, to_blocker);
+                    }
+                    if (open) {                                       // TRT.c:945-954
+                        const DevLightPoint &Lp = c_scene.point[light - num_dir];
+                        const double f = intensity * fmin(dot(nrm, d), 1.0);
+                        d3 diffuse = mk3(Lp.color[0] * f, Lp.color[1] * f, Lp.color[2] * f);
+                        diffuse = hadamard(diffuse, mcol);
+                        lit = lit + diffuse;
+                    }
+                }
+                light++;
+                if (light == num_lights) shade_done = true;
+            }
+
+            if (!shade_done) {
+                // aim the shadow ray of light `light` from the surface point o
+                if (light < num_dir) {
+                    const DevLightDir &Ld = c_scene.dir[light];
+                    d = mk3(Ld.L[0], Ld.L[1], Ld.L[2]);
+                } else {
+                    const DevLightPoint &Lp = c_scene.point[light - num_dir];
+                    d3 L = mk3(Lp.pos[0] - o.x, Lp.pos[1] - o.y, Lp.pos[2] - o.z);   // TRT.c:929
+                    light_d2 = dot(L, L);
+                    intensity = clampd(Lp.intensity / light_d2, 0.0, 1.0);           // TRT.c:931
+                    d = unit(L);
+                }
+                continue;
+            }
+
+            // ---- surface colour complete: tail of the bounce loop, TRT.c:1034-1056 --------------
+            lit.x = clampd(lit.x, 0.0, 1.0);                          // TRT.c:960
+            lit.y = clampd(lit.y, 0.0, 1.0);
+            lit.z = clampd(lit.z, 0.0, 1.0);
+            double reflectivity;
+            {
+                const DevMaterial *m = (surf_obj == 1) ? &P.sphere_mat[surf_index]
+                                                       : (surf_index ? &c_scene.ground_odd : &c_scene.ground_even);
+                reflectivity = m->reflectivity;
+            }
+            weight_sum += weight;
+            lit = lit * weight;
+            weight *= reflectivity;
+            bounces++;
+            sample = sample + lit;
+            if (bounces < TRT_BOUNCE_LIMIT && weight > 0.00001) {     // loop condition, TRT.c:1018
+                const double dn = dot(d_main, nrm);                   // reflect_vector, TRT.c:627-633
+                d3 r = mk3(d_main.x - 2.0 * dn * nrm.x, d_main.y - 2.0 * dn * nrm.y, d_main.z - 2.0 * dn * nrm.z);
+                d = unit(r);
+                phase = PH_MAIN;                                      // origin o already is the surface point
+            } else {
+                if (COUNT) atomicAdd(&P.counters[CTR_BOUNCE_HIST0 + bounces], 1ull);
+                sample = sample * (1.0 / weight_sum);
+                average = average + sample;
+                k++;
+                new_sample = true;
+            }
+        }
+
+        average = average * (1.0 / TRT_RAYS_PER_PIXEL);               // TRT.c:1065
+        const size_t pix = (size_t)brow * (size_t)P.width + (size_t)col;
+        if (P.pixels) {
+            P.pixels[pix * 3 + 0] = average.x;
+            P.pixels[pix * 3 + 1] = average.y;
+            P.pixels[pix * 3 + 2] = average.z;
+        }
+        if (P.quant) {
+            // the quantisation of buffered_draw_screen, TRT.c:1157-1163: truncation toward zero
+            uchar4 q;
+            q.x = (unsigned char)x86_int(average.x * 255);
+            q.y = (unsigned char)x86_int(average.y * 255);
+            q.z = (unsigned char)x86_int(average.z * 255);
+            q.w = 0;
+            P.quant[pix] = q;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side of this TU: scene upload (constant memory lives here) and the launcher
+
+static void die(cudaError_t e, const char *file, int line)
+{
+    if (e != cudaSuccess) {
+        fprintf(stderr, "%s:%d: CUDA error: %s\n", file, line, cudaGetErrorString(e));
+        exit(1);
+    }
+}
+#define CK(x) die((x), __FILE__, __LINE__)
+
+void upload_scene_constants(const DevScene &scene, const double4 *geom, int count, cudaStream_t stream)
+{
+    CK(cudaMemcpyToSymbolAsync(c_scene, &scene, sizeof(DevScene), 0, cudaMemcpyHostToDevice, stream));
+    if (count > 0 && count <= TRT_MAX_CONST_SPHERES)
+        CK(cudaMemcpyToSymbolAsync(c_sphere_geom, geom, sizeof(double4) * (size_t)count, 0, cudaMemcpyHostToDevice, stream));
+}
+
+int render_ctas_per_sm()
+{
+    static int cached = 0;
+    if (!cached) {
+        int n = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_render<false, true>, CTA_THREADS, 0));
+        cached = n > 0 ? n : 1;
+    }
+    return cached;
+}
+
+void launch_render(const RenderParams &p, bool count, bool const_geom, int num_sms, cudaStream_t stream)
+{
+    CK(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), stream));
+    const int band_rows = p.row1 - p.row0;
+    if (band_rows <= 0 || p.width <= 0) return;
+    const long long tiles = (long long)((p.width + TILE_W - 1) / TILE_W) * ((band_rows + TILE_H - 1) / TILE_H);
+    long long want = (tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    long long grid = (long long)num_sms * render_ctas_per_sm();   // persistent: every CTA slot of the chip, once
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    dim3 g((unsigned)grid), b(CTA_THREADS);
+    if (count) {
+        if (const_geom) k_render<true, true><<<g, b, 0, stream>>>(p);
+        else k_render<true, false><<<g, b, 0, stream>>>(p);
+    } else {
+        if (const_geom) k_render<false, true><<<g, b, 0, stream>>>(p);
+        else k_render<false, false><<<g, b, 0, stream>>>(p);
+    }
+    CK(cudaGetLastError());
+}
+
+} // namespace trt
