@@ -44,6 +44,9 @@ void trt_shutdown(void);
 int trt_is_initialized(void);
 /* the library's CUDA stream as an opaque pointer (cudaStream_t), so plumbing code (torch) can order against it */
 void *trt_stream(void);
+/* Run all subsequent work on the caller's CUDA stream (a cudaStream_t; e.g. torch's current stream, so that
+ * the caller's events and collectives are ordered with the kernels).  NULL restores the library's own stream. */
+int trt_set_stream(void *cuda_stream);
 
 /* ---- skybox ingest (replaces the pointer chase through Scene.skybox, TRT.c:782-788) ----------- */
 /* Copies the six dim*dim RGB planes to the device (each padded with dim+1 black texels, see
@@ -95,6 +98,13 @@ int trt_stream_frame_device(char *d_stream, int width, int height);
 int trt_count_rows_device(int width, int height, int row0, int row1, double *d_pixels, long long *counters);
 /* F(frame) of SURVEY.md §8(d) from such a counter array */
 double trt_model_flops(const long long *counters);
+
+/* Unit-level probes for parity tests of single queries (host arrays in and out, synchronous):
+ * trace_ray (TRT.c:793) for n rays (6 doubles each: origin, direction) -> 11 doubles each:
+ * kind (0 none,1 sphere,2 ground), pushed-back point[3], unit normal[3], material colour[3], reflectivity;
+ * get_skybox_color (TRT.c:700) for n directions (3 doubles each) -> 5 ints each: face, texel index, r, g, b. */
+int trt_probe_trace_ray(const trt_Scene *scene, const double *rays, int n, double *out);
+int trt_probe_skybox(const double *dirs, int n, int *out);
 
 /* device memory helpers for plain-C callers (thin wrappers over cudaMalloc / cudaMemcpy) */
 void *trt_device_alloc(size_t bytes);

@@ -63,6 +63,7 @@ struct Context {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_render_ms = 0.f, last_encode_ms = 0.f;
     // scene
@@ -222,7 +223,8 @@ int trt_init(int device)
     CK(cudaSetDevice(device));
     g.device = device;
     CK(cudaDeviceGetAttribute(&g.num_sms, cudaDevAttrMultiProcessorCount, device));
-    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+    g.stream = g.own_stream;
     for (auto &ev : g.ev) CK(cudaEventCreate(&ev));
     g.tile_counter.reserve(256);
     g.counters.reserve(sizeof(unsigned long long) * TRT_NUM_COUNTERS);
@@ -247,8 +249,8 @@ void trt_shutdown(void)
         if (ev) cudaEventDestroy(ev);
         ev = nullptr;
     }
-    cudaStreamDestroy(g.stream);
-    g.stream = nullptr;
+    cudaStreamDestroy(g.own_stream);
+    g.stream = g.own_stream = nullptr;
     g.have_scene = false;
     g.sky_dim = -1;
     g.ready = false;
@@ -256,6 +258,14 @@ void trt_shutdown(void)
 
 int trt_is_initialized(void) { return g.ready ? 1 : 0; }
 void *trt_stream(void) { return (void *)g.stream; }
+
+int trt_set_stream(void *cuda_stream)
+{
+    require_init("trt_set_stream");
+    CK(cudaStreamSynchronize(g.stream));
+    g.stream = cuda_stream ? (cudaStream_t)cuda_stream : g.own_stream;
+    return 0;
+}
 
 int trt_upload_skybox(const trt_Skybox *skybox)
 {
@@ -349,6 +359,58 @@ double trt_model_flops(const long long *c)
            5.0 * c[CTR_PLANE_TESTS] + 9.0 * c[CTR_PLANE_DENOM_OK] + 14.0 * c[CTR_PLANE_T_POS] + 1.0 * c[CTR_PLANE_CLOSEST] +
            90.0 * c[CTR_SKY_LOOKUPS] + 27.0 * c[CTR_TRACE_HITS] + 55.0 * c[CTR_LIGHTING_CALLS] + 34.0 * c[CTR_BOUNCE_ITERS] +
            68.0 * c[CTR_SAMPLES] + 4.0 * c[CTR_PIXELS];
+}
+
+// ---- unit-level probes (parity tests of single queries) -------------------------------------------------
+
+int trt_probe_trace_ray(const trt_Scene *scene, const double *rays, int n, double *out)
+{
+    require_init("trt_probe_trace_ray");
+    upload_scene(scene);
+    if (n <= 0) return 0;
+    Buffer d_in, d_out;
+    d_in.reserve(sizeof(double) * 6 * (size_t)n);
+    d_out.reserve(sizeof(double) * 11 * (size_t)n);
+    CK(cudaMemcpyAsync(d_in.p, rays, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice, g.stream));
+    RenderParams p = make_params(1, 1, 0, 1, nullptr, nullptr, false);
+    launch_probe_trace(p, (const double *)d_in.p, n, (double *)d_out.p, g.stream);
+    CK(cudaMemcpyAsync(out, d_out.p, sizeof(double) * 11 * (size_t)n, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    d_in.release();
+    d_out.release();
+    return 0;
+}
+
+int trt_probe_skybox(const double *dirs, int n, int *out)
+{
+    require_init("trt_probe_skybox");
+    if (n <= 0) return 0;
+    if (!g.have_scene) {
+        // the sampler only needs the skybox fields of the constant block
+        memset(&g.scene, 0, sizeof g.scene);
+        g.scene.sky_dim = g.sky_dim;
+        g.scene.sky_face_stride = g.sky_face_stride;
+        g.scene.spheres_in_const = 1;
+        upload_scene_constants(g.scene, nullptr, 0, g.stream);
+        g.sphere_geom.reserve(sizeof(double4));
+        g.sphere_mat.reserve(sizeof(DevMaterial));
+        g.have_scene = true;
+    } else {
+        g.scene.sky_dim = g.sky_dim;
+        g.scene.sky_face_stride = g.sky_face_stride;
+        upload_scene_constants(g.scene, nullptr, 0, g.stream);
+    }
+    Buffer d_in, d_out;
+    d_in.reserve(sizeof(double) * 3 * (size_t)n);
+    d_out.reserve(sizeof(int) * 5 * (size_t)n);
+    CK(cudaMemcpyAsync(d_in.p, dirs, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, g.stream));
+    RenderParams p = make_params(1, 1, 0, 1, nullptr, nullptr, false);
+    launch_probe_sky(p, (const double *)d_in.p, n, (int *)d_out.p, g.stream);
+    CK(cudaMemcpyAsync(out, d_out.p, sizeof(int) * 5 * (size_t)n, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    d_in.release();
+    d_out.release();
+    return 0;
 }
 
 // ---- drop-ins ---------------------------------------------------------------------------------------

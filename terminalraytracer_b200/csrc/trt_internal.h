@@ -9,6 +9,8 @@ namespace trt {
 void upload_scene_constants(const DevScene &scene, const double4 *geom, int count, cudaStream_t stream);
 void launch_render(const RenderParams &p, bool count, bool const_geom, int num_sms, cudaStream_t stream);
 int render_ctas_per_sm();
+void launch_probe_trace(const RenderParams &p, const double *d_rays, int n, double *d_out, cudaStream_t stream);
+void launch_probe_sky(const RenderParams &p, const double *d_dirs, int n, int *d_out, cudaStream_t stream);
 
 // trt_encode.cu
 // Encode `rows` rows of `width` cells into out_base[byte_offset ...); source is either the FP64

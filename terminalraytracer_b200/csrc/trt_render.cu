@@ -396,6 +396,72 @@ __global__ void __launch_bounds__(CTA_THREADS) k_render(const RenderParams P)
     }
 }
 
+// ---- unit-level probe: trace_ray (TRT.c:793-889) for an array of rays, all out-params ---------------
+// Used by the parity tests to compare single queries (hit kind, pushed-back point, unit normal,
+// material incl. the skybox colour on a miss) with the reference, not only whole frames.
+// out: 11 doubles per ray = kind, point[3], normal[3], colour[3], reflectivity
+__global__ void k_probe_trace(const RenderParams P, const double *__restrict__ rays, int n, double *__restrict__ out)
+{
+    __shared__ double s_byte_to_unit[256];
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_byte_to_unit[k] = (double)k / 255.0;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const d3 o = mk3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]);
+    const d3 d = mk3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
+    const Tally<false> tally{nullptr};
+    int obj, index;
+    d3 hit;
+    if (c_scene.spheres_in_const) closest_hit<false, true>(P, o, d, obj, index, hit, tally);
+    else closest_hit<false, false>(P, o, d, obj, index, hit, tally);
+    d3 point, normal, colour;
+    double reflectivity = 0.0;
+    if (obj == 0) {
+        point = o;
+        normal = d;
+        int face;
+        const int texel = sky_texel_index(d, c_scene.sky_dim, face);
+        const uchar4 t = __ldg(&P.sky[(size_t)face * (size_t)c_scene.sky_face_stride + (size_t)texel]);
+        colour = mk3(s_byte_to_unit[t.x], s_byte_to_unit[t.y], s_byte_to_unit[t.z]);
+    } else {
+        const DevMaterial *m;
+        if (obj == 1) {
+            const double4 g = c_scene.spheres_in_const ? c_sphere_geom[index] : ldg_geom(P.sphere_geom, index);
+            normal = mk3(hit.x - g.x, hit.y - g.y, hit.z - g.z);
+            m = &P.sphere_mat[index];
+        } else {
+            normal = mk3(c_scene.ground_normal[0], c_scene.ground_normal[1], c_scene.ground_normal[2]);
+            m = index ? &c_scene.ground_odd : &c_scene.ground_even;
+        }
+        colour = mk3(m->color[0], m->color[1], m->color[2]);
+        reflectivity = m->reflectivity;
+        point = push_back(o, hit);
+    }
+    normal = unit(normal);
+    double *r = out + (size_t)i * 11;
+    r[0] = (double)obj;
+    r[1] = point.x; r[2] = point.y; r[3] = point.z;
+    r[4] = normal.x; r[5] = normal.y; r[6] = normal.z;
+    r[7] = colour.x; r[8] = colour.y; r[9] = colour.z;
+    r[10] = reflectivity;
+}
+
+// get_skybox_color (TRT.c:700-789) for an array of directions: face, texel index, r, g, b per entry
+__global__ void k_probe_sky(const RenderParams P, const double *__restrict__ dirs, int n, int *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const d3 d = mk3(dirs[i * 3 + 0], dirs[i * 3 + 1], dirs[i * 3 + 2]);
+    int face;
+    const int texel = sky_texel_index(d, c_scene.sky_dim, face);
+    const uchar4 t = __ldg(&P.sky[(size_t)face * (size_t)c_scene.sky_face_stride + (size_t)texel]);
+    out[i * 5 + 0] = face;
+    out[i * 5 + 1] = texel;
+    out[i * 5 + 2] = t.x;
+    out[i * 5 + 3] = t.y;
+    out[i * 5 + 4] = t.z;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // host side of this TU: scene upload (constant memory lives here) and the launcher
 
@@ -444,6 +510,20 @@ void launch_render(const RenderParams &p, bool count, bool const_geom, int num_s
         if (const_geom) k_render<false, true><<<g, b, 0, stream>>>(p);
         else k_render<false, false><<<g, b, 0, stream>>>(p);
     }
+    CK(cudaGetLastError());
+}
+
+void launch_probe_trace(const RenderParams &p, const double *d_rays, int n, double *d_out, cudaStream_t stream)
+{
+    if (n <= 0) return;
+    k_probe_trace<<<(n + 127) / 128, 128, 0, stream>>>(p, d_rays, n, d_out);
+    CK(cudaGetLastError());
+}
+
+void launch_probe_sky(const RenderParams &p, const double *d_dirs, int n, int *d_out, cudaStream_t stream)
+{
+    if (n <= 0) return;
+    k_probe_sky<<<(n + 127) / 128, 128, 0, stream>>>(p, d_dirs, n, d_out);
     CK(cudaGetLastError());
 }
 

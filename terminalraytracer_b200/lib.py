@@ -17,6 +17,7 @@ SIGNATURES = {
     "trt_shutdown": (None, []),
     "trt_is_initialized": (C.c_int, []),
     "trt_stream": (C.c_void_p, []),
+    "trt_set_stream": (C.c_int, [C.c_void_p]),
     "trt_upload_skybox": (C.c_int, [C.POINTER(abi.Skybox)]),
     "trt_project_scene": (None, [C.POINTER(abi.Scene), C.POINTER(abi.Screen)]),
     "trt_draw_screen": (C.c_size_t, [C.POINTER(abi.Screen), C.c_void_p]),
@@ -30,6 +31,8 @@ SIGNATURES = {
     "trt_stream_frame_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "trt_count_rows_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_longlong)]),
     "trt_model_flops": (C.c_double, [C.POINTER(C.c_longlong)]),
+    "trt_probe_trace_ray": (C.c_int, [C.POINTER(abi.Scene), C.c_void_p, C.c_int, C.c_void_p]),
+    "trt_probe_skybox": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "trt_device_alloc": (C.c_void_p, [C.c_size_t]),
     "trt_device_free": (None, [C.c_void_p]),
     "trt_host_alloc_pinned": (C.c_void_p, [C.c_size_t]),

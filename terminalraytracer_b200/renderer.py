@@ -88,6 +88,10 @@ class Renderer:
         self.L.trt_count_rows_device(width, height, row0, row1, d_pixels_ptr, ctr)
         return list(ctr), self.L.trt_model_flops(ctr)
 
+    def use_stream(self, cuda_stream_ptr):
+        """Run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); None = own stream."""
+        self.L.trt_set_stream(cuda_stream_ptr)
+
     def synchronize(self):
         self.L.trt_synchronize()
 

@@ -1,0 +1,145 @@
+"""Shared helpers for the test-suite: loading the checkers (oracle restatement, reference build) and
+calling them on the same ctypes structures the product receives.  Test infrastructure only."""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+
+from terminalraytracer_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libtrt_oracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libtrt_ref.so")
+REF_ROWS_SO = os.path.join(ROOT, "oracle", "_ref", "libtrt_ref_rows.so")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REFERENCE_DIR = "/root/reference"
+
+VP = C.c_void_p
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_longlong) for n in (
+        "sphere_tests", "sphere_disc_ok", "sphere_t0_pos", "sphere_closest", "plane_tests", "plane_denom_ok",
+        "plane_t_pos", "plane_closest", "sky_lookups", "trace_calls", "trace_hits", "lighting_calls",
+        "bounce_iters", "samples", "pixels")] + [("bounce_hist", C.c_longlong * (abi.BOUNCE_LIMIT + 1))]
+
+    def as_gpu_order(self):
+        """same order as CounterId in csrc/trt_device.cuh"""
+        head = [self.sphere_tests, self.sphere_disc_ok, self.sphere_t0_pos, self.sphere_closest, self.plane_tests,
+                self.plane_denom_ok, self.plane_t_pos, self.plane_closest, self.sky_lookups, self.trace_calls,
+                self.trace_hits, self.lighting_calls, self.bounce_iters, self.samples, self.pixels]
+        return head + list(self.bounce_hist)
+
+
+def build_oracle():
+    if not os.path.exists(ORACLE_SO):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    return ORACLE_SO
+
+
+def load_oracle():
+    lib = C.CDLL(build_oracle())
+    lib.orc_project_scene.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Screen)]
+    lib.orc_render_rows.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Screen), C.c_int, C.c_int, C.POINTER(Counters)]
+    lib.orc_encode_stream.argtypes = [C.POINTER(abi.Screen), VP]
+    lib.orc_encode_stream.restype = C.c_size_t
+    lib.orc_encode_rows.argtypes = [C.POINTER(abi.Screen), C.c_int, C.c_int, VP]
+    lib.orc_encode_rows.restype = C.c_size_t
+    lib.orc_stream_bytes.argtypes = [C.c_int, C.c_int]
+    lib.orc_stream_bytes.restype = C.c_size_t
+    lib.orc_hit_sphere.argtypes = [C.POINTER(abi.Ray), C.POINTER(abi.Sphere), C.POINTER(abi.Vector), VP]
+    lib.orc_hit_plane.argtypes = [C.POINTER(abi.Ray), C.POINTER(abi.Plane), C.POINTER(abi.Vector), VP]
+    lib.orc_sky_texel.argtypes = [C.POINTER(abi.Skybox), C.POINTER(abi.Vector), C.POINTER(abi.Color), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_long)]
+    lib.orc_closest_hit.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Ray), C.POINTER(abi.Vector), C.POINTER(abi.Vector),
+                                    C.POINTER(abi.Material), VP]
+    lib.orc_closest_hit.restype = C.c_int
+    lib.orc_light_surface.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Vector), C.POINTER(abi.Vector),
+                                      C.POINTER(abi.Material), VP]
+    lib.orc_subpixel_offsets.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.orc_model_flops.argtypes = [C.POINTER(Counters)]
+    lib.orc_model_flops.restype = C.c_double
+    lib.orc_sizeof_counters.restype = C.c_size_t
+    return lib
+
+
+def have_reference_build():
+    return os.path.exists(REF_SO)
+
+
+def load_reference(path=REF_SO):
+    lib = C.CDLL(path)
+    lib.project_scene.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Screen)]
+    lib.ref_orbit_camera.argtypes = [C.POINTER(abi.Camera), C.c_double]
+    lib.ref_subpixel_offsets.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.ref_draw_screen_bytes.argtypes = [C.POINTER(abi.Screen), VP, C.c_long]
+    lib.ref_draw_screen_bytes.restype = C.c_long
+    lib.ref_time_project_scene.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Screen)]
+    lib.ref_time_project_scene.restype = C.c_double
+    lib.ray_intersects_sphere.argtypes = [C.POINTER(abi.Ray), C.POINTER(abi.Sphere), C.POINTER(abi.Vector)]
+    lib.ray_intersects_plane.argtypes = [C.POINTER(abi.Ray), C.POINTER(abi.Plane), C.POINTER(abi.Vector)]
+    lib.get_skybox_color.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Vector), C.POINTER(abi.Color)]
+    lib.trace_ray.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Ray), C.POINTER(abi.Vector), C.POINTER(abi.Vector),
+                              C.POINTER(abi.Material)]
+    lib.trace_ray.restype = C.c_int
+    lib.apply_lighting.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Vector), C.POINTER(abi.Vector), C.POINTER(abi.Vector),
+                                   C.POINTER(abi.Material)]
+    lib.byte_to_digits.argtypes = [C.c_int, C.c_char_p]
+    for name in ("ref_sizeof_scene", "ref_sizeof_sphere", "ref_sizeof_plane", "ref_sizeof_camera", "ref_sizeof_skybox",
+                 "ref_sizeof_screen", "ref_offsetof_scene_camera", "ref_offsetof_scene_skybox", "ref_offsetof_scene_ground",
+                 "ref_offsetof_scene_point_lights", "ref_screenbuffer_bytes"):
+        getattr(lib, name).restype = C.c_size_t
+    return lib
+
+
+def screen_for(px):
+    h, w, _ = px.shape
+    return abi.Screen(px.ctypes.data_as(C.POINTER(abi.Vector)), w, h)
+
+
+def cpu_render(lib, fn_name, scene):
+    """Run a CPU checker's project_scene-like function on a SceneData; returns (H,W,3) float64."""
+    px = np.zeros((scene.height, scene.width, 3), dtype=np.float64)
+    scr = screen_for(px)
+    getattr(lib, fn_name)(C.byref(scene.c), C.byref(scr))
+    return px
+
+
+def oracle_rows(orc, scene, row0, row1, counters=None):
+    px = np.zeros((scene.height, scene.width, 3), dtype=np.float64)
+    scr = screen_for(px)
+    orc.orc_render_rows(C.byref(scene.c), C.byref(scr), row0, row1, C.byref(counters) if counters is not None else None)
+    return px[row0:row1]
+
+
+def oracle_stream(orc, px):
+    h, w, _ = px.shape
+    px = np.ascontiguousarray(px, dtype=np.float64)
+    out = np.zeros(abi.stream_bytes(w, h), dtype=np.uint8)
+    n = orc.orc_encode_stream(C.byref(screen_for(px)), VP(out.ctypes.data))
+    assert n == out.size
+    return out
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def hash_uniform(shape, seed, lo=0.0, hi=1.0):
+    """Deterministic uniform doubles from splitmix64 (integer arithmetic only, so fixtures regenerate
+    identically on any numpy version)."""
+    from terminalraytracer_b200.scene import _splitmix64
+    n = int(np.prod(shape))
+    with np.errstate(over="ignore"):
+        z = _splitmix64(np.arange(n, dtype=np.uint64) + (np.uint64(seed) << np.uint64(32)))
+    u = (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return (lo + u * (hi - lo)).reshape(shape)
+
+
+def random_encoder_pixels():
+    """The 480x280 input of the 'random pixels' encoder golden (values outside [0,1] included)."""
+    px = hash_uniform((280, 480, 3), 77, -0.2, 1.3)
+    px[0, :16, 0] = np.arange(16) / 255.0
+    return px

@@ -1,0 +1,173 @@
+"""Host-side logic of the product (no GPU): ABI surface, scene fixtures, camera recipe, PPM ingest,
+sharding.  The camera/scene helpers are compared with the reference's own functions through the
+golden vectors (and live when the reference build is present)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from terminalraytracer_b200 import abi, lib as trtlib, scene as S, sharding
+from tests import _util as U
+
+
+def header_symbols():
+    text = open(os.path.join(U.ROOT, "include", "trt_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(trt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(trt):
+    declared = header_symbols()
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(trt, name), f"{name} declared in include/trt_b200.h but not exported"
+    # and the Python binding types exactly the declared set
+    assert sorted(trtlib.SIGNATURES) == declared
+
+
+def test_library_is_not_initialised_without_a_gpu_call(trt):
+    assert trt.trt_is_initialized() in (0, 1)
+
+
+def test_camera_recipe_matches_reference_golden(trt):
+    units = np.load(os.path.join(U.GOLDEN, "units.npz"))
+    for t, want in zip(units["camera_t"], units["camera_frame"]):
+        cam = abi.Camera()
+        trt.trt_init_camera(C.byref(cam), 480, 280)
+        trt.trt_orbit_camera(C.byref(cam), float(t))
+        got = np.frombuffer(bytes(cam.frame), dtype=np.float64)
+        assert np.array_equal(got, want), t
+    dx = (C.c_double * 10)()
+    dy = (C.c_double * 10)()
+    trt.trt_subpixel_offsets(dx, dy)
+    assert list(dx) == list(units["sub_dx"]) and list(dy) == list(units["sub_dy"])
+
+
+def test_camera_recipe_matches_reference_live(trt, ref):
+    for t in np.linspace(0, 40, 37):
+        a, b = abi.Camera(), abi.Camera()
+        trt.trt_init_camera(C.byref(a), 480, 280)
+        trt.trt_init_camera(C.byref(b), 480, 280)
+        trt.trt_orbit_camera(C.byref(a), float(t))
+        ref.ref_orbit_camera(C.byref(b), float(t))
+        assert bytes(a) == bytes(b)
+    cam = abi.Camera()
+    ref.init_camera(C.byref(cam))
+    mine = abi.Camera()
+    trt.trt_init_camera(C.byref(mine), 480, 280)
+    assert bytes(cam) == bytes(mine)
+
+
+def test_demo_scene_literals(trt):
+    """TRT.c:1256-1306"""
+    sc = S.SceneData(480, 280, S.synthetic_cubemap("colors", 8))
+    c = sc.c
+    assert c.num_spheres == 6 and c.num_directional_lights == 1 and c.num_point_lights == 1
+    centres = [c.spheres[i].center.tup() for i in range(6)]
+    assert centres == [(1, 0, 0), (0, 1, 0), (0, 0, 1), (-1, 0, 0), (0, -1, 0), (0, 0, -1)]
+    assert [c.spheres[i].radius for i in range(6)] == [0.5] * 6
+    assert [c.spheres[i].material.reflectivity for i in range(6)] == [1.0, 0.8, 0.8, 0.8, 0.8, 0.8]
+    assert [c.spheres[i].material.color.tup() for i in range(6)] == [(1, 0, 0), (0, 1, 0), (0, 0, 1), (0, 1, 1), (1, 0, 1), (1, 1, 0)]
+    assert c.ground.point.tup() == (0, -2, 0) and c.ground.normal.tup() == (0, 1, 0)
+    assert c.ground.even_material.color.tup() == (1, 1, 1) and c.ground.odd_material.color.tup() == (1, 0, 0)
+    assert c.ground.even_material.reflectivity == 0.2 == c.ground.odd_material.reflectivity
+    assert c.directional_lights[0].direction.tup() == (-1, -1, -1)
+    assert c.point_lights[0].position.tup() == (0, 0, 0) and c.point_lights[0].intensity == 10.0
+    assert c.camera.screen_distance == 1.0 and c.camera.screen_height == 5.0
+    assert c.camera.screen_width == 5 * 480.0 / 280.0
+
+
+def test_stress_scene_is_deterministic_and_clear_of_the_orbit(trt):
+    a = S.SceneData(64, 36, S.synthetic_cubemap("colors", 8), kind="stress", num_spheres=1024)
+    b = S.SceneData(64, 36, S.synthetic_cubemap("colors", 8), kind="stress", num_spheres=1024)
+    assert bytes(a.spheres) == bytes(b.spheres)
+    refl = set()
+    for i in range(1024):
+        s = a.spheres[i]
+        d = np.linalg.norm(s.center.tup())
+        assert not (1.99 - s.radius - 0.05 < d < 1.99 + s.radius + 0.05)
+        assert 0.1 <= s.radius <= 0.5
+        refl.add(s.material.reflectivity)
+    assert refl == {0.0, 0.2, 0.8, 1.0}
+
+
+def test_ppm_reader_matches_c_loader_and_grammar(trt, tmp_path):
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (5, 5, 3), dtype=np.uint8)
+    d = tmp_path / "sky"
+    d.mkdir()
+    for i, name in enumerate(S.FACE_FILES):
+        with open(d / name, "wb") as f:
+            # GIMP-style header with a comment line, as in the reference's assets
+            f.write(b"P6\n# Created by GIMP version 2.10.24 PNM plug-in\n5 5\n255\n")
+            f.write(((img.astype(int) + i) % 256).astype(np.uint8).tobytes())
+    sky_py = S.load_skybox_dir(str(d))
+    sky_c = abi.Skybox()
+    trt.trt_load_skybox_dir(C.byref(sky_c), str(d).encode())
+    assert sky_c.dim == 5 == sky_py.dim
+    for f in range(6):
+        got = np.ctypeslib.as_array(C.cast(sky_c.colors[f], C.POINTER(C.c_ubyte)), shape=((25 + 6) * 3,))
+        assert np.array_equal(got[:75].reshape(5, 5, 3), sky_py.face(f))
+        assert not got[75:].any()  # dim+1 black pad texels
+    trt.trt_free_skybox(C.byref(sky_c))
+    assert sky_c.dim == -1
+
+
+def test_reference_assets_load_identically(trt):
+    d = os.path.join(U.REFERENCE_DIR, "skybox", "colors")
+    if not os.path.isdir(d):
+        pytest.skip("reference assets not present")
+    real = S.load_skybox_dir(d)
+    synth = S.synthetic_cubemap("colors", 256)
+    for f in range(6):
+        assert np.array_equal(real.face(f), synth.face(f))  # the synthetic stand-in IS the reference card
+
+
+def test_row_bands_cover_every_row_once():
+    for h in (1, 7, 280, 2160, 4320):
+        for n in (1, 2, 3, 4, 8):
+            bands = sharding.row_bands(h, n)
+            assert bands[0][0] == 0 and bands[-1][1] == h and len(bands) == n
+            for (a0, a1), (b0, b1) in zip(bands, bands[1:]):
+                assert a1 == b0 and a0 <= a1
+    assert sharding.row_bands(4320, 8) == [(i * 540, (i + 1) * 540) for i in range(8)]
+    assert sharding.row_bands(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+
+
+def test_weighted_row_bands_balance_cost():
+    w = [1.0] * 100 + [5.0] * 100
+    bands = sharding.row_bands(200, 4, w)
+    assert bands[0][0] == 0 and bands[-1][1] == 200
+    costs = [sum(w[a:b]) for a, b in bands]
+    assert max(costs) - min(costs) <= 10.0
+    for (a0, a1), (b0, b1) in zip(bands, bands[1:]):
+        assert a1 == b0
+
+
+def test_band_byte_ranges_tile_the_stream():
+    w, h = 37, 23
+    bands = sharding.row_bands(h, 5)
+    pos = abi.HOME_BYTES
+    for b in bands:
+        b0, b1 = sharding.band_byte_range(w, b)
+        assert b0 == pos
+        pos = b1
+    assert pos + abi.TAIL_NULS == abi.stream_bytes(w, h)
+
+
+def test_frame_sharding():
+    assert sharding.frames_for_rank(10, 1, 4) == [1, 5, 9]
+    assert sorted(sum((sharding.frames_for_rank(360, r, 8) for r in range(8)), [])) == list(range(360))
+    ts = sharding.orbit_times(360)
+    assert ts[0] == 0.0 and abs(ts[-1] - (20.0 - 20.0 / 360)) < 1e-12
+
+
+def test_synthetic_skyboxes_are_deterministic():
+    a = S.synthetic_cubemap("milky_way", 64)
+    b = S.synthetic_cubemap("milky_way", 64)
+    for f in range(6):
+        assert np.array_equal(a.face(f), b.face(f))
+    stars = sum(int((a.face(f).max(axis=2) > 50).sum()) for f in range(6))
+    assert 0.001 < stars / (6 * 64 * 64) < 0.01
