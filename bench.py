@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the render path (BASELINE.json: Mrays/s on the default demo scene
+at 7680x4320, reference bounce depth, milky_way skybox, row-band sharded over 1/2/4/8 GPUs).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one frame through the hot path: K1 (render band, persistent FP64 kernel) -> K2 (ANSI
+encode) -> gather of the byte bands on rank 0.  Prints ONE JSON line on rank 0.
+
+  value      Mrays/s = 10*W*H*K / seconds (primary samples; TRT.c:58 RAYS_PER_PIXEL = 10), scene and
+             skybox resident in HBM, device-timed (CUDA events), max over ranks.
+  e2e        same metric through the C-ABI call a host program makes (trt_render_ansi at N=1: scene
+             upload H2D, K1, K2, D2H of the byte stream into pinned host memory — all inside the timing).
+  roofline   K1 against the FP32 CUDA-core peak (the path has no dense contraction and ~400 flop/byte,
+             SURVEY.md §8d): achieved = algorithmic flops of the frame (work counters x the as-written
+             per-event flop costs, counted by the kernel itself in a separate untimed launch and
+             cross-checked against the oracle's counters in tests) / K1's CUDA-event time.
+             peak = FFMA throughput measured on this GPU by libtrt_b200 (MEASURED_PEAKS.json has no
+             CUDA-core figure).  The encoder's HBM roofline is reported beside it.
+  cpu_baseline  the UNMODIFIED reference project_scene (oracle/_ref, built from /root/reference by
+             oracle/Makefile) on one host core, on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT, SKYBOX, T_POSE = 7680, 4320, "milky_way", 3.7
+CPU_SAMPLE_W, CPU_SAMPLE_H = 480, 270   # same 16:9 framing, 1/256 of the pixels
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": f"default demo scene (6 spheres + checker ground + 1 directional + 1 point light), {WIDTH}x{HEIGHT} cells, "
+                    f"10 samples/pixel, bounce limit 10, skybox {SKYBOX} (synthetic 1024^2 x 6 stand-in: the reference's "
+                    f"milky_way assets are not in its checkout), orbit pose t={T_POSE}s",
+        "width": WIDTH, "height": HEIGHT, "samples_per_pixel": 10, "bounce_limit": 10, "skybox": SKYBOX,
+        "sharding": f"row-bands x{n_gpus}" if n_gpus > 1 else "single GPU",
+        "l2": "no explicit flush: each step writes 133 MB of cells + 829 MB of stream (> 126 MB L2); inputs (scene 1 KB, "
+              "skybox 25 MB) are meant to stay cache resident, the kernel is ALU-bound",
+    }
+
+
+# --------------------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); power.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------------
+# CPU reference timing (the only place bench.py executes anything under oracle/)
+
+def time_reference_cpu(width, height, repeats):
+    """project_scene of the unmodified reference (oracle/_ref) — or of the oracle port when the reference
+    build is absent — on ONE host thread (the reference is single-threaded as written)."""
+    import numpy as np
+    from terminalraytracer_b200 import abi, scene as S
+    from tests import _util as U
+    if U.have_reference_build():
+        lib, fn, kind = U.load_reference(), "project_scene", "reference"
+    else:
+        lib, fn, kind = U.load_oracle(), "orc_project_scene", "port"
+    sky = S.get_skybox(SKYBOX)
+    sc = S.SceneData(width, height, sky).set_time(T_POSE)
+    px = np.zeros((height, width, 3))
+    scr = abi.Screen(px.ctypes.data_as(C.POINTER(abi.Vector)), width, height)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        getattr(lib, fn)(C.byref(sc.c), C.byref(scr))
+        times.append(time.perf_counter() - t0)
+    return kind, times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    kind, times = time_reference_cpu(CPU_SAMPLE_W, CPU_SAMPLE_H, args.warmup + args.steps)
+    timed = times[args.warmup:]
+    total = sum(timed)
+    rays = 10.0 * CPU_SAMPLE_W * CPU_SAMPLE_H * len(timed)
+    value = rays / total / 1e6
+    sample = (f"{len(timed)} frames of the same scene, pose and skybox at {CPU_SAMPLE_W}x{CPU_SAMPLE_H} "
+              f"(1/256 of the pixels of the {WIDTH}x{HEIGHT} workload; cost per ray is resolution independent), "
+              f"1 thread as written, {'unmodified reference TU' if kind == 'reference' else 'oracle port'} built -O3 -ffp-contract=off")
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": 1, "kind": kind, "sample": sample,
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--width", type=int, default=WIDTH)
+    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from terminalraytracer_b200 import abi, pipeline, renderer as R, scene as S
+
+    width, height = args.width, args.height
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rd = R.Renderer(local_rank)
+    sky = S.get_skybox(SKYBOX)
+    rd.upload_skybox(sky)
+    sc = S.SceneData(width, height, sky).set_time(T_POSE)
+    pipe = pipeline.FramePipeline(rd, width, height, rank, world)
+    stream = torch.cuda.current_stream()
+    rows = pipe.row1 - pipe.row0
+
+    # ---- algorithmic flops of this rank's band (untimed counting launch of the same kernel) ------------
+    rd.set_scene(sc)
+    counters, band_flops = rd.count_rows(width, height, pipe.row0, pipe.row1)
+    peaks = rd.measure_peaks() if rank == 0 else None
+
+    # ---- device-resident steps ------------------------------------------------------------------------
+    k1_events = []
+
+    def step():
+        rd.set_scene(sc)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        if rows > 0:
+            rd.render_rows_quant(width, height, pipe.row0, pipe.row1, pipe.quant.data_ptr())
+        e1.record(stream)
+        k1_events.append((e0, e1))
+        if rank == 0:
+            rd.stream_frame(pipe.stream.data_ptr(), width, height)
+            if rows > 0:
+                rd.encode_rows_quant(pipe.quant.data_ptr(), width, rows, pipe.stream.data_ptr(), abi.HOME_BYTES)
+        elif rows > 0:
+            rd.encode_rows_quant(pipe.quant.data_ptr(), width, rows, pipe.band_bytes.data_ptr(), 0)
+        pipe.gather()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    k1_events.clear()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record(stream)
+    for _ in range(args.steps):
+        step()
+    t_end.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = t_begin.elapsed_time(t_end)
+    k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / max(len(k1_events), 1)
+
+    # encoder alone (rank 0's band), for its HBM roofline
+    enc_ms = None
+    if rank == 0 and rows > 0:
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(stream)
+        for _ in range(5):
+            rd.encode_rows_quant(pipe.quant.data_ptr(), width, rows, pipe.stream.data_ptr(), abi.HOME_BYTES)
+        eb.record(stream)
+        torch.cuda.synchronize()
+        enc_ms = ea.elapsed_time(eb) / 5
+
+    # ---- end-to-end steps through the host-facing call ----------------------------------------------------
+    total_bytes = abi.stream_bytes(width, height)
+    scene_bytes = C.sizeof(abi.Scene) + C.sizeof(abi.Sphere) * sc.c.num_spheres + C.sizeof(abi.DirectionalLight) + C.sizeof(abi.PointLight)
+    host_out = torch.empty(total_bytes, dtype=torch.uint8).pin_memory() if (rank == 0 and world > 1) else None
+
+    def e2e_step():
+        if world == 1:
+            rd.render_ansi(sc)       # trt_render_ansi: H2D scene, K1, K2, D2H stream into pinned memory, sync
+        else:
+            out = pipe.render(sc)    # set_scene (H2D) + K1 + K2 + NCCL gather
+            if rank == 0:
+                host_out.copy_(out, non_blocking=True)
+            torch.cuda.synchronize()
+
+    if world == 1:
+        rd.use_stream(None)          # the plain C-ABI call runs on the library's own stream
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - w0
+
+    # ---- reduce over ranks ------------------------------------------------------------------------------------
+    stats = torch.tensor([ms_total, k1_ms, e2e_s * 1e3, band_flops], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total, k1_ms_max, e2e_ms_total = mx[0].item(), mx[1].item(), mx[2].item()
+        frame_flops = sm[3].item()
+    else:
+        k1_ms_max, e2e_ms_total, frame_flops = k1_ms, e2e_s * 1e3, band_flops
+
+    if rank == 0:
+        rays_per_step = 10.0 * width * height
+        value = rays_per_step * args.steps / (ms_total * 1e-3) / 1e6
+        e2e_value = rays_per_step * args.steps / (e2e_ms_total * 1e-3) / 1e6
+        peak32, peak64 = peaks["fp32_tflops"], peaks["fp64_tflops"]
+        # dominant kernel = K1 on the slowest rank; its algorithmic flops = that launch's band.  With equal-cost
+        # accounting across ranks use frame flops / N over the max K1 time (conservative for the roofline).
+        achieved = (frame_flops / world) / (k1_ms_max * 1e-3) / 1e12
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                hbm_peak = json.load(f)["hbm_gbs"]
+            hbm_src = "MEASURED_PEAKS.json hbm_gbs"
+        except (OSError, KeyError, ValueError):
+            hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+            "frames_per_s": args.steps / (ms_total * 1e-3),
+            "roofline": {
+                "bound": "alu-fp32", "achieved": achieved, "peak": peak32, "unit": "TFLOP/s", "frac": achieved / peak32,
+                "traffic": None,
+                "kernel": "k_render (K1)", "kernel_ms": k1_ms_max,
+                "algorithmic_flops_per_launch": frame_flops / world, "flops_per_primary_ray": frame_flops / rays_per_step,
+                "peak_source": "FFMA loop measured in this run by libtrt_b200 (trt_measure_fp32_tflops); MEASURED_PEAKS.json "
+                               "has no CUDA-core peak. The kernel executes FP64 (bit-exact parity), whose measured DFMA peak is "
+                               f"{peak64:.2f} TFLOP/s",
+                "frac_of_fp64_peak": achieved / peak64, "fp64_peak": peak64,
+            },
+            "roofline_encode": None if enc_ms is None else {
+                "bound": "hbm", "achieved": (4.0 * width * rows + abi.row_bytes(width) * rows) / (enc_ms * 1e-3) / 1e9,
+                "peak": hbm_peak, "unit": "GB/s", "kernel": "k_encode (K2)", "kernel_ms": enc_ms, "peak_source": hbm_src,
+                "frac": (4.0 * width * rows + abi.row_bytes(width) * rows) / (enc_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(total_bytes),
+                    "ms_per_step": e2e_ms_total / args.steps,
+                    "call": "trt_render_ansi(scene,w,h,pinned_out,cap)" if world == 1 else "FramePipeline.render + D2H of the gathered stream"},
+            "gpu_launches": int(args.steps * (3 + 2 * (world - 1))),
+            "clocks": clocks,
+            "work_counters_rank0": {"trace_calls": counters[9], "sphere_tests": counters[0], "sky_lookups": counters[8],
+                                    "bounce_iters": counters[12], "lighting_calls": counters[11]},
+        }
+        if not args.no_cpu_baseline:
+            kind, times = time_reference_cpu(CPU_SAMPLE_W, CPU_SAMPLE_H, 12)
+            best = min(times[1:])
+            mean = sum(times[1:]) / len(times[1:])
+            line["cpu_baseline"] = {
+                "value": 10.0 * CPU_SAMPLE_W * CPU_SAMPLE_H / mean / 1e6, "unit": "Mrays/s", "cores": 1, "kind": kind,
+                "best_value": 10.0 * CPU_SAMPLE_W * CPU_SAMPLE_H / best / 1e6, "host_cores_available": os.cpu_count(),
+                "sample": f"11 timed frames of the same scene, pose and skybox at {CPU_SAMPLE_W}x{CPU_SAMPLE_H} (1/256 of the pixels), "
+                          f"single thread as the reference is written, gcc -O3 -ffp-contract=off"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    rd.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
