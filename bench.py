@@ -58,11 +58,18 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -72,7 +79,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if not self.proc:
@@ -83,8 +90,8 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
-        for r in self.rows:
-            if len(r) < 7:
+        for stamp, r in self.rows:
+            if len(r) < 7 or (self.t0 and stamp < self.t0) or (self.t1 and stamp > self.t1 + 0.05):
                 continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1])); power.append(float(r[2]))
@@ -153,7 +160,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--width", type=int, default=WIDTH)
@@ -218,20 +225,22 @@ def main():
             rd.encode_rows_quant(pipe.quant.data_ptr(), width, rows, pipe.band_bytes.data_ptr(), 0)
         pipe.gather()
 
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # nvidia-smi takes a while to start: launch it before the warm-up,
+    for _ in range(args.warmup):  # keep only the samples that fall inside the timed region
         step()
     barrier()
     k1_events.clear()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     t_begin.record(stream)
     for _ in range(args.steps):
         step()
     t_end.record(stream)
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = t_begin.elapsed_time(t_end)
     k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / max(len(k1_events), 1)

@@ -45,8 +45,16 @@ int trt_is_initialized(void);
 /* the library's CUDA stream as an opaque pointer (cudaStream_t), so plumbing code (torch) can order against it */
 void *trt_stream(void);
 /* Run all subsequent work on the caller's CUDA stream (a cudaStream_t; e.g. torch's current stream, so that
- * the caller's events and collectives are ordered with the kernels).  NULL restores the library's own stream. */
+ * the caller's events and collectives are ordered with the kernels).  NULL means the legacy default stream,
+ * which is what torch uses unless told otherwise.  trt_use_own_stream() goes back to the library's stream. */
 int trt_set_stream(void *cuda_stream);
+int trt_use_own_stream(void);
+
+/* The render kernel skips the FP64 sphere test whenever a conservative FP32 test certifies the
+ * reference's `discriminant < 0` outcome (DESIGN.md "FP32 cull"; results are bit-identical either way).
+ * trt_set_cull(0) forces the all-FP64 path — for A/B measurements and for the parity tests of that path.
+ * Takes effect at the next scene upload. */
+int trt_set_cull(int enabled);
 
 /* ---- skybox ingest (replaces the pointer chase through Scene.skybox, TRT.c:782-788) ----------- */
 /* Copies the six dim*dim RGB planes to the device (each padded with dim+1 black texels, see
@@ -105,6 +113,11 @@ double trt_model_flops(const long long *counters);
  * get_skybox_color (TRT.c:700) for n directions (3 doubles each) -> 5 ints each: face, texel index, r, g, b. */
 int trt_probe_trace_ray(const trt_Scene *scene, const double *rays, int n, double *out);
 int trt_probe_skybox(const double *dirs, int n, int *out);
+
+/* Self-test of the shared-reciprocal division used by the normalisations (csrc/trt_device.cuh): evaluates
+ * about `quotients` random and adversarial a/b on the GPU both ways and returns how many differ from the
+ * IEEE-754 division in any bit (must be 0). */
+long long trt_selftest_division(unsigned long long seed, long long quotients);
 
 /* device memory helpers for plain-C callers (thin wrappers over cudaMalloc / cudaMemcpy) */
 void *trt_device_alloc(size_t bytes);

@@ -69,8 +69,9 @@ struct Context {
     // scene
     DevScene scene;
     bool have_scene = false;
-    bool const_geom = true;
-    Buffer sphere_geom, sphere_mat;
+    bool cull_allowed = true;   // trt_set_cull(); the FP32 miss test can be switched off for A/B runs
+    bool cull = true;           // cull_allowed && this scene's magnitudes are inside the bound's range
+    Buffer sphere_geom, sphere_cull, sphere_mat;
     // skybox
     Buffer sky;
     int sky_dim = -1, sky_face_stride = 0;
@@ -106,6 +107,14 @@ void negated_unit(const trt_Vector &dir, double out[3])
         out[1] = y;
         out[2] = z;
     }
+}
+
+// smallest float >= v
+float float_round_up(double v)
+{
+    float f = (float)v;
+    if ((double)f < v) f = nextafterf(f, INFINITY);
+    return f;
 }
 
 void set_material(DevMaterial &m, const trt_Material &src)
@@ -151,8 +160,7 @@ void upload_scene(const trt_Scene *scene)
         s.point[i].intensity = p.intensity;
     }
     s.num_spheres = scene->num_spheres;
-    g.const_geom = s.num_spheres <= TRT_MAX_CONST_SPHERES;
-    s.spheres_in_const = g.const_geom ? 1 : 0;
+    s.filter_in_const = s.num_spheres <= TRT_MAX_CONST_SPHERES ? 1 : 0;
     s.sky_dim = g.sky_dim;
     s.sky_face_stride = g.sky_face_stride;
     trt_subpixel_offsets(s.sub_dx, s.sub_dy);
@@ -160,19 +168,34 @@ void upload_scene(const trt_Scene *scene)
     const int n = s.num_spheres;
     std::vector<double4> geom((size_t)(n > 0 ? n : 1));
     std::vector<DevMaterial> mats((size_t)(n > 0 ? n : 1));
+    std::vector<float4> cull((size_t)(n > 0 ? n : 1));
+    bool in_range = true;       // magnitudes for which the FP32 cull's error bound was derived
+    double centre_l1 = 0.0;
     for (int i = 0; i < n; i++) {
         const trt_Sphere &sp = scene->spheres[i];
         volatile double r2 = sp.radius * sp.radius;   // TRT.c:648, a single rounded product
         geom[i] = make_double4(sp.center.x, sp.center.y, sp.center.z, r2);
         set_material(mats[i], sp.material);
+        // FP32 cull record: centre rounded to nearest, radius padded and rounded UP (trt_render.cu, sphere_cull)
+        const double l1 = fabs(sp.center.x) + fabs(sp.center.y) + fabs(sp.center.z);
+        const double r = sqrt((double)r2);
+        if (!(l1 < 1e12) || !(r < 1e12) || (r != 0.0 && !(r > 1e-12))) in_range = false;
+        if (l1 > centre_l1) centre_l1 = l1;
+        cull[i] = make_float4((float)sp.center.x, (float)sp.center.y, (float)sp.center.z,
+                              float_round_up(r * (1.0 + 1.0 / 1048576.0)));
     }
+    g.cull = g.cull_allowed && in_range;
+    s.filter_enabled = g.cull ? 1 : 0;
+    s.filter_centre_l1 = float_round_up(centre_l1 * (1.0 + 1.0 / 1048576.0));
     g.sphere_geom.reserve(sizeof(double4) * geom.size());
     g.sphere_mat.reserve(sizeof(DevMaterial) * mats.size());
+    g.sphere_cull.reserve(sizeof(float4) * cull.size());
+    CK(cudaMemcpyAsync(g.sphere_cull.p, cull.data(), sizeof(float4) * cull.size(), cudaMemcpyHostToDevice, g.stream));
     // The vectors above die at the end of this function, so these copies must complete before it
     // returns: plain (staged) cudaMemcpyAsync from pageable memory is synchronous w.r.t. the host buffer.
     CK(cudaMemcpyAsync(g.sphere_geom.p, geom.data(), sizeof(double4) * geom.size(), cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(g.sphere_mat.p, mats.data(), sizeof(DevMaterial) * mats.size(), cudaMemcpyHostToDevice, g.stream));
-    upload_scene_constants(s, geom.data(), n, g.stream);
+    upload_scene_constants(s, cull.data(), n, g.stream);
     CK(cudaStreamSynchronize(g.stream));
     g.have_scene = true;
 }
@@ -195,6 +218,7 @@ RenderParams make_params(int width, int height, int row0, int row1, double *d_pi
     p.pixels = d_pixels;
     p.quant = d_quant;
     p.sphere_geom = (const double4 *)g.sphere_geom.p;
+    p.sphere_cull = (const float4 *)g.sphere_cull.p;
     p.sphere_mat = (const DevMaterial *)g.sphere_mat.p;
     p.sky = (const uchar4 *)g.sky.p;
     p.tile_counter = (unsigned int *)g.tile_counter.p;
@@ -237,6 +261,7 @@ void trt_shutdown(void)
     if (!g.ready) return;
     cudaStreamSynchronize(g.stream);
     g.sphere_geom.release();
+    g.sphere_cull.release();
     g.sphere_mat.release();
     g.sky.release();
     g.tile_counter.release();
@@ -263,7 +288,21 @@ int trt_set_stream(void *cuda_stream)
 {
     require_init("trt_set_stream");
     CK(cudaStreamSynchronize(g.stream));
-    g.stream = cuda_stream ? (cudaStream_t)cuda_stream : g.own_stream;
+    g.stream = (cudaStream_t)cuda_stream;   // NULL is a valid handle: the legacy default stream
+    return 0;
+}
+
+int trt_set_cull(int enabled)
+{
+    g.cull_allowed = enabled != 0;
+    return 0;
+}
+
+int trt_use_own_stream(void)
+{
+    require_init("trt_use_own_stream");
+    CK(cudaStreamSynchronize(g.stream));
+    g.stream = g.own_stream;
     return 0;
 }
 
@@ -308,7 +347,7 @@ int trt_render_rows_device(int width, int height, int row0, int row1, double *d_
 {
     require_init("trt_render_rows_device");
     RenderParams p = make_params(width, height, row0, row1, d_pixels, nullptr, false);
-    launch_render(p, false, g.const_geom, g.num_sms, g.stream);
+    launch_render(p, false, g.cull, g.num_sms, g.stream);
     return 0;
 }
 
@@ -316,7 +355,7 @@ int trt_render_rows_quant_device(int width, int height, int row0, int row1, unsi
 {
     require_init("trt_render_rows_quant_device");
     RenderParams p = make_params(width, height, row0, row1, nullptr, (uchar4 *)d_quant, false);
-    launch_render(p, false, g.const_geom, g.num_sms, g.stream);
+    launch_render(p, false, g.cull, g.num_sms, g.stream);
     return 0;
 }
 
@@ -346,7 +385,7 @@ int trt_count_rows_device(int width, int height, int row0, int row1, double *d_p
     require_init("trt_count_rows_device");
     CK(cudaMemsetAsync(g.counters.p, 0, sizeof(unsigned long long) * TRT_NUM_COUNTERS, g.stream));
     RenderParams p = make_params(width, height, row0, row1, d_pixels, nullptr, true);
-    launch_render(p, true, g.const_geom, g.num_sms, g.stream);
+    launch_render(p, true, g.cull, g.num_sms, g.stream);
     CK(cudaMemcpyAsync(counters, g.counters.p, sizeof(unsigned long long) * TRT_NUM_COUNTERS, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     return 0;
@@ -390,9 +429,10 @@ int trt_probe_skybox(const double *dirs, int n, int *out)
         memset(&g.scene, 0, sizeof g.scene);
         g.scene.sky_dim = g.sky_dim;
         g.scene.sky_face_stride = g.sky_face_stride;
-        g.scene.spheres_in_const = 1;
+        g.scene.filter_in_const = 1;
         upload_scene_constants(g.scene, nullptr, 0, g.stream);
         g.sphere_geom.reserve(sizeof(double4));
+        g.sphere_cull.reserve(sizeof(float4));
         g.sphere_mat.reserve(sizeof(DevMaterial));
         g.have_scene = true;
     } else {
@@ -413,6 +453,17 @@ int trt_probe_skybox(const double *dirs, int n, int *out)
     return 0;
 }
 
+long long trt_selftest_division(unsigned long long seed, long long quotients)
+{
+    require_init("trt_selftest_division");
+    // 3 quotients per iteration, 256 threads per CTA
+    const int iters = 4096;
+    long long ctas = quotients / (3LL * 256 * iters);
+    if (ctas < 1) ctas = 1;
+    if (ctas > 1 << 20) ctas = 1 << 20;
+    return (long long)run_selftest_division(seed, (int)ctas, iters, (unsigned long long *)g.counters.p, g.stream);
+}
+
 // ---- drop-ins ---------------------------------------------------------------------------------------
 
 void trt_project_scene(const trt_Scene *scene, trt_Screen *screen)
@@ -425,7 +476,7 @@ void trt_project_scene(const trt_Scene *scene, trt_Screen *screen)
     g.pixels.reserve(bytes);
     RenderParams p = make_params(w, h, 0, h, (double *)g.pixels.p, nullptr, false);
     CK(cudaEventRecord(g.ev[0], g.stream));
-    launch_render(p, false, g.const_geom, g.num_sms, g.stream);
+    launch_render(p, false, g.cull, g.num_sms, g.stream);
     CK(cudaEventRecord(g.ev[1], g.stream));
     CK(cudaMemcpyAsync(screen->pixels, g.pixels.p, bytes, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
@@ -470,7 +521,7 @@ size_t trt_render_ansi(const trt_Scene *scene, int width, int height, char *out,
     g.bytes.reserve(total + 16);
     RenderParams p = make_params(width, height, 0, height, nullptr, (uchar4 *)g.quant.p, false);
     CK(cudaEventRecord(g.ev[0], g.stream));
-    launch_render(p, false, g.const_geom, g.num_sms, g.stream);
+    launch_render(p, false, g.cull, g.num_sms, g.stream);
     CK(cudaEventRecord(g.ev[1], g.stream));
     launch_stream_frame((char *)g.bytes.p, width, height, g.stream);
     launch_encode_quant((const uchar4 *)g.quant.p, width, height, (char *)g.bytes.p, TRT_HOME_BYTES, g.stream);

@@ -31,7 +31,7 @@
 namespace trt {
 
 __constant__ DevScene c_scene;
-__constant__ double4 c_sphere_geom[TRT_MAX_CONST_SPHERES]; // (cx, cy, cz, r*r)
+__constant__ float4 c_sphere_cull[TRT_MAX_CONST_SPHERES]; // (cx, cy, cz, r_pad) in float, see sphere_cull()
 
 constexpr int TILE_W = 8;
 constexpr int TILE_H = 4;
@@ -100,9 +100,94 @@ __device__ __forceinline__ int sky_texel_index(const d3 &direction, int dim, int
     return ui + vi * dim;
 }
 
+// ---- conservative FP32 miss test ---------------------------------------------------------------------
+// ~90% of all ray/sphere tests of this path end at `discriminant < 0` (TRT.c:651).  That outcome is a
+// geometric fact — the line passes the centre at more than r — which single precision can CERTIFY for
+// all but the rays that graze the silhouette.  A sphere is culled only when
+//        |oc_f x d_f|^2  >  ( |d_f| * r_pad  +  |d_f| * CULL_EPS * (|o|_1 + max_i |c_i|_1) )^2
+// evaluated in float, where r_pad >= r*(1+2^-20) (host, rounded up) and CULL_EPS = 64 * 2^-24.
+// Error budget (DESIGN.md "FP32 cull"): rounding o, c, d to float and the float evaluation of the
+// cross product move |oc x d| by at most 9*2^-24*|d|*(|o|_1+|c|_1); the reference's own FP64 rounding
+// of the discriminant is below 2^-50 of the same scale.  With the 64*2^-24 margin the inequality above
+// implies the reference's COMPUTED discriminant is negative, i.e. the reference returns "miss" for this
+// sphere; everything else (and any NaN/inf, which makes the comparison false) goes to the exact FP64
+// test below, so results stay bit-identical.  The counting build re-checks every culled sphere exactly
+// (CTR_CULL_VIOLATIONS must be 0; tests/test_gpu_parity.py).
+constexpr float CULL_EPS = 64.0f * 5.9604644775390625e-08f;
+
+struct RayF32 {
+    float ox, oy, oz, dx, dy, dz;
+    float norm_d;     // |d_f|
+    float slack;      // |d_f| * CULL_EPS * (|o|_1 + max_i |c_i|_1)
+    bool usable;      // magnitudes inside the range the bound was derived for
+};
+
+__device__ __forceinline__ RayF32 ray_to_f32(const d3 &o, const d3 &d)
+{
+    RayF32 r;
+    r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
+    r.dx = (float)d.x; r.dy = (float)d.y; r.dz = (float)d.z;
+    r.norm_d = __fsqrt_rn(__fmaf_rn(r.dz, r.dz, __fmaf_rn(r.dy, r.dy, r.dx * r.dx)));
+    const float l1 = (fabsf(r.ox) + fabsf(r.oy)) + (fabsf(r.oz) + c_scene.filter_centre_l1);
+    r.slack = r.norm_d * (CULL_EPS * l1);
+    r.usable = c_scene.filter_enabled && (l1 < 1e15f) && (r.norm_d > 1e-15f) && (r.norm_d < 1e15f);
+    return r;
+}
+
+// true = the reference certainly computes discriminant < 0 for this sphere
+__device__ __forceinline__ bool sphere_cull(const RayF32 &r, const float4 g)
+{
+    const float ocx = r.ox - g.x, ocy = r.oy - g.y, ocz = r.oz - g.z;
+    const float cx = __fmaf_rn(ocy, r.dz, -(ocz * r.dy));
+    const float cy = __fmaf_rn(ocz, r.dx, -(ocx * r.dz));
+    const float cz = __fmaf_rn(ocx, r.dy, -(ocy * r.dx));
+    const float q = __fmaf_rn(cz, cz, __fmaf_rn(cy, cy, cx * cx));
+    const float t = __fmaf_rn(r.norm_d, g.w, r.slack);
+    return q > t * t;
+}
+
+// ---- ray_intersects_sphere (TRT.c:638-672) + the closest-so-far update of trace_ray (TRT.c:807-827) ----
+template <bool COUNT>
+__device__ __forceinline__ void sphere_exact(const double4 g, int i, const d3 &o, const d3 &d, double two_a, double four_a,
+                                             double &closest, int &obj, int &index, d3 &hit, const Tally<COUNT> &tally)
+{
+    tally.add(CTR_EXACT_SPHERE_TESTS);
+    const d3 oc = mk3(o.x - g.x, o.y - g.y, o.z - g.z);
+    const double b = 2.0 * dot(oc, d);
+    const double c = dot(oc, oc) - g.w;      // g.w = radius*radius, evaluated on the host in double
+    const double disc = b * b - four_a * c;  // (4.0*a)*c, scaling by 4 is exact
+    if (!(disc < 0.0)) {                     // TRT.c:651
+        tally.add(CTR_SPHERE_DISC_OK);
+        const double t0 = (-b - sqrt(disc)) / two_a;
+        if (t0 > 0.0) {
+            tally.add(CTR_SPHERE_T0_POS);
+            const d3 p = mk3(o.x + t0 * d.x, o.y + t0 * d.y, o.z + t0 * d.z);
+            const d3 back = o - p;
+            const double d2 = dot(back, back);
+            if (d2 < closest) {
+                tally.add(CTR_SPHERE_CLOSEST);
+                closest = d2;
+                obj = 1;
+                index = i;
+                hit = p;
+            }
+        }
+    }
+}
+
+// exact discriminant sign only — used by the counting build to audit the cull
+__device__ __forceinline__ bool exact_disc_negative(const double4 g, const d3 &o, const d3 &d, double four_a)
+{
+    const d3 oc = mk3(o.x - g.x, o.y - g.y, o.z - g.z);
+    const double b = 2.0 * dot(oc, d);
+    const double c = dot(oc, oc) - g.w;
+    return (b * b - four_a * c) < 0.0;
+}
+
 // ---- closest-hit query, the geometric half of trace_ray (TRT.c:805-853) -------------------------------
 // obj: 0 none, 1 sphere, 2 ground.  hit = un-pushed intersection point of the closest object.
-template <bool COUNT, bool CONST_GEOM>
+// Spheres are visited in index order (ties keep the lowest index, strict <), the ground last.
+template <bool COUNT, bool CULL>
 __device__ __forceinline__ void closest_hit(const RenderParams &P, const d3 &o, const d3 &d, int &obj, int &index,
                                             d3 &hit, const Tally<COUNT> &tally)
 {
@@ -113,32 +198,35 @@ __device__ __forceinline__ void closest_hit(const RenderParams &P, const d3 &o, 
     const double two_a = 2.0 * a;
     const double four_a = 4.0 * a;
     const int n = c_scene.num_spheres;
-    for (int i = 0; i < n; i++) {
-        double4 g;
-        if (CONST_GEOM) g = c_sphere_geom[i];
-        else g = ldg_geom(P.sphere_geom, i);
-        tally.add(CTR_SPHERE_TESTS);
-        const d3 oc = mk3(o.x - g.x, o.y - g.y, o.z - g.z);
-        const double b = 2.0 * dot(oc, d);
-        const double c = dot(oc, oc) - g.w;      // g.w = radius*radius, evaluated on the host in double
-        const double disc = b * b - four_a * c;  // (4.0*a)*c, scaling by 4 is exact
-        if (!(disc < 0.0)) {                     // TRT.c:651
-            tally.add(CTR_SPHERE_DISC_OK);
-            const double t0 = (-b - sqrt(disc)) / two_a;
-            if (t0 > 0.0) {
-                tally.add(CTR_SPHERE_T0_POS);
-                const d3 p = mk3(o.x + t0 * d.x, o.y + t0 * d.y, o.z + t0 * d.z);
-                const d3 back = o - p;
-                const double d2 = dot(back, back);
-                if (d2 < closest) {
-                    tally.add(CTR_SPHERE_CLOSEST);
-                    closest = d2;
-                    obj = 1;
-                    index = i;
-                    hit = p;
-                }
+    if (COUNT) atomicAdd(&P.counters[CTR_SPHERE_TESTS], (unsigned long long)n);
+    if (CULL) {
+        const RayF32 rf = ray_to_f32(o, d);
+        const bool in_const = c_scene.filter_in_const != 0;
+        for (int base = 0; base < n; base += 32) {
+            const int cnt = min(32, n - base);
+            // pass 1 (FP32, branch-free, warp-uniform operands): which spheres of this chunk survive
+            unsigned int survivors = 0;
+#pragma unroll 6
+            for (int j = 0; j < cnt; j++) {
+                const float4 g = in_const ? c_sphere_cull[base + j] : __ldg(&P.sphere_cull[base + j]);
+                const bool culled = rf.usable && sphere_cull(rf, g);
+                survivors |= (culled ? 0u : 1u) << j;
+            }
+            if (COUNT) {
+                for (int j = 0; j < cnt; j++)
+                    if (!((survivors >> j) & 1u) && !exact_disc_negative(ldg_geom(P.sphere_geom, base + j), o, d, four_a))
+                        atomicAdd(&P.counters[CTR_CULL_VIOLATIONS], 1ull);
+            }
+            // pass 2 (FP64, exact): each lane walks its own survivors in index order
+            while (survivors) {
+                const int j = __ffs(survivors) - 1;
+                survivors &= survivors - 1;
+                sphere_exact<COUNT>(ldg_geom(P.sphere_geom, base + j), base + j, o, d, two_a, four_a, closest, obj, index, hit, tally);
             }
         }
+    } else {
+        for (int i = 0; i < n; i++)
+            sphere_exact<COUNT>(ldg_geom(P.sphere_geom, i), i, o, d, two_a, four_a, closest, obj, index, hit, tally);
     }
     // ground, TRT.c:677-695 and 831-853
     tally.add(CTR_PLANE_TESTS);
@@ -172,7 +260,7 @@ __device__ __forceinline__ d3 push_back(const d3 &o, const d3 &hit)
     return hit + back;
 }
 
-template <bool COUNT, bool CONST_GEOM>
+template <bool COUNT, bool CULL>
 __global__ void __launch_bounds__(CTA_THREADS) k_render(const RenderParams P)
 {
     __shared__ double s_byte_to_unit[256]; // k/255.0, the division of TRT.c:866 done once per CTA
@@ -254,7 +342,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_render(const RenderParams P)
             d3 hit;
             tally.add(CTR_TRACE_CALLS);
             if (phase == PH_MAIN) tally.add(CTR_BOUNCE_ITERS);
-            closest_hit<COUNT, CONST_GEOM>(P, o, d, obj, index, hit, tally);
+            closest_hit<COUNT, CULL>(P, o, d, obj, index, hit, tally);
             if (obj != 0) tally.add(CTR_TRACE_HITS);
             else { tally.add(CTR_SKY_LOOKUPS); if (phase != PH_MAIN) tally.add(CTR_SKY_SKIPPED); }
 
@@ -283,9 +371,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_render(const RenderParams P)
                 surf_index = index;
                 d3 n;
                 if (obj == 1) {
-                    double4 g;
-                    if (CONST_GEOM) g = c_sphere_geom[index];
-                    else g = ldg_geom(P.sphere_geom, index);
+                    const double4 g = ldg_geom(P.sphere_geom, index);
                     n = mk3(hit.x - g.x, hit.y - g.y, hit.z - g.z);   // TRT.c:824
                 } else {
                     n = mk3(c_scene.ground_normal[0], c_scene.ground_normal[1], c_scene.ground_normal[2]);
@@ -412,8 +498,7 @@ __global__ void k_probe_trace(const RenderParams P, const double *__restrict__ r
     const Tally<false> tally{nullptr};
     int obj, index;
     d3 hit;
-    if (c_scene.spheres_in_const) closest_hit<false, true>(P, o, d, obj, index, hit, tally);
-    else closest_hit<false, false>(P, o, d, obj, index, hit, tally);
+    closest_hit<false, true>(P, o, d, obj, index, hit, tally);
     d3 point, normal, colour;
     double reflectivity = 0.0;
     if (obj == 0) {
@@ -426,7 +511,7 @@ __global__ void k_probe_trace(const RenderParams P, const double *__restrict__ r
     } else {
         const DevMaterial *m;
         if (obj == 1) {
-            const double4 g = c_scene.spheres_in_const ? c_sphere_geom[index] : ldg_geom(P.sphere_geom, index);
+            const double4 g = ldg_geom(P.sphere_geom, index);
             normal = mk3(hit.x - g.x, hit.y - g.y, hit.z - g.z);
             m = &P.sphere_mat[index];
         } else {
@@ -462,6 +547,58 @@ __global__ void k_probe_sky(const RenderParams P, const double *__restrict__ dir
     out[i * 5 + 4] = t.z;
 }
 
+// ---- self-test: shared-reciprocal division (trt_device.cuh) against the IEEE division --------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long &state)
+{
+    unsigned long long z = (state += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ double random_double(unsigned long long &state, int exp_lo, int exp_hi)
+{
+    const unsigned long long bits = mix64(state);
+    const unsigned long long mant = bits & 0x000FFFFFFFFFFFFFull;
+    const int e = exp_lo + (int)((bits >> 52) % (unsigned long long)(exp_hi - exp_lo + 1));
+    const unsigned long long sign = (mix64(state) & 1ull) << 63;
+    return __longlong_as_double((long long)(sign | ((unsigned long long)(e + 1023) << 52) | mant));
+}
+
+__global__ void k_selftest_division(unsigned long long seed, int iters, unsigned long long *mismatches)
+{
+    unsigned long long state = seed + 0x1000003ull * (unsigned long long)(blockIdx.x * blockDim.x + threadIdx.x);
+    unsigned long long bad = 0;
+    for (int it = 0; it < iters; it++) {
+        double a[3], b;
+        const int mode = it & 3;
+        if (mode == 0) {            // what unit() does: components over their own length, moderate scale
+            const int e = -20 + (int)(mix64(state) % 41);
+            a[0] = random_double(state, e - 3, e); a[1] = random_double(state, e - 3, e); a[2] = random_double(state, e - 30, e);
+            b = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+        } else if (mode == 1) {     // unrelated operands, wide exponent range
+            a[0] = random_double(state, -500, 500); a[1] = random_double(state, -500, 500); a[2] = random_double(state, -1022, 1023);
+            b = random_double(state, -500, 500);
+        } else if (mode == 2) {     // quotients near the overflow / underflow guards and zeros
+            a[0] = random_double(state, -1022, -960); a[1] = 0.0; a[2] = random_double(state, 900, 1023);
+            b = random_double(state, -60, 60);
+        } else {                    // divisors with extreme significands (all ones / all zeros)
+            a[0] = random_double(state, -4, 4); a[1] = random_double(state, -4, 4); a[2] = 1.0;
+            const int e = -8 + (int)(mix64(state) % 17);
+            const unsigned long long m = (mix64(state) & 1ull) ? 0x000FFFFFFFFFFFFFull : (mix64(state) & 0xFull);
+            b = __longlong_as_double((long long)(((unsigned long long)(e + 1023) << 52) | m));
+        }
+        const Reciprocal inv = reciprocal_of(b);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const double fast = div_by(a[k], inv);
+            const double ieee = __ddiv_rn(a[k], b);
+            if (__double_as_longlong(fast) != __double_as_longlong(ieee) && !(fast != fast && ieee != ieee)) bad++;
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // host side of this TU: scene upload (constant memory lives here) and the launcher
 
@@ -474,11 +611,11 @@ static void die(cudaError_t e, const char *file, int line)
 }
 #define CK(x) die((x), __FILE__, __LINE__)
 
-void upload_scene_constants(const DevScene &scene, const double4 *geom, int count, cudaStream_t stream)
+void upload_scene_constants(const DevScene &scene, const float4 *cull, int count, cudaStream_t stream)
 {
     CK(cudaMemcpyToSymbolAsync(c_scene, &scene, sizeof(DevScene), 0, cudaMemcpyHostToDevice, stream));
-    if (count > 0 && count <= TRT_MAX_CONST_SPHERES)
-        CK(cudaMemcpyToSymbolAsync(c_sphere_geom, geom, sizeof(double4) * (size_t)count, 0, cudaMemcpyHostToDevice, stream));
+    if (cull && count > 0 && count <= TRT_MAX_CONST_SPHERES)
+        CK(cudaMemcpyToSymbolAsync(c_sphere_cull, cull, sizeof(float4) * (size_t)count, 0, cudaMemcpyHostToDevice, stream));
 }
 
 int render_ctas_per_sm()
@@ -492,7 +629,7 @@ int render_ctas_per_sm()
     return cached;
 }
 
-void launch_render(const RenderParams &p, bool count, bool const_geom, int num_sms, cudaStream_t stream)
+void launch_render(const RenderParams &p, bool count, bool cull, int num_sms, cudaStream_t stream)
 {
     CK(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), stream));
     const int band_rows = p.row1 - p.row0;
@@ -504,13 +641,24 @@ void launch_render(const RenderParams &p, bool count, bool const_geom, int num_s
     if (grid < 1) grid = 1;
     dim3 g((unsigned)grid), b(CTA_THREADS);
     if (count) {
-        if (const_geom) k_render<true, true><<<g, b, 0, stream>>>(p);
+        if (cull) k_render<true, true><<<g, b, 0, stream>>>(p);
         else k_render<true, false><<<g, b, 0, stream>>>(p);
     } else {
-        if (const_geom) k_render<false, true><<<g, b, 0, stream>>>(p);
+        if (cull) k_render<false, true><<<g, b, 0, stream>>>(p);
         else k_render<false, false><<<g, b, 0, stream>>>(p);
     }
     CK(cudaGetLastError());
+}
+
+unsigned long long run_selftest_division(unsigned long long seed, int ctas, int iters, unsigned long long *d_scratch, cudaStream_t stream)
+{
+    CK(cudaMemsetAsync(d_scratch, 0, sizeof(unsigned long long), stream));
+    k_selftest_division<<<ctas, 256, 0, stream>>>(seed, iters, d_scratch);
+    CK(cudaGetLastError());
+    unsigned long long bad = 0;
+    CK(cudaMemcpyAsync(&bad, d_scratch, sizeof bad, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return bad;
 }
 
 void launch_probe_trace(const RenderParams &p, const double *d_rays, int n, double *d_out, cudaStream_t stream)

@@ -18,6 +18,8 @@ SIGNATURES = {
     "trt_is_initialized": (C.c_int, []),
     "trt_stream": (C.c_void_p, []),
     "trt_set_stream": (C.c_int, [C.c_void_p]),
+    "trt_use_own_stream": (C.c_int, []),
+    "trt_set_cull": (C.c_int, [C.c_int]),
     "trt_upload_skybox": (C.c_int, [C.POINTER(abi.Skybox)]),
     "trt_project_scene": (None, [C.POINTER(abi.Scene), C.POINTER(abi.Screen)]),
     "trt_draw_screen": (C.c_size_t, [C.POINTER(abi.Screen), C.c_void_p]),
@@ -33,6 +35,7 @@ SIGNATURES = {
     "trt_model_flops": (C.c_double, [C.POINTER(C.c_longlong)]),
     "trt_probe_trace_ray": (C.c_int, [C.POINTER(abi.Scene), C.c_void_p, C.c_int, C.c_void_p]),
     "trt_probe_skybox": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "trt_selftest_division": (C.c_longlong, [C.c_ulonglong, C.c_longlong]),
     "trt_device_alloc": (C.c_void_p, [C.c_size_t]),
     "trt_device_free": (None, [C.c_void_p]),
     "trt_host_alloc_pinned": (C.c_void_p, [C.c_size_t]),

@@ -89,8 +89,12 @@ class Renderer:
         return list(ctr), self.L.trt_model_flops(ctr)
 
     def use_stream(self, cuda_stream_ptr):
-        """Run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); None = own stream."""
-        self.L.trt_set_stream(cuda_stream_ptr)
+        """Run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream, where 0 is the
+        legacy default stream); None = back to the library's own stream."""
+        if cuda_stream_ptr is None:
+            self.L.trt_use_own_stream()
+        else:
+            self.L.trt_set_stream(C.c_void_p(int(cuda_stream_ptr)))
 
     def synchronize(self):
         self.L.trt_synchronize()

@@ -175,6 +175,39 @@ def test_gpu_skybox_known_answers(renderer):
     assert (out[:, 1] >= 64 * 64).any()  # the +0.5 clamp overflow into the pad texels was exercised
 
 
+def test_gpu_shared_reciprocal_division_is_ieee(renderer):
+    """the normalisations divide by a shared Newton reciprocal; every quotient must equal a / b bit for bit"""
+    for seed in (1, 2, 3):
+        assert renderer.L.trt_selftest_division(seed, 3_000_000_000) == 0
+
+
+def test_gpu_cull_never_rejects_a_real_candidate_and_off_switch(renderer, orc):
+    """FP32 miss test: the counting build re-evaluates every culled sphere exactly (violations must be 0),
+    and the all-FP64 path (cull off) renders the same bits"""
+    cases = [S.SceneData(160, 90, S.synthetic_cubemap("uv_gradient", 64)).set_time(3.7),
+             S.SceneData(96, 54, S.synthetic_cubemap("uv_gradient", 64), kind="stress", num_spheres=1024).set_time(3.7),
+             S.SceneData(64, 36, S.synthetic_cubemap("uv_gradient", 64), kind="stress", num_spheres=1100).set_time(8.1)]
+    far = S.SceneData(96, 54, S.synthetic_cubemap("uv_gradient", 64))
+    far.c.camera.frame.origin = abi.Vector(0.0, 300.0, 4000.0)
+    cases.append(far)
+    for sc in cases:
+        renderer.upload_skybox(sc.skybox)
+        renderer.set_scene(sc)
+        ctr, _ = renderer.count_rows(sc.width, sc.height, 0, sc.height)
+        violations, exact = ctr[28], ctr[27]
+        assert violations == 0
+        assert exact < ctr[0]          # the cull does remove work ...
+        assert exact >= ctr[1]         # ... but never a sphere whose discriminant is >= 0
+        with_cull = renderer.project_scene(sc)
+        renderer.L.trt_set_cull(0)
+        try:
+            without = renderer.project_scene(sc)
+        finally:
+            renderer.L.trt_set_cull(1)
+        assert np.array_equal(with_cull, without)
+        assert np.array_equal(with_cull, U.cpu_render(orc, "orc_project_scene", sc))
+
+
 # ---- encoder edge cases -----------------------------------------------------------------------------------
 
 def test_gpu_encoder_values_and_alignment(renderer, orc):
