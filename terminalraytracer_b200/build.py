@@ -42,7 +42,14 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, defines=(), out=None):
+    """defines/out: experiment builds (e.g. defines=["TRT_MIN_CTAS_PER_SM=6"], out="libtrt_b200_x.so");
+    the product build uses neither."""
+    global OBJ, LIB
+    if out:
+        LIB = os.path.join(HERE, out)
+        OBJ = os.path.join(HERE, "_obj_" + os.path.splitext(out)[0])
+        force = True
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
@@ -55,7 +62,7 @@ def build_library(force=False, verbose=False):
         o = os.path.join(OBJ, src + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + ARCH + NVCC_COMMON + extra + ["-c", s, "-o", o]
+            cmd = [nvcc] + ARCH + NVCC_COMMON + extra + ["-D" + d for d in defines] + ["-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             log.append(" ".join(cmd) + "\n" + r.stdout + r.stderr)
             if r.returncode != 0:
@@ -84,4 +91,6 @@ def build_library(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build_library(force="--force" in sys.argv, verbose="--quiet" not in sys.argv, defines=defs, out=outs[0] if outs else None))

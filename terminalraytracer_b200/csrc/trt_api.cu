@@ -76,7 +76,7 @@ struct Context {
     Buffer sky;
     int sky_dim = -1, sky_face_stride = 0;
     // work
-    Buffer tile_counter, counters;
+    Buffer tile_counter, counters, byte_to_unit;
     Buffer pixels, quant, bytes;
     PinnedBuffer stage;
 } g;
@@ -133,6 +133,7 @@ void upload_scene(const trt_Scene *scene)
         exit(1);
     }
     DevScene &s = g.scene;
+    bool ground_in_range = true;
     const trt_Camera &c = scene->camera;
     s.bx[0] = c.frame.basis.x.x; s.bx[1] = c.frame.basis.x.y; s.bx[2] = c.frame.basis.x.z;
     s.by[0] = c.frame.basis.y.x; s.by[1] = c.frame.basis.y.y; s.by[2] = c.frame.basis.y.z;
@@ -143,6 +144,11 @@ void upload_scene(const trt_Scene *scene)
     s.screen_height = c.screen_height;
     s.ground_point[0] = scene->ground.point.x; s.ground_point[1] = scene->ground.point.y; s.ground_point[2] = scene->ground.point.z;
     s.ground_normal[0] = scene->ground.normal.x; s.ground_normal[1] = scene->ground.normal.y; s.ground_normal[2] = scene->ground.normal.z;
+    for (int k = 0; k < 3; k++) {
+        s.ground_point_f[k] = (float)s.ground_point[k];
+        s.ground_normal_f[k] = (float)s.ground_normal[k];
+    }
+    if (!(fabs(s.ground_point[0]) + fabs(s.ground_point[1]) + fabs(s.ground_point[2]) < 1e12)) ground_in_range = false;
     set_material(s.ground_even, scene->ground.even_material);
     set_material(s.ground_odd, scene->ground.odd_material);
     s.num_dir = scene->num_directional_lights;
@@ -168,7 +174,7 @@ void upload_scene(const trt_Scene *scene)
     const int n = s.num_spheres;
     std::vector<double4> geom((size_t)(n > 0 ? n : 1));
     std::vector<DevMaterial> mats((size_t)(n > 0 ? n : 1));
-    std::vector<float4> cull((size_t)(n > 0 ? n : 1));
+    std::vector<float4> cull((size_t)n + 2, make_float4(0.f, 0.f, 0.f, 0.f));   // padded to an even count (+1 spare)
     bool in_range = true;       // magnitudes for which the FP32 cull's error bound was derived
     double centre_l1 = 0.0;
     for (int i = 0; i < n; i++) {
@@ -184,7 +190,7 @@ void upload_scene(const trt_Scene *scene)
         cull[i] = make_float4((float)sp.center.x, (float)sp.center.y, (float)sp.center.z,
                               float_round_up(r * (1.0 + 1.0 / 1048576.0)));
     }
-    g.cull = g.cull_allowed && in_range;
+    g.cull = g.cull_allowed && in_range && ground_in_range;
     s.filter_enabled = g.cull ? 1 : 0;
     s.filter_centre_l1 = float_round_up(centre_l1 * (1.0 + 1.0 / 1048576.0));
     g.sphere_geom.reserve(sizeof(double4) * geom.size());
@@ -195,10 +201,13 @@ void upload_scene(const trt_Scene *scene)
     // returns: plain (staged) cudaMemcpyAsync from pageable memory is synchronous w.r.t. the host buffer.
     CK(cudaMemcpyAsync(g.sphere_geom.p, geom.data(), sizeof(double4) * geom.size(), cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(g.sphere_mat.p, mats.data(), sizeof(DevMaterial) * mats.size(), cudaMemcpyHostToDevice, g.stream));
-    upload_scene_constants(s, cull.data(), n, g.stream);
+    upload_scene_constants(s, cull.data(), n + 2, g.stream);
     CK(cudaStreamSynchronize(g.stream));
     g.have_scene = true;
 }
+
+// 0: all FP64; 1: FP32 cull records in __constant__; 2: cull records in global memory (big scenes)
+int cull_mode() { return !g.cull ? 0 : (g.scene.filter_in_const ? 1 : 2); }
 
 RenderParams make_params(int width, int height, int row0, int row1, double *d_pixels, uchar4 *d_quant, bool count)
 {
@@ -220,6 +229,7 @@ RenderParams make_params(int width, int height, int row0, int row1, double *d_pi
     p.sphere_geom = (const double4 *)g.sphere_geom.p;
     p.sphere_cull = (const float4 *)g.sphere_cull.p;
     p.sphere_mat = (const DevMaterial *)g.sphere_mat.p;
+    p.byte_to_unit = (const double *)g.byte_to_unit.p;
     p.sky = (const uchar4 *)g.sky.p;
     p.tile_counter = (unsigned int *)g.tile_counter.p;
     p.counters = count ? (unsigned long long *)g.counters.p : nullptr;
@@ -252,6 +262,16 @@ int trt_init(int device)
     for (auto &ev : g.ev) CK(cudaEventCreate(&ev));
     g.tile_counter.reserve(256);
     g.counters.reserve(sizeof(unsigned long long) * TRT_NUM_COUNTERS);
+    {
+        // k/255.0 for every byte value: the three divisions of TRT.c:866, evaluated once, in host double
+        double table[256];
+        for (int k = 0; k < 256; k++) {
+            volatile double num = (double)k;
+            table[k] = num / 255.0;
+        }
+        g.byte_to_unit.reserve(sizeof table);
+        CK(cudaMemcpy(g.byte_to_unit.p, table, sizeof table, cudaMemcpyHostToDevice));
+    }
     g.ready = true;
     return 0;
 }
@@ -265,6 +285,7 @@ void trt_shutdown(void)
     g.sphere_mat.release();
     g.sky.release();
     g.tile_counter.release();
+    g.byte_to_unit.release();
     g.counters.release();
     g.pixels.release();
     g.quant.release();
@@ -347,7 +368,7 @@ int trt_render_rows_device(int width, int height, int row0, int row1, double *d_
 {
     require_init("trt_render_rows_device");
     RenderParams p = make_params(width, height, row0, row1, d_pixels, nullptr, false);
-    launch_render(p, false, g.cull, g.num_sms, g.stream);
+    launch_render(p, false, cull_mode(), g.num_sms, g.stream);
     return 0;
 }
 
@@ -355,7 +376,7 @@ int trt_render_rows_quant_device(int width, int height, int row0, int row1, unsi
 {
     require_init("trt_render_rows_quant_device");
     RenderParams p = make_params(width, height, row0, row1, nullptr, (uchar4 *)d_quant, false);
-    launch_render(p, false, g.cull, g.num_sms, g.stream);
+    launch_render(p, false, cull_mode(), g.num_sms, g.stream);
     return 0;
 }
 
@@ -385,7 +406,7 @@ int trt_count_rows_device(int width, int height, int row0, int row1, double *d_p
     require_init("trt_count_rows_device");
     CK(cudaMemsetAsync(g.counters.p, 0, sizeof(unsigned long long) * TRT_NUM_COUNTERS, g.stream));
     RenderParams p = make_params(width, height, row0, row1, d_pixels, nullptr, true);
-    launch_render(p, true, g.cull, g.num_sms, g.stream);
+    launch_render(p, true, cull_mode(), g.num_sms, g.stream);
     CK(cudaMemcpyAsync(counters, g.counters.p, sizeof(unsigned long long) * TRT_NUM_COUNTERS, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     return 0;
@@ -476,7 +497,7 @@ void trt_project_scene(const trt_Scene *scene, trt_Screen *screen)
     g.pixels.reserve(bytes);
     RenderParams p = make_params(w, h, 0, h, (double *)g.pixels.p, nullptr, false);
     CK(cudaEventRecord(g.ev[0], g.stream));
-    launch_render(p, false, g.cull, g.num_sms, g.stream);
+    launch_render(p, false, cull_mode(), g.num_sms, g.stream);
     CK(cudaEventRecord(g.ev[1], g.stream));
     CK(cudaMemcpyAsync(screen->pixels, g.pixels.p, bytes, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
@@ -521,7 +542,7 @@ size_t trt_render_ansi(const trt_Scene *scene, int width, int height, char *out,
     g.bytes.reserve(total + 16);
     RenderParams p = make_params(width, height, 0, height, nullptr, (uchar4 *)g.quant.p, false);
     CK(cudaEventRecord(g.ev[0], g.stream));
-    launch_render(p, false, g.cull, g.num_sms, g.stream);
+    launch_render(p, false, cull_mode(), g.num_sms, g.stream);
     CK(cudaEventRecord(g.ev[1], g.stream));
     launch_stream_frame((char *)g.bytes.p, width, height, g.stream);
     launch_encode_quant((const uchar4 *)g.quant.p, width, height, (char *)g.bytes.p, TRT_HOME_BYTES, g.stream);

@@ -31,11 +31,17 @@
 namespace trt {
 
 __constant__ DevScene c_scene;
-__constant__ float4 c_sphere_cull[TRT_MAX_CONST_SPHERES]; // (cx, cy, cz, r_pad) in float, see sphere_cull()
+__constant__ float4 c_sphere_cull[TRT_MAX_CONST_SPHERES + 2]; // (cx, cy, cz, r_pad) in float, see sphere_cull()
 
 constexpr int TILE_W = 8;
 constexpr int TILE_H = 4;
-constexpr int WARPS_PER_CTA = 4;
+#ifndef TRT_WARPS_PER_CTA
+#define TRT_WARPS_PER_CTA 4
+#endif
+#ifndef TRT_MIN_CTAS_PER_SM
+#define TRT_MIN_CTAS_PER_SM 6
+#endif
+constexpr int WARPS_PER_CTA = TRT_WARPS_PER_CTA;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 
 enum Phase : int { PH_MAIN = 0, PH_SHADOW = 1 };
@@ -61,9 +67,9 @@ struct Tally {
 // Returns the linear texel index inside the chosen face and the face itself.  The dot products with
 // the axis table reduce exactly (x*1.0 + y*0.0 + z*0.0 == x for finite inputs), so the face argmax,
 // the projection and the (u,v) extraction below are the reference's values, not approximations.
-__device__ __forceinline__ int sky_texel_index(const d3 &direction, int dim, int &face)
+// `dir` is the already normalised direction (normalize_vector_copy, TRT.c:702, is done by the caller).
+__device__ __forceinline__ int sky_texel_index(const d3 &dir, int dim, int &face)
 {
-    d3 dir = unit(direction);
     // argmax over (+x,-x,+y,-y,+z,-z), strict >, first wins, start at -1.0 (TRT.c:703-713)
     double best_t = -1.0;
     int best = -1;
@@ -146,6 +152,29 @@ __device__ __forceinline__ bool sphere_cull(const RayF32 &r, const float4 g)
     return q > t * t;
 }
 
+// Conservative FP32 miss test for the ground plane (TRT.c:677-695): the reference reports a hit only if
+// t = ((point - origin) . n) / (direction . n) > 1e-5.  When numerator and denominator have opposite signs
+// the quotient is negative (or -0), so the test is a miss; single precision certifies the two signs unless
+// either value is within its rounding error of zero.  Error bounds: every product of the two 3-term dot
+// products is computed from float-rounded inputs (relative error 2^-24 each) and accumulated in float, so
+// |num_f - num| <= 8*2^-24 * sum_k (|p_k| + |o_k|)|n_k| and |den_f - den| <= 8*2^-24 * sum_k |d_k||n_k|;
+// the margins below are twice that, and the reference's own FP64 rounding is ~2^-29 of them.
+// NaN/inf make the comparisons false.
+__device__ __forceinline__ bool plane_cull(const RayF32 &r)
+{
+    const float nx = c_scene.ground_normal_f[0], ny = c_scene.ground_normal_f[1], nz = c_scene.ground_normal_f[2];
+    const float px = c_scene.ground_point_f[0], py = c_scene.ground_point_f[1], pz = c_scene.ground_point_f[2];
+    const float anx = fabsf(nx), any = fabsf(ny), anz = fabsf(nz);
+    const float num = __fmaf_rn(pz - r.oz, nz, __fmaf_rn(py - r.oy, ny, (px - r.ox) * nx));
+    const float den = __fmaf_rn(r.dz, nz, __fmaf_rn(r.dy, ny, r.dx * nx));
+    const float num_scale = __fmaf_rn(fabsf(pz) + fabsf(r.oz), anz, __fmaf_rn(fabsf(py) + fabsf(r.oy), any, (fabsf(px) + fabsf(r.ox)) * anx));
+    const float den_scale = __fmaf_rn(fabsf(r.dz), anz, __fmaf_rn(fabsf(r.dy), any, fabsf(r.dx) * anx));
+    const float e_num = (16.0f * 5.9604644775390625e-08f) * num_scale;
+    const float e_den = (16.0f * 5.9604644775390625e-08f) * den_scale;
+    const bool finite = r.usable && (num_scale < 1e30f) && (den_scale < 1e30f);
+    return finite && ((num < -e_num && den > e_den) || (num > e_num && den < -e_den));
+}
+
 // ---- ray_intersects_sphere (TRT.c:638-672) + the closest-so-far update of trace_ray (TRT.c:807-827) ----
 template <bool COUNT>
 __device__ __forceinline__ void sphere_exact(const double4 g, int i, const d3 &o, const d3 &d, double two_a, double four_a,
@@ -187,7 +216,8 @@ __device__ __forceinline__ bool exact_disc_negative(const double4 g, const d3 &o
 // ---- closest-hit query, the geometric half of trace_ray (TRT.c:805-853) -------------------------------
 // obj: 0 none, 1 sphere, 2 ground.  hit = un-pushed intersection point of the closest object.
 // Spheres are visited in index order (ties keep the lowest index, strict <), the ground last.
-template <bool COUNT, bool CULL>
+// CULL: 0 = every test in FP64; 1 = FP32 cull records in __constant__; 2 = cull records in global memory.
+template <bool COUNT, int CULL>
 __device__ __forceinline__ void closest_hit(const RenderParams &P, const d3 &o, const d3 &d, int &obj, int &index,
                                             d3 &hit, const Tally<COUNT> &tally)
 {
@@ -199,19 +229,25 @@ __device__ __forceinline__ void closest_hit(const RenderParams &P, const d3 &o, 
     const double four_a = 4.0 * a;
     const int n = c_scene.num_spheres;
     if (COUNT) atomicAdd(&P.counters[CTR_SPHERE_TESTS], (unsigned long long)n);
+    bool ground_culled = false;
     if (CULL) {
         const RayF32 rf = ray_to_f32(o, d);
-        const bool in_const = c_scene.filter_in_const != 0;
+        ground_culled = !COUNT && plane_cull(rf);   // the counting build runs the exact plane test: it counts its branches
         for (int base = 0; base < n; base += 32) {
             const int cnt = min(32, n - base);
-            // pass 1 (FP32, branch-free, warp-uniform operands): which spheres of this chunk survive
+            // pass 1 (FP32, branch-free, warp-uniform operands): which spheres of this chunk survive.
+            // The records are padded to an even count (pad records are masked off below), so the loop
+            // needs no remainder handling: two independent tests per trip.
             unsigned int survivors = 0;
-#pragma unroll 6
-            for (int j = 0; j < cnt; j++) {
-                const float4 g = in_const ? c_sphere_cull[base + j] : __ldg(&P.sphere_cull[base + j]);
-                const bool culled = rf.usable && sphere_cull(rf, g);
-                survivors |= (culled ? 0u : 1u) << j;
+            for (int j = 0; j < cnt; j += 2) {
+                const float4 g0 = CULL == 1 ? c_sphere_cull[base + j] : __ldg(&P.sphere_cull[base + j]);
+                const float4 g1 = CULL == 1 ? c_sphere_cull[base + j + 1] : __ldg(&P.sphere_cull[base + j + 1]);
+                const unsigned int s0 = sphere_cull(rf, g0) ? 0u : 1u;
+                const unsigned int s1 = sphere_cull(rf, g1) ? 0u : 2u;
+                survivors |= (s0 | s1) << j;
             }
+            const unsigned int valid = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+            survivors = rf.usable ? (survivors & valid) : valid;
             if (COUNT) {
                 for (int j = 0; j < cnt; j++)
                     if (!((survivors >> j) & 1u) && !exact_disc_negative(ldg_geom(P.sphere_geom, base + j), o, d, four_a))
@@ -230,6 +266,7 @@ __device__ __forceinline__ void closest_hit(const RenderParams &P, const d3 &o, 
     }
     // ground, TRT.c:677-695 and 831-853
     tally.add(CTR_PLANE_TESTS);
+    if (ground_culled) return;
     const d3 gn = mk3(c_scene.ground_normal[0], c_scene.ground_normal[1], c_scene.ground_normal[2]);
     const double denom = dot(d, gn);
     if (fabs(denom) > 0.00001) {
@@ -260,12 +297,24 @@ __device__ __forceinline__ d3 push_back(const d3 &o, const d3 &hit)
     return hit + back;
 }
 
-template <bool COUNT, bool CULL>
-__global__ void __launch_bounds__(CTA_THREADS) k_render(const RenderParams P)
+__device__ __forceinline__ const DevMaterial *surface_material(const RenderParams &P, int obj, int index)
 {
-    __shared__ double s_byte_to_unit[256]; // k/255.0, the division of TRT.c:866 done once per CTA
+    return (obj == 1) ? &P.sphere_mat[index] : (index ? &c_scene.ground_odd : &c_scene.ground_even);
+}
+
+// ---- K1 ------------------------------------------------------------------------------------------------
+// One loop, one ray per trip.  Every step of the trip appears ONCE in the instruction stream (one
+// normalisation of the ray direction, one closest-hit query, one push-back, one normal/sky normalisation,
+// one accumulate, one reflect, one shadow-ray setup) and is predicated by the lane's state, so primary,
+// bounce and shadow rays of different lanes execute the same instructions, and the loop body stays small
+// enough for the instruction caches (an earlier version that inlined trace_ray's callees per call site was
+// 41 KB of SASS and stalled on instruction fetch as soon as occupancy was raised; profiles/).
+template <bool COUNT, int CULL>
+__global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(const RenderParams P)
+{
+    __shared__ double s_byte_to_unit[256]; // k/255.0 (TRT.c:866), evaluated on the host in double
     __shared__ unsigned int s_tile[WARPS_PER_CTA];
-    for (int k = threadIdx.x; k < 256; k += CTA_THREADS) s_byte_to_unit[k] = (double)k / 255.0;
+    for (int k = threadIdx.x; k < 256; k += CTA_THREADS) s_byte_to_unit[k] = P.byte_to_unit[k];
     __syncthreads();
 
     const Tally<COUNT> tally{P.counters};
@@ -276,14 +325,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_render(const RenderParams P)
     const int tiles_y = (band_rows + TILE_H - 1) / TILE_H;
     const unsigned int num_tiles = (unsigned int)(tiles_x * tiles_y);
 
-    const d3 bx = mk3(c_scene.bx[0], c_scene.bx[1], c_scene.bx[2]);
-    const d3 by = mk3(c_scene.by[0], c_scene.by[1], c_scene.by[2]);
-    const d3 bz = mk3(c_scene.bz[0], c_scene.bz[1], c_scene.bz[2]);
-    const d3 eye = mk3(c_scene.eye[0], c_scene.eye[1], c_scene.eye[2]);
     const double sw = c_scene.screen_width, sh = c_scene.screen_height;
     const double pixel_w = sw / P.width;   // TRT.c:981
     const double pixel_h = sh / P.height;  // TRT.c:982
-    const double sz = -c_scene.screen_distance;
     const int num_dir = c_scene.num_dir;
     const int num_lights = num_dir + c_scene.num_point;
 
@@ -305,165 +349,166 @@ __global__ void __launch_bounds__(CTA_THREADS) k_render(const RenderParams P)
         const double sy0 = -(((double)row / (double)P.height) * sh - sh / 2.0);
 
         d3 average = mk3(0.0, 0.0, 0.0);
-        // ---- per-lane state machine -----------------------------------------------------------
-        int k = 0;            // sample index (ray_num)
+        // ---- per-lane ray state ------------------------------------------------------------------
+        int k = 0;                         // sample index (ray_num)
         int phase = PH_MAIN;
         int bounces = 0;
-        int light = 0;        // index of the light whose shadow ray is in flight
+        int light = 0;                     // index of the light whose shadow ray is in flight
         int surf_obj = 0, surf_index = 0;  // what the main ray hit
         double weight = 1.0, weight_sum = 0.0, light_d2 = 0.0, intensity = 0.0;
-        d3 o, d, d_main, nrm, lit, sample;
-        bool new_sample = true;
+        d3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), d_main = d, nrm = d, lit = d, sample = d;
+        bool fresh = true;                 // start the next sample of this pixel
+        bool raw_dir = false;              // d still has to be normalised
 
-        while (k < TRT_RAYS_PER_PIXEL) {
-            if (new_sample) {
+        for (;;) {
+            if (fresh) {
+                if (k == TRT_RAYS_PER_PIXEL) break;
                 // primary ray of sample k, TRT.c:987-1016
                 tally.add(CTR_SAMPLES);
                 const double sx = sx0 + c_scene.sub_dx[k] * pixel_w;
                 const double sy = sy0 + c_scene.sub_dy[k] * pixel_h;
-                const d3 wx = bx * sx, wy = by * sy, wz = bz * sz;
+                const double sz = -c_scene.screen_distance;
                 d3 sp = mk3(0.0, 0.0, 0.0);
-                sp = sp + wx;
-                sp = sp + wy;
-                sp = sp + wz;
-                sp = sp - eye;              // TRT.c:1005 (origin subtracted from an untranslated vector)
-                d = unit(sp);
-                o = eye;
+                sp = sp + mk3(c_scene.bx[0] * sx, c_scene.bx[1] * sx, c_scene.bx[2] * sx);
+                sp = sp + mk3(c_scene.by[0] * sy, c_scene.by[1] * sy, c_scene.by[2] * sy);
+                sp = sp + mk3(c_scene.bz[0] * sz, c_scene.bz[1] * sz, c_scene.bz[2] * sz);
+                o = mk3(c_scene.eye[0], c_scene.eye[1], c_scene.eye[2]);
+                d = sp - o;                 // TRT.c:1005 (origin subtracted from an untranslated vector)
+                raw_dir = true;
                 sample = mk3(0.0, 0.0, 0.0);
                 bounces = 0;
                 weight = 1.0;
                 weight_sum = 0.0;
                 phase = PH_MAIN;
-                new_sample = false;
+                fresh = false;
             }
+            // (1) the one normalisation of a ray direction: primary (TRT.c:1008), reflected (1055), point-light (933)
+            if (raw_dir) d = unit(d);
 
-            // ---- the shared part: closest hit of the current ray -----------------------------
+            // (2) the one closest-hit query
             int obj, index;
             d3 hit;
+            const bool is_main = phase == PH_MAIN;
             tally.add(CTR_TRACE_CALLS);
-            if (phase == PH_MAIN) tally.add(CTR_BOUNCE_ITERS);
+            if (is_main) tally.add(CTR_BOUNCE_ITERS);
             closest_hit<COUNT, CULL>(P, o, d, obj, index, hit, tally);
             if (obj != 0) tally.add(CTR_TRACE_HITS);
-            else { tally.add(CTR_SKY_LOOKUPS); if (phase != PH_MAIN) tally.add(CTR_SKY_SKIPPED); }
+            else { tally.add(CTR_SKY_LOOKUPS); if (!is_main) tally.add(CTR_SKY_SKIPPED); }
 
-            bool shade_done = false; // true when `lit` holds the final surface colour of the main hit
-            if (phase == PH_MAIN) {
-                if (obj == 0) {
-                    // sky: TRT.c:858-867, then the tail of the bounce loop 1034-1051 with weight -> 0
-                    int face;
-                    const int texel = sky_texel_index(d, c_scene.sky_dim, face);
-                    const uchar4 t = __ldg(&P.sky[(size_t)face * (size_t)c_scene.sky_face_stride + (size_t)texel]);
-                    d3 c = mk3(s_byte_to_unit[t.x], s_byte_to_unit[t.y], s_byte_to_unit[t.z]);
-                    weight_sum += weight;
-                    c = c * weight;
-                    sample = sample + c;
-                    // sample finished
-                    if (COUNT) atomicAdd(&P.counters[CTR_BOUNCE_HIST0 + bounces], 1ull);
-                    sample = sample * (1.0 / weight_sum);   // TRT.c:1061
-                    average = average + sample;             // TRT.c:1063
-                    k++;
-                    new_sample = true;
-                    continue;
-                }
-                // surface hit: remember it, start the light loop (apply_lighting, TRT.c:894-963)
-                tally.add(CTR_LIGHTING_CALLS);
-                surf_obj = obj;
-                surf_index = index;
-                d3 n;
+            // (3) the one push-back (TRT.c:871-874); a directional light's shadow ray only needs hit / no hit
+            const bool point_shadow = !is_main && light >= num_dir;
+            d3 at = o;
+            if (obj != 0 && (is_main || point_shadow)) at = push_back(o, hit);
+
+            bool shade_done = false, sample_done = false, have_colour = false;
+            d3 colour = mk3(0.0, 0.0, 0.0);
+            if (is_main) {
+                // (4) the one normal / sky normalisation: unit(hit - centre) or unit(ground normal) on a hit
+                //     (TRT.c:878), unit(direction) once more for the cubemap lookup on a miss (TRT.c:702)
+                d3 v = d;
                 if (obj == 1) {
                     const double4 g = ldg_geom(P.sphere_geom, index);
-                    n = mk3(hit.x - g.x, hit.y - g.y, hit.z - g.z);   // TRT.c:824
-                } else {
-                    n = mk3(c_scene.ground_normal[0], c_scene.ground_normal[1], c_scene.ground_normal[2]);
+                    v = mk3(hit.x - g.x, hit.y - g.y, hit.z - g.z);   // TRT.c:824
+                } else if (obj == 2) {
+                    v = mk3(c_scene.ground_normal[0], c_scene.ground_normal[1], c_scene.ground_normal[2]);
                 }
-                const d3 at = push_back(o, hit);
-                nrm = unit(n);                                       // TRT.c:878
-                d_main = d;
-                o = at;
-                lit = mk3(0.0, 0.0, 0.0);
-                light = 0;
-                if (num_lights == 0) shade_done = true;
-                else phase = PH_SHADOW;
+                const d3 u = unit(v);
+                if (obj == 0) {
+                    // sky: TRT.c:858-867; the sample ends here
+                    int face;
+                    const int texel = sky_texel_index(u, c_scene.sky_dim, face);
+                    const uchar4 t = __ldg(&P.sky[(size_t)face * (size_t)c_scene.sky_face_stride + (size_t)texel]);
+                    colour = mk3(s_byte_to_unit[t.x], s_byte_to_unit[t.y], s_byte_to_unit[t.z]);
+                    have_colour = true;
+                    sample_done = true;
+                } else {
+                    // surface hit: remember it, start the light loop (apply_lighting, TRT.c:894-963)
+                    tally.add(CTR_LIGHTING_CALLS);
+                    surf_obj = obj;
+                    surf_index = index;
+                    nrm = u;
+                    d_main = d;
+                    o = at;
+                    lit = mk3(0.0, 0.0, 0.0);
+                    light = 0;
+                    if (num_lights == 0) shade_done = true;
+                    else phase = PH_SHADOW;
+                }
             } else {
-                // ---- a shadow ray came back: add this light's contribution ------------------
-                d3 mcol;
-                {
-                    const DevMaterial *m = (surf_obj == 1) ? &P.sphere_mat[surf_index]
-                                                           : (surf_index ? &c_scene.ground_odd : &c_scene.ground_even);
-                    mcol = mk3(m->color[0], m->color[1], m->color[2]);
-                }
-                if (light < num_dir) {
-                    if (obj == 0) {                                   // TRT.c:908-921
-                        const DevLightDir &Ld = c_scene.dir[light];
-                        const double f = fmin(dot(nrm, d), 1.0);
-                        d3 diffuse = mk3(Ld.color[0] * f, Ld.color[1] * f, Ld.color[2] * f);
-                        diffuse = hadamard(diffuse, mcol);
-                        lit = lit + diffuse;
-                    }
-                } else {
-                    bool open = (obj == 0);
-                    if (!open) {                                      // TRT.c:939-942
-                        const d3 blocker = push_back(o, hit);
-                        const d3 to_blocker = blocker - o;
+                // ---- a shadow ray came back: add this light's contribution ---------------------------
+                bool open = (obj == 0);
+                double f = 1.0;
+                const double *lc;
+                if (light < num_dir) {                                    // TRT.c:908-921
+                    lc = c_scene.dir[light].color;
+                } else {                                                  // TRT.c:939-954
+                    if (!open) {
+                        const d3 to_blocker = at - o;
                         open = light_d2 < dot(to_blocker, to_blocker);
                     }
-                    if (open) {                                       // TRT.c:945-954
-                        const DevLightPoint &Lp = c_scene.point[light - num_dir];
-                        const double f = intensity * fmin(dot(nrm, d), 1.0);
-                        d3 diffuse = mk3(Lp.color[0] * f, Lp.color[1] * f, Lp.color[2] * f);
-                        diffuse = hadamard(diffuse, mcol);
-                        lit = lit + diffuse;
-                    }
+                    lc = c_scene.point[light - num_dir].color;
+                    f = intensity;
+                }
+                if (open) {
+                    const DevMaterial *m = surface_material(P, surf_obj, surf_index);
+                    const double lambert = fmin(dot(nrm, d), 1.0);
+                    if (light >= num_dir) f = f * lambert; else f = lambert;
+                    d3 diffuse = mk3(lc[0] * f, lc[1] * f, lc[2] * f);
+                    diffuse = hadamard(diffuse, mk3(m->color[0], m->color[1], m->color[2]));
+                    lit = lit + diffuse;
                 }
                 light++;
                 if (light == num_lights) shade_done = true;
             }
 
-            if (!shade_done) {
-                // aim the shadow ray of light `light` from the surface point o
+            if (shade_done) {
+                colour.x = clampd(lit.x, 0.0, 1.0);                       // TRT.c:960
+                colour.y = clampd(lit.y, 0.0, 1.0);
+                colour.z = clampd(lit.z, 0.0, 1.0);
+                have_colour = true;
+            }
+            // (5) the one accumulate, TRT.c:1034-1035, 1051
+            if (have_colour) {
+                weight_sum += weight;
+                colour = colour * weight;
+                sample = sample + colour;
+            }
+            if (shade_done) {
+                weight *= surface_material(P, surf_obj, surf_index)->reflectivity;   // TRT.c:1041-1042
+                bounces++;
+                if (bounces < TRT_BOUNCE_LIMIT && weight > 0.00001) {      // loop condition, TRT.c:1018
+                    // (6) the one reflect, TRT.c:627-633; normalised at the top of the next trip
+                    const double dn = dot(d_main, nrm);
+                    d = mk3(d_main.x - 2.0 * dn * nrm.x, d_main.y - 2.0 * dn * nrm.y, d_main.z - 2.0 * dn * nrm.z);
+                    raw_dir = true;
+                    phase = PH_MAIN;                                      // the origin o already is the surface point
+                } else {
+                    sample_done = true;
+                }
+            } else if (!sample_done) {
+                // (7) the one shadow-ray setup: aim at light `light` from the surface point o
                 if (light < num_dir) {
                     const DevLightDir &Ld = c_scene.dir[light];
-                    d = mk3(Ld.L[0], Ld.L[1], Ld.L[2]);
+                    d = mk3(Ld.L[0], Ld.L[1], Ld.L[2]);                    // unit(-direction), host-evaluated (TRT.c:903-904)
+                    raw_dir = false;
                 } else {
                     const DevLightPoint &Lp = c_scene.point[light - num_dir];
-                    d3 L = mk3(Lp.pos[0] - o.x, Lp.pos[1] - o.y, Lp.pos[2] - o.z);   // TRT.c:929
-                    light_d2 = dot(L, L);
-                    intensity = clampd(Lp.intensity / light_d2, 0.0, 1.0);           // TRT.c:931
-                    d = unit(L);
+                    d = mk3(Lp.pos[0] - o.x, Lp.pos[1] - o.y, Lp.pos[2] - o.z);   // TRT.c:929
+                    light_d2 = dot(d, d);
+                    intensity = clampd(Lp.intensity / light_d2, 0.0, 1.0);         // TRT.c:931
+                    raw_dir = true;
                 }
-                continue;
             }
-
-            // ---- surface colour complete: tail of the bounce loop, TRT.c:1034-1056 --------------
-            lit.x = clampd(lit.x, 0.0, 1.0);                          // TRT.c:960
-            lit.y = clampd(lit.y, 0.0, 1.0);
-            lit.z = clampd(lit.z, 0.0, 1.0);
-            double reflectivity;
-            {
-                const DevMaterial *m = (surf_obj == 1) ? &P.sphere_mat[surf_index]
-                                                       : (surf_index ? &c_scene.ground_odd : &c_scene.ground_even);
-                reflectivity = m->reflectivity;
-            }
-            weight_sum += weight;
-            lit = lit * weight;
-            weight *= reflectivity;
-            bounces++;
-            sample = sample + lit;
-            if (bounces < TRT_BOUNCE_LIMIT && weight > 0.00001) {     // loop condition, TRT.c:1018
-                const double dn = dot(d_main, nrm);                   // reflect_vector, TRT.c:627-633
-                d3 r = mk3(d_main.x - 2.0 * dn * nrm.x, d_main.y - 2.0 * dn * nrm.y, d_main.z - 2.0 * dn * nrm.z);
-                d = unit(r);
-                phase = PH_MAIN;                                      // origin o already is the surface point
-            } else {
+            if (sample_done) {
                 if (COUNT) atomicAdd(&P.counters[CTR_BOUNCE_HIST0 + bounces], 1ull);
-                sample = sample * (1.0 / weight_sum);
-                average = average + sample;
+                sample = sample * (1.0 / weight_sum);                     // TRT.c:1061
+                average = average + sample;                               // TRT.c:1063
                 k++;
-                new_sample = true;
+                fresh = true;
             }
         }
 
-        average = average * (1.0 / TRT_RAYS_PER_PIXEL);               // TRT.c:1065
+        average = average * (1.0 / TRT_RAYS_PER_PIXEL);                   // TRT.c:1065
         const size_t pix = (size_t)brow * (size_t)P.width + (size_t)col;
         if (P.pixels) {
             P.pixels[pix * 3 + 0] = average.x;
@@ -489,7 +534,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_render(const RenderParams P)
 __global__ void k_probe_trace(const RenderParams P, const double *__restrict__ rays, int n, double *__restrict__ out)
 {
     __shared__ double s_byte_to_unit[256];
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_byte_to_unit[k] = (double)k / 255.0;
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_byte_to_unit[k] = P.byte_to_unit[k];
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -498,14 +543,15 @@ __global__ void k_probe_trace(const RenderParams P, const double *__restrict__ r
     const Tally<false> tally{nullptr};
     int obj, index;
     d3 hit;
-    closest_hit<false, true>(P, o, d, obj, index, hit, tally);
+    if (c_scene.filter_in_const) closest_hit<false, 1>(P, o, d, obj, index, hit, tally);
+    else closest_hit<false, 2>(P, o, d, obj, index, hit, tally);
     d3 point, normal, colour;
     double reflectivity = 0.0;
     if (obj == 0) {
         point = o;
         normal = d;
         int face;
-        const int texel = sky_texel_index(d, c_scene.sky_dim, face);
+        const int texel = sky_texel_index(unit(d), c_scene.sky_dim, face);
         const uchar4 t = __ldg(&P.sky[(size_t)face * (size_t)c_scene.sky_face_stride + (size_t)texel]);
         colour = mk3(s_byte_to_unit[t.x], s_byte_to_unit[t.y], s_byte_to_unit[t.z]);
     } else {
@@ -538,7 +584,7 @@ __global__ void k_probe_sky(const RenderParams P, const double *__restrict__ dir
     if (i >= n) return;
     const d3 d = mk3(dirs[i * 3 + 0], dirs[i * 3 + 1], dirs[i * 3 + 2]);
     int face;
-    const int texel = sky_texel_index(d, c_scene.sky_dim, face);
+    const int texel = sky_texel_index(unit(d), c_scene.sky_dim, face);
     const uchar4 t = __ldg(&P.sky[(size_t)face * (size_t)c_scene.sky_face_stride + (size_t)texel]);
     out[i * 5 + 0] = face;
     out[i * 5 + 1] = texel;
@@ -588,6 +634,17 @@ __global__ void k_selftest_division(unsigned long long seed, int iters, unsigned
             const unsigned long long m = (mix64(state) & 1ull) ? 0x000FFFFFFFFFFFFFull : (mix64(state) & 0xFull);
             b = __longlong_as_double((long long)(((unsigned long long)(e + 1023) << 52) | m));
         }
+        if (mode == 0 || mode == 2) {
+            // the vector form used by the renderer: unit() against sqrt + three IEEE divisions
+            const d3 v = mode == 0 ? mk3(a[0], a[1], a[2]) : mk3(a[0] * 1e-30, a[2] * 1e-250, a[1]);
+            const d3 u = unit(v);
+            const double len = sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+            d3 w = v;
+            if (len > 0.0001) { w.x = __ddiv_rn(v.x, len); w.y = __ddiv_rn(v.y, len); w.z = __ddiv_rn(v.z, len); }
+            if (__double_as_longlong(u.x) != __double_as_longlong(w.x) && !(u.x != u.x && w.x != w.x)) bad++;
+            if (__double_as_longlong(u.y) != __double_as_longlong(w.y) && !(u.y != u.y && w.y != w.y)) bad++;
+            if (__double_as_longlong(u.z) != __double_as_longlong(w.z) && !(u.z != u.z && w.z != w.z)) bad++;
+        }
         const Reciprocal inv = reciprocal_of(b);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -614,7 +671,7 @@ static void die(cudaError_t e, const char *file, int line)
 void upload_scene_constants(const DevScene &scene, const float4 *cull, int count, cudaStream_t stream)
 {
     CK(cudaMemcpyToSymbolAsync(c_scene, &scene, sizeof(DevScene), 0, cudaMemcpyHostToDevice, stream));
-    if (cull && count > 0 && count <= TRT_MAX_CONST_SPHERES)
+    if (cull && count > 0 && count <= TRT_MAX_CONST_SPHERES + 2)
         CK(cudaMemcpyToSymbolAsync(c_sphere_cull, cull, sizeof(float4) * (size_t)count, 0, cudaMemcpyHostToDevice, stream));
 }
 
@@ -623,13 +680,13 @@ int render_ctas_per_sm()
     static int cached = 0;
     if (!cached) {
         int n = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_render<false, true>, CTA_THREADS, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_render<false, 1>, CTA_THREADS, 0));
         cached = n > 0 ? n : 1;
     }
     return cached;
 }
 
-void launch_render(const RenderParams &p, bool count, bool cull, int num_sms, cudaStream_t stream)
+void launch_render(const RenderParams &p, bool count, int cull, int num_sms, cudaStream_t stream)
 {
     CK(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), stream));
     const int band_rows = p.row1 - p.row0;
@@ -641,11 +698,13 @@ void launch_render(const RenderParams &p, bool count, bool cull, int num_sms, cu
     if (grid < 1) grid = 1;
     dim3 g((unsigned)grid), b(CTA_THREADS);
     if (count) {
-        if (cull) k_render<true, true><<<g, b, 0, stream>>>(p);
-        else k_render<true, false><<<g, b, 0, stream>>>(p);
+        if (cull == 1) k_render<true, 1><<<g, b, 0, stream>>>(p);
+        else if (cull == 2) k_render<true, 2><<<g, b, 0, stream>>>(p);
+        else k_render<true, 0><<<g, b, 0, stream>>>(p);
     } else {
-        if (cull) k_render<false, true><<<g, b, 0, stream>>>(p);
-        else k_render<false, false><<<g, b, 0, stream>>>(p);
+        if (cull == 1) k_render<false, 1><<<g, b, 0, stream>>>(p);
+        else if (cull == 2) k_render<false, 2><<<g, b, 0, stream>>>(p);
+        else k_render<false, 0><<<g, b, 0, stream>>>(p);
     }
     CK(cudaGetLastError());
 }

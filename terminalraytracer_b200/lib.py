@@ -9,7 +9,8 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtrt_b200.so")
+# TRT_B200_LIB selects an experiment build of the same library (scripts/ only); the product is libtrt_b200.so
+LIB_PATH = os.path.join(_HERE, os.environ.get("TRT_B200_LIB", "libtrt_b200.so"))
 
 # name -> (restype, argtypes); mirrors include/trt_b200.h one to one
 SIGNATURES = {
