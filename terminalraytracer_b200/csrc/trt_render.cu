@@ -239,6 +239,7 @@ __device__ __forceinline__ void closest_hit(const RenderParams &P, const d3 &o, 
             // The records are padded to an even count (pad records are masked off below), so the loop
             // needs no remainder handling: two independent tests per trip.
             unsigned int survivors = 0;
+#pragma unroll 1
             for (int j = 0; j < cnt; j += 2) {
                 const float4 g0 = CULL == 1 ? c_sphere_cull[base + j] : __ldg(&P.sphere_cull[base + j]);
                 const float4 g1 = CULL == 1 ? c_sphere_cull[base + j + 1] : __ldg(&P.sphere_cull[base + j + 1]);
@@ -330,6 +331,9 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
     const double pixel_h = sh / P.height;  // TRT.c:982
     const int num_dir = c_scene.num_dir;
     const int num_lights = num_dir + c_scene.num_point;
+    // (double)col / (double)width and (double)row / (double)height (TRT.c:987-988) through shared reciprocals:
+    // numerators are integers >= 1 (0 is special-cased), far inside the fast path of the IEEE division
+    const Reciprocal inv_w = reciprocal_of((double)P.width), inv_h = reciprocal_of((double)P.height);
 
     for (;;) {
         if (lane == 0) s_tile[warp] = atomicAdd(P.tile_counter, 1u);
@@ -345,8 +349,10 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
         tally.add(CTR_PIXELS);
 
         // per-pixel part of the primary ray, TRT.c:987-988
-        const double sx0 = (((double)col / (double)P.width) * sw - sw / 2.0);
-        const double sy0 = -(((double)row / (double)P.height) * sh - sh / 2.0);
+        const double fx = col ? div_by_unchecked((double)col, inv_w) : 0.0;
+        const double fy = row ? div_by_unchecked((double)row, inv_h) : 0.0;
+        const double sx0 = (fx * sw - sw / 2.0);
+        const double sy0 = -(fy * sh - sh / 2.0);
 
         d3 average = mk3(0.0, 0.0, 0.0);
         // ---- per-lane ray state ------------------------------------------------------------------
