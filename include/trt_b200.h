@@ -100,6 +100,11 @@ int trt_encode_rows_quant_device(const unsigned char *d_quant, int width, int ro
  * width x height stream (TRT.c:1102, 1104, 1130). */
 int trt_stream_frame_device(char *d_stream, int width, int height);
 
+/* Load-balancing pre-pass for row-band sharding: renders the scene at 1/8 resolution with the same camera and
+ * returns, for every row of the width x height frame, an estimate of its cost (closest-hit queries).  Deterministic,
+ * so every rank that calls it derives the same bands (terminalraytracer_b200/sharding.py, row_bands(weights=...)). */
+int trt_estimate_row_costs(const trt_Scene *scene, int width, int height, double *cost_per_row);
+
 /* Same render as trt_render_rows_device, additionally accumulating the work counters of the
  * algorithmic flop model into counters[TRT_NUM_COUNTERS] (host array). Synchronous. */
 #define TRT_NUM_COUNTERS 32

@@ -233,6 +233,7 @@ RenderParams make_params(int width, int height, int row0, int row1, double *d_pi
     p.sky = (const uchar4 *)g.sky.p;
     p.tile_counter = (unsigned int *)g.tile_counter.p;
     p.counters = count ? (unsigned long long *)g.counters.p : nullptr;
+    p.row_cost = nullptr;
     return p;
 }
 
@@ -409,6 +410,35 @@ int trt_count_rows_device(int width, int height, int row0, int row1, double *d_p
     launch_render(p, true, cull_mode(), g.num_sms, g.stream);
     CK(cudaMemcpyAsync(counters, g.counters.p, sizeof(unsigned long long) * TRT_NUM_COUNTERS, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int trt_estimate_row_costs(const trt_Scene *scene, int width, int height, double *cost_per_row)
+{
+    require_init("trt_estimate_row_costs");
+    if (width <= 0 || height <= 0) return 0;
+    // Same camera, 1/8 of the rows and columns (at least 64 x 32): per-row closest-hit counts of the small frame
+    // are spread over the rows of the big one.  Sky rows cost ~1 query per sample, sphere/ground rows 5+.
+    int sw = width / 8, sh = height / 8;
+    if (sw < 64) sw = width < 64 ? width : 64;
+    if (sh < 32) sh = height < 32 ? height : 32;
+    upload_scene(scene);
+    Buffer d_cost, d_quant;
+    d_cost.reserve(sizeof(unsigned int) * (size_t)sh);
+    d_quant.reserve(sizeof(uchar4) * (size_t)sw * (size_t)sh);
+    CK(cudaMemsetAsync(d_cost.p, 0, sizeof(unsigned int) * (size_t)sh, g.stream));
+    RenderParams p = make_params(sw, sh, 0, sh, nullptr, (uchar4 *)d_quant.p, false);
+    p.row_cost = (unsigned int *)d_cost.p;
+    launch_render(p, false, cull_mode(), g.num_sms, g.stream);
+    std::vector<unsigned int> cost((size_t)sh);
+    CK(cudaMemcpyAsync(cost.data(), d_cost.p, sizeof(unsigned int) * (size_t)sh, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    d_cost.release();
+    d_quant.release();
+    for (int r = 0; r < height; r++) {
+        const int sr = (int)(((long long)r * sh) / height);
+        cost_per_row[r] = (double)cost[(size_t)sr] + 1.0;
+    }
     return 0;
 }
 

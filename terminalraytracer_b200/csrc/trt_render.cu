@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
         d3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), d_main = d, nrm = d, lit = d, sample = d;
         bool fresh = true;                 // start the next sample of this pixel
         bool raw_dir = false;              // d still has to be normalised
+        unsigned int trips = 0;            // closest-hit queries of this pixel (cost estimate for band balancing)
 
         for (;;) {
             if (fresh) {
@@ -392,6 +393,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
             if (raw_dir) d = unit(d);
 
             // (2) the one closest-hit query
+            trips++;
             int obj, index;
             d3 hit;
             const bool is_main = phase == PH_MAIN;
@@ -514,6 +516,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
             }
         }
 
+        if (P.row_cost) atomicAdd(&P.row_cost[brow], trips);
         average = average * (1.0 / TRT_RAYS_PER_PIXEL);                   // TRT.c:1065
         const size_t pix = (size_t)brow * (size_t)P.width + (size_t)col;
         if (P.pixels) {

@@ -32,6 +32,7 @@ SIGNATURES = {
     "trt_render_rows_quant_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "trt_encode_rows_quant_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "trt_stream_frame_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "trt_estimate_row_costs": (C.c_int, [C.POINTER(abi.Scene), C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "trt_count_rows_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_longlong)]),
     "trt_model_flops": (C.c_double, [C.POINTER(C.c_longlong)]),
     "trt_probe_trace_ray": (C.c_int, [C.POINTER(abi.Scene), C.c_void_p, C.c_int, C.c_void_p]),

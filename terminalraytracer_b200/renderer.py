@@ -83,6 +83,12 @@ class Renderer:
     def stream_frame(self, d_stream_ptr, width, height):
         self.L.trt_stream_frame_device(d_stream_ptr, width, height)
 
+    def estimate_row_costs(self, scene):
+        """Per-row cost estimate of scene.width x scene.height (1/8-resolution pre-pass on the GPU)."""
+        out = (C.c_double * scene.height)()
+        self.L.trt_estimate_row_costs(C.byref(scene.c), scene.width, scene.height, out)
+        return list(out)
+
     def count_rows(self, width, height, row0, row1, d_pixels_ptr=None):
         ctr = (C.c_longlong * abi.NUM_COUNTERS)()
         self.L.trt_count_rows_device(width, height, row0, row1, d_pixels_ptr, ctr)

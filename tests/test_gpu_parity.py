@@ -267,6 +267,34 @@ def test_gpu_row_bands_reassemble_full_frame_and_stream(renderer, orc):
         renderer.use_stream(None)
 
 
+def test_gpu_cost_weighted_bands_same_bytes(renderer, orc):
+    """the load-balancing pre-pass only moves band boundaries: the reassembled stream is unchanged"""
+    import torch
+    w, h = 128, 96
+    sc = S.SceneData(w, h, S.synthetic_cubemap("uv_gradient", 64)).set_time(3.7)
+    renderer.upload_skybox(sc.skybox)
+    costs = renderer.estimate_row_costs(sc)
+    assert len(costs) == h and min(costs) >= 1.0
+    assert sum(costs[h // 2:]) > sum(costs[:h // 2])      # ground + reflections below, sky above
+    want = U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc))
+    renderer.use_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        renderer.set_scene(sc)
+        bands = sharding.row_bands(h, 4, costs)
+        assert bands != sharding.row_bands(h, 4)
+        stream = torch.zeros(abi.stream_bytes(w, h), dtype=torch.uint8, device="cuda")
+        renderer.stream_frame(stream.data_ptr(), w, h)
+        for (r0, r1) in bands:
+            if r1 > r0:
+                quant = torch.zeros((r1 - r0) * w * 4, dtype=torch.uint8, device="cuda")
+                renderer.render_rows_quant(w, h, r0, r1, quant.data_ptr())
+                renderer.encode_rows_quant(quant.data_ptr(), w, r1 - r0, stream.data_ptr(), sharding.band_byte_range(w, (r0, r1))[0])
+        torch.cuda.synchronize()
+        assert np.array_equal(stream.cpu().numpy(), want)
+    finally:
+        renderer.use_stream(None)
+
+
 def test_gpu_counters_match_oracle(renderer, orc):
     w, h = 96, 54
     sc = S.SceneData(w, h, S.synthetic_cubemap("colors", 256)).set_time(3.7)
