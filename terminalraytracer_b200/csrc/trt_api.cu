@@ -64,6 +64,9 @@ struct Context {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // device-to-host copies of finished row chunks (trt_render_ansi)
+    static constexpr int MAX_CHUNKS = 8;
+    cudaEvent_t chunk_ev[MAX_CHUNKS][3] = {};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_render_ms = 0.f, last_encode_ms = 0.f;
     // scene
@@ -260,7 +263,10 @@ int trt_init(int device)
     CK(cudaDeviceGetAttribute(&g.num_sms, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
     g.stream = g.own_stream;
+    CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
     for (auto &ev : g.ev) CK(cudaEventCreate(&ev));
+    for (auto &row : g.chunk_ev)
+        for (auto &ev : row) CK(cudaEventCreate(&ev));
     g.tile_counter.reserve(256);
     g.counters.reserve(sizeof(unsigned long long) * TRT_NUM_COUNTERS);
     {
@@ -296,6 +302,13 @@ void trt_shutdown(void)
         if (ev) cudaEventDestroy(ev);
         ev = nullptr;
     }
+    for (auto &row : g.chunk_ev)
+        for (auto &ev : row) {
+            if (ev) cudaEventDestroy(ev);
+            ev = nullptr;
+        }
+    cudaStreamDestroy(g.copy_stream);
+    g.copy_stream = nullptr;
     cudaStreamDestroy(g.own_stream);
     g.stream = g.own_stream = nullptr;
     g.have_scene = false;
@@ -570,17 +583,44 @@ size_t trt_render_ansi(const trt_Scene *scene, int width, int height, char *out,
     upload_scene(scene);
     g.quant.reserve(sizeof(uchar4) * (size_t)width * (size_t)height);
     g.bytes.reserve(total + 16);
-    RenderParams p = make_params(width, height, 0, height, nullptr, (uchar4 *)g.quant.p, false);
-    CK(cudaEventRecord(g.ev[0], g.stream));
-    launch_render(p, false, cull_mode(), g.num_sms, g.stream);
-    CK(cudaEventRecord(g.ev[1], g.stream));
+    // Big frames are rendered as up to MAX_CHUNKS row chunks so that the device-to-host copy of a chunk's
+    // bytes (829 MB per 7680x4320 frame: PCIe time comparable to K1's) overlaps the rendering of the next one.
+    // All kernels are enqueued first; the copies run on a second stream, each behind its chunk's event, so the
+    // overlap also happens when `out` is pageable memory (where cudaMemcpyAsync blocks the host).
+    const size_t pixels = (size_t)width * (size_t)height;
+    int chunks = (int)(pixels >> 21);          // ~2 Mpixel (a few ms of K1) per chunk
+    if (chunks > Context::MAX_CHUNKS) chunks = Context::MAX_CHUNKS;
+    if (chunks > height) chunks = height;
+    if (chunks < 1) chunks = 1;
+    const size_t row_bytes = TRT_ROW_BYTES(width);
     launch_stream_frame((char *)g.bytes.p, width, height, g.stream);
-    launch_encode_quant((const uchar4 *)g.quant.p, width, height, (char *)g.bytes.p, TRT_HOME_BYTES, g.stream);
-    CK(cudaEventRecord(g.ev[3], g.stream));
-    CK(cudaMemcpyAsync(out, g.bytes.p, total, cudaMemcpyDeviceToHost, g.stream));
+    for (int c = 0; c < chunks; c++) {
+        const int r0 = (int)((long long)height * c / chunks), r1 = (int)((long long)height * (c + 1) / chunks);
+        RenderParams p = make_params(width, height, r0, r1, nullptr, (uchar4 *)g.quant.p + (size_t)r0 * (size_t)width, false);
+        CK(cudaEventRecord(g.chunk_ev[c][0], g.stream));
+        launch_render(p, false, cull_mode(), g.num_sms, g.stream);
+        CK(cudaEventRecord(g.chunk_ev[c][1], g.stream));
+        launch_encode_quant((const uchar4 *)g.quant.p + (size_t)r0 * (size_t)width, width, r1 - r0, (char *)g.bytes.p,
+                            TRT_HOME_BYTES + (size_t)r0 * row_bytes, g.stream);
+        CK(cudaEventRecord(g.chunk_ev[c][2], g.stream));
+    }
+    for (int c = 0; c < chunks; c++) {
+        const int r0 = (int)((long long)height * c / chunks), r1 = (int)((long long)height * (c + 1) / chunks);
+        const size_t b0 = c == 0 ? 0 : TRT_HOME_BYTES + (size_t)r0 * row_bytes;
+        const size_t b1 = c == chunks - 1 ? total : TRT_HOME_BYTES + (size_t)r1 * row_bytes;
+        CK(cudaStreamWaitEvent(g.copy_stream, g.chunk_ev[c][2], 0));
+        CK(cudaMemcpyAsync(out + b0, (const char *)g.bytes.p + b0, b1 - b0, cudaMemcpyDeviceToHost, g.copy_stream));
+    }
+    CK(cudaStreamSynchronize(g.copy_stream));
     CK(cudaStreamSynchronize(g.stream));
-    CK(cudaEventElapsedTime(&g.last_render_ms, g.ev[0], g.ev[1]));
-    CK(cudaEventElapsedTime(&g.last_encode_ms, g.ev[1], g.ev[3]));
+    g.last_render_ms = g.last_encode_ms = 0.f;
+    for (int c = 0; c < chunks; c++) {
+        float k1 = 0.f, k2 = 0.f;
+        CK(cudaEventElapsedTime(&k1, g.chunk_ev[c][0], g.chunk_ev[c][1]));
+        CK(cudaEventElapsedTime(&k2, g.chunk_ev[c][1], g.chunk_ev[c][2]));
+        g.last_render_ms += k1;
+        g.last_encode_ms += k2;
+    }
     return total;
 }
 

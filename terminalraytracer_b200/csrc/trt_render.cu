@@ -82,7 +82,7 @@ __device__ __forceinline__ int sky_texel_index(const d3 &dir, int dim, int &face
         }
     }
     // scale_by == best_t (sum of dir (*) axis), TRT.c:717-719
-    const double s = 1.0 / best_t;
+    const double s = ieee_div(1.0, best_t);
     const double px = dir.x * s, py = dir.y * s, pz = dir.z * s;
     // orthogonal component * 0.5, then dots with axes (best+2)%6 and (best+4)%6 (TRT.c:720-727)
     double u, v;
@@ -187,7 +187,7 @@ __device__ __forceinline__ void sphere_exact(const double4 g, int i, const d3 &o
     const double disc = b * b - four_a * c;  // (4.0*a)*c, scaling by 4 is exact
     if (!(disc < 0.0)) {                     // TRT.c:651
         tally.add(CTR_SPHERE_DISC_OK);
-        const double t0 = (-b - sqrt(disc)) / two_a;
+        const double t0 = ieee_div(-b - sqrt(disc), two_a);
         if (t0 > 0.0) {
             tally.add(CTR_SPHERE_T0_POS);
             const d3 p = mk3(o.x + t0 * d.x, o.y + t0 * d.y, o.z + t0 * d.z);
@@ -273,7 +273,7 @@ __device__ __forceinline__ void closest_hit(const RenderParams &P, const d3 &o, 
     if (fabs(denom) > 0.00001) {
         tally.add(CTR_PLANE_DENOM_OK);
         const d3 to_plane = mk3(c_scene.ground_point[0] - o.x, c_scene.ground_point[1] - o.y, c_scene.ground_point[2] - o.z);
-        const double t = dot(to_plane, gn) / denom;
+        const double t = ieee_div(dot(to_plane, gn), denom);
         if (t > 0.00001) {
             tally.add(CTR_PLANE_T_POS);
             const d3 p = mk3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
@@ -503,13 +503,13 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                     const DevLightPoint &Lp = c_scene.point[light - num_dir];
                     d = mk3(Lp.pos[0] - o.x, Lp.pos[1] - o.y, Lp.pos[2] - o.z);   // TRT.c:929
                     light_d2 = dot(d, d);
-                    intensity = clampd(Lp.intensity / light_d2, 0.0, 1.0);         // TRT.c:931
+                    intensity = clampd(ieee_div(Lp.intensity, light_d2), 0.0, 1.0);         // TRT.c:931
                     raw_dir = true;
                 }
             }
             if (sample_done) {
                 if (COUNT) atomicAdd(&P.counters[CTR_BOUNCE_HIST0 + bounces], 1ull);
-                sample = sample * (1.0 / weight_sum);                     // TRT.c:1061
+                sample = sample * ieee_div(1.0, weight_sum);                     // TRT.c:1061
                 average = average + sample;                               // TRT.c:1063
                 k++;
                 fresh = true;
