@@ -74,7 +74,7 @@ struct Context {
     bool have_scene = false;
     bool cull_allowed = true;   // trt_set_cull(); the FP32 miss test can be switched off for A/B runs
     bool cull = true;           // cull_allowed && this scene's magnitudes are inside the bound's range
-    Buffer sphere_geom, sphere_cull, sphere_mat;
+    Buffer sphere_geom, sphere_cull, sphere_mat, sphere_prim;
     // skybox
     Buffer sky;
     int sky_dim = -1, sky_face_stride = 0;
@@ -113,11 +113,25 @@ void negated_unit(const trt_Vector &dir, double out[3])
 }
 
 // smallest float >= v
-float float_round_up(double v)
+float float_round_up(double v) { return trt_cert_round_up(v); }
+
+// dot_product with the reference's grouping (TRT.c:461-464), every product and sum rounded once
+double dot3_ref(const double a[3], const double b[3])
 {
-    float f = (float)v;
-    if ((double)f < v) f = nextafterf(f, INFINITY);
-    return f;
+    volatile double xx = a[0] * b[0], yy = a[1] * b[1], zz = a[2] * b[2];
+    volatile double s = xx + yy;
+    s = s + zz;
+    return s;
+}
+
+// normalize_vector, TRT.c:439-450
+void unit3_ref(const double v[3], double out[3])
+{
+    const double len = sqrt(dot3_ref(v, v));
+    for (int k = 0; k < 3; k++) {
+        volatile double q = len > 0.0001 ? v[k] / len : v[k];
+        out[k] = q;
+    }
 }
 
 void set_material(DevMaterial &m, const trt_Material &src)
@@ -152,6 +166,40 @@ void upload_scene(const trt_Scene *scene)
         s.ground_normal_f[k] = (float)s.ground_normal[k];
     }
     if (!(fabs(s.ground_point[0]) + fabs(s.ground_point[1]) + fabs(s.ground_point[2]) < 1e12)) ground_in_range = false;
+    unit3_ref(s.ground_normal, s.ground_unit_normal);
+    {
+        // rays leaving the eye: numerator of TRT.c:685 and its robust sign
+        double to_plane[3];
+        for (int k = 0; k < 3; k++) {
+            volatile double d = s.ground_point[k] - s.eye[k];
+            to_plane[k] = d;
+        }
+        s.prim_num = dot3_ref(to_plane, s.ground_normal);
+        double scale = 0.0, nl1 = 0.0;
+        for (int k = 0; k < 3; k++) {
+            scale += fabs(s.ground_point[k]) + fabs(s.eye[k]);
+            nl1 += fabs(s.ground_normal[k]);
+        }
+        const double tol = 1e-9 * scale * nl1;
+        s.prim_num_sign = s.prim_num < -tol ? -1 : (s.prim_num > tol ? 1 : 0);
+        s.ground_normal_l1 = float_round_up(nl1);
+        // camera in float for the tile certificates (trt_cert.h)
+        trt_cert_camera &cf = s.cam_f;
+        cf.ex = (float)s.eye[0]; cf.ey = (float)s.eye[1]; cf.ez = (float)s.eye[2];
+        for (int k = 0; k < 3; k++) {
+            cf.bx[k] = (float)s.bx[k];
+            cf.by[k] = (float)s.by[k];
+            cf.bz[k] = (float)s.bz[k];
+        }
+        cf.nbx = float_round_up(sqrt(dot3_ref(s.bx, s.bx)) * (1.0 + 1e-6));
+        cf.nby = float_round_up(sqrt(dot3_ref(s.by, s.by)) * (1.0 + 1e-6));
+        cf.sw = (float)s.screen_width;
+        cf.sh = (float)s.screen_height;
+        cf.dist = (float)s.screen_distance;
+        s.eye_l1 = float_round_up((fabs(s.eye[0]) + fabs(s.eye[1]) + fabs(s.eye[2])) * (1.0 + 1e-6));
+        if (!(fabs(s.eye[0]) + fabs(s.eye[1]) + fabs(s.eye[2]) < 1e12) || !(fabs(s.screen_width) + fabs(s.screen_height) + fabs(s.screen_distance) < 1e12))
+            ground_in_range = false;
+    }
     set_material(s.ground_even, scene->ground.even_material);
     set_material(s.ground_odd, scene->ground.odd_material);
     s.num_dir = scene->num_directional_lights;
@@ -161,12 +209,41 @@ void upload_scene(const trt_Scene *scene)
         s.dir[i].color[0] = scene->directional_lights[i].color.x;
         s.dir[i].color[1] = scene->directional_lights[i].color.y;
         s.dir[i].color[2] = scene->directional_lights[i].color.z;
+        s.dir[i].plane_denom = dot3_ref(s.dir[i].L, s.ground_normal);      // TRT.c:681 for this light's shadow rays
+        s.dir[i].plane_possible = fabs(s.dir[i].plane_denom) > 0.00001 ? 1 : 0;
+        for (int k = 0; k < 3; k++) s.dir[i].Lf[k] = (float)s.dir[i].L[k];
     }
+    double light_l1 = 0.0;
     for (int i = 0; i < s.num_point; i++) {
         const trt_PointLight &p = scene->point_lights[i];
         s.point[i].pos[0] = p.position.x; s.point[i].pos[1] = p.position.y; s.point[i].pos[2] = p.position.z;
         s.point[i].color[0] = p.color.x; s.point[i].color[1] = p.color.y; s.point[i].color[2] = p.color.z;
         s.point[i].intensity = p.intensity;
+        double rel[3], l1 = 0.0;
+        for (int k = 0; k < 3; k++) {
+            rel[k] = s.point[i].pos[k] - s.ground_point[k];
+            s.point[i].pos_f[k] = (float)s.point[i].pos[k];
+            l1 += fabs(s.point[i].pos[k]);
+        }
+        s.point[i].height = dot3_ref(rel, s.ground_normal);
+        s.point[i].pos_l1 = float_round_up(l1 * (1.0 + 1e-6));
+        if (!(l1 < 1e12)) ground_in_range = false;
+        if (l1 > light_l1) light_l1 = l1;
+    }
+    {
+        double gl1 = 0.0;
+        for (int k = 0; k < 3; k++) gl1 += fabs(s.ground_point[k]);
+        s.ground_margin = sqrt(dot3_ref(s.ground_normal, s.ground_normal)) * (1e-4 + 1e-9 * (gl1 + light_l1));
+    }
+    {
+        double mx = 0.0, my = 0.0, dx[TRT_RAYS_PER_PIXEL], dy[TRT_RAYS_PER_PIXEL];
+        trt_subpixel_offsets(dx, dy);
+        for (int k = 0; k < TRT_RAYS_PER_PIXEL; k++) {
+            if (dx[k] > mx) mx = dx[k];
+            if (dy[k] > my) my = dy[k];
+        }
+        s.cam_f.off_x = float_round_up(mx);
+        s.cam_f.off_y = float_round_up(my);
     }
     s.num_spheres = scene->num_spheres;
     s.filter_in_const = s.num_spheres <= TRT_MAX_CONST_SPHERES ? 1 : 0;
@@ -176,6 +253,7 @@ void upload_scene(const trt_Scene *scene)
 
     const int n = s.num_spheres;
     std::vector<double4> geom((size_t)(n > 0 ? n : 1));
+    std::vector<double4> prim((size_t)(n > 0 ? n : 1));
     std::vector<DevMaterial> mats((size_t)(n > 0 ? n : 1));
     std::vector<float4> cull((size_t)n + 2, make_float4(0.f, 0.f, 0.f, 0.f));   // padded to an even count (+1 spare)
     bool in_range = true;       // magnitudes for which the FP32 cull's error bound was derived
@@ -184,14 +262,25 @@ void upload_scene(const trt_Scene *scene)
         const trt_Sphere &sp = scene->spheres[i];
         volatile double r2 = sp.radius * sp.radius;   // TRT.c:648, a single rounded product
         geom[i] = make_double4(sp.center.x, sp.center.y, sp.center.z, r2);
+        {
+            // oc = origin - centre and c = oc.oc - r*r of TRT.c:640-648 for rays leaving the eye
+            double oc[3];
+            const double ctr[3] = {sp.center.x, sp.center.y, sp.center.z};
+            for (int k = 0; k < 3; k++) {
+                volatile double d = s.eye[k] - ctr[k];
+                oc[k] = d;
+            }
+            volatile double c = dot3_ref(oc, oc) - r2;
+            prim[i] = make_double4(oc[0], oc[1], oc[2], c);
+        }
         set_material(mats[i], sp.material);
         // FP32 cull record: centre rounded to nearest, radius padded and rounded UP (trt_render.cu, sphere_cull)
         const double l1 = fabs(sp.center.x) + fabs(sp.center.y) + fabs(sp.center.z);
         const double r = sqrt((double)r2);
         if (!(l1 < 1e12) || !(r < 1e12) || (r != 0.0 && !(r > 1e-12))) in_range = false;
         if (l1 > centre_l1) centre_l1 = l1;
-        cull[i] = make_float4((float)sp.center.x, (float)sp.center.y, (float)sp.center.z,
-                              float_round_up(r * (1.0 + 1.0 / 1048576.0)));
+        cull[i] = make_float4((float)sp.center.x, (float)sp.center.y, (float)sp.center.z, trt_cert_pad_radius(sp.radius));
+        (void)r;
     }
     g.cull = g.cull_allowed && in_range && ground_in_range;
     s.filter_enabled = g.cull ? 1 : 0;
@@ -199,6 +288,8 @@ void upload_scene(const trt_Scene *scene)
     g.sphere_geom.reserve(sizeof(double4) * geom.size());
     g.sphere_mat.reserve(sizeof(DevMaterial) * mats.size());
     g.sphere_cull.reserve(sizeof(float4) * cull.size());
+    g.sphere_prim.reserve(sizeof(double4) * prim.size());
+    CK(cudaMemcpyAsync(g.sphere_prim.p, prim.data(), sizeof(double4) * prim.size(), cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(g.sphere_cull.p, cull.data(), sizeof(float4) * cull.size(), cudaMemcpyHostToDevice, g.stream));
     // The vectors above die at the end of this function, so these copies must complete before it
     // returns: plain (staged) cudaMemcpyAsync from pageable memory is synchronous w.r.t. the host buffer.
@@ -231,6 +322,7 @@ RenderParams make_params(int width, int height, int row0, int row1, double *d_pi
     p.quant = d_quant;
     p.sphere_geom = (const double4 *)g.sphere_geom.p;
     p.sphere_cull = (const float4 *)g.sphere_cull.p;
+    p.sphere_prim = (const double4 *)g.sphere_prim.p;
     p.sphere_mat = (const DevMaterial *)g.sphere_mat.p;
     p.byte_to_unit = (const double *)g.byte_to_unit.p;
     p.sky = (const uchar4 *)g.sky.p;
@@ -290,6 +382,7 @@ void trt_shutdown(void)
     g.sphere_geom.release();
     g.sphere_cull.release();
     g.sphere_mat.release();
+    g.sphere_prim.release();
     g.sky.release();
     g.tile_counter.release();
     g.byte_to_unit.release();
@@ -497,6 +590,7 @@ int trt_probe_skybox(const double *dirs, int n, int *out)
         upload_scene_constants(g.scene, nullptr, 0, g.stream);
         g.sphere_geom.reserve(sizeof(double4));
         g.sphere_cull.reserve(sizeof(float4));
+        g.sphere_prim.reserve(sizeof(double4));
         g.sphere_mat.reserve(sizeof(DevMaterial));
         g.have_scene = true;
     } else {

@@ -1,0 +1,249 @@
+/*
+ * trt_cert.h — single-precision CERTIFICATES for outcomes of the reference's FP64 intersection tests.
+ *
+ * The render kernel (trt_render.cu) must reproduce the reference's IEEE-double results bit for bit
+ * (TRT.c = /root/reference/TerminalRayTracer.c).  Most ray/sphere and ray/plane tests, however, only
+ * feed a DECISION (hit / no hit, blocked / open), and most of those decisions are geometrically
+ * clear-cut.  The functions below evaluate a test in float together with a bound on everything float
+ * got wrong, and answer only when the reference's own double evaluation provably reaches the same
+ * decision; every other case is reported as "unknown" and is evaluated exactly in FP64 by the caller.
+ * They never produce a value that reaches a pixel.
+ *
+ * The header is plain C99 / C++ with no CUDA dependency except the TRT_HD qualifier, so that the very
+ * same code is (a) compiled into the kernel and (b) run on the CPU against the oracle on millions of
+ * rays (tests/test_certificates.py via oracle/cert_check.c; 0 contradictions required), in addition to
+ * the on-device audit of the counting build (CTR_CULL_VIOLATIONS).
+ *
+ * Notation: u = 2^-24 (float unit round-off).  S = an upper bound on the L1 norm of every point
+ * that enters a difference (ray origin, sphere centres, light position).  A float dot product of
+ * differences of such points with a unit vector, and the distance of such a point from the ray's line,
+ * are within 16uS of the real value; the slack used is 2x that.  The reference's own
+ * double rounding is ~2^-29 of the slacks, which is why a decision certified here is also the
+ * decision of the reference's COMPUTED discriminant / quotient and not only of the real-valued one.
+ */
+#ifndef TRT_CERT_H
+#define TRT_CERT_H
+
+#include <math.h>
+
+#ifdef __CUDACC__
+#define TRT_HD __host__ __device__ __forceinline__
+#else
+#define TRT_HD static inline
+#endif
+
+#define TRT_CERT_U 5.9604644775390625e-08f /* 2^-24 */
+
+/* a ray as the certificates see it */
+typedef struct {
+    float ox, oy, oz;  /* origin, rounded to nearest                                             */
+    float dx, dy, dz;  /* direction, |d| = 1 within `dir_err`                                    */
+    float slack_t;     /* 2x the bound on the float error of a coordinate along or across the ray */
+    int usable;        /* 0: magnitudes outside the range the bounds hold for -> everything unknown */
+} trt_cert_ray;
+
+/* origin of a certificate ray from the double origin; returns |o|_1 (float) */
+TRT_HD float trt_cert_set_origin(trt_cert_ray *r, double ox, double oy, double oz)
+{
+    r->ox = (float)ox;
+    r->oy = (float)oy;
+    r->oz = (float)oz;
+    return fabsf(r->ox) + fabsf(r->oy) + fabsf(r->oz);
+}
+
+/* direction rounded from a double UNIT vector (primary, bounce and directional-light rays).
+ * S >= |o|_1 + max_i |c_i|_1.  A direction that is not unit to float accuracy (normalize_vector's
+ * len <= 1e-4 escape, TRT.c:441) makes the ray unusable: every answer becomes "unknown". */
+TRT_HD void trt_cert_set_unit_dir(trt_cert_ray *r, double dx, double dy, double dz, float S)
+{
+    r->dx = (float)dx;
+    r->dy = (float)dy;
+    r->dz = (float)dz;
+    const float dd = fmaf(r->dz, r->dz, fmaf(r->dy, r->dy, r->dx * r->dx));
+    r->slack_t = (32.0f * TRT_CERT_U) * S;
+    r->usable = (S < 1e15f) && (dd > 0.99999f) && (dd < 1.00001f);
+}
+
+#if defined(__CUDA_ARCH__)
+#define TRT_CERT_RSQRT(x) rsqrtf(x)
+#else
+#define TRT_CERT_RSQRT(x) (1.0f / sqrtf(x))
+#endif
+
+/* direction from the ray's origin toward the point (lx,ly,lz), formed and normalised in float
+ * (point-light shadow rays, TRT.c:929-934).  S >= |o|_1 + max_i |c_i|_1 + |l|_1.  Returns the float
+ * distance to the point.  The float direction is off by up to ~2u * S / distance, which enters the slacks. */
+TRT_HD float trt_cert_set_dir_toward(trt_cert_ray *r, float lx, float ly, float lz, float S)
+{
+    const float vx = lx - r->ox, vy = ly - r->oy, vz = lz - r->oz;
+    const float dd = fmaf(vz, vz, fmaf(vy, vy, vx * vx));
+    const float inv = TRT_CERT_RSQRT(dd);
+    r->dx = vx * inv;
+    r->dy = vy * inv;
+    r->dz = vz * inv;
+    const float k = fmaf(2.0f * S, inv, 1.0f);
+    r->slack_t = (32.0f * TRT_CERT_U) * S * k;
+    r->usable = (S < 1e15f) && (k < 1e4f) && (dd > 1e-30f) && (dd < 1e30f);
+    return dd * inv;
+}
+
+/* outcome bits of one ray/sphere classification */
+#define TRT_CERT_MISS 1   /* the reference's ray_intersects_sphere (TRT.c:638-672) returns false, or its hit
+                             lies beyond `far_limit` and therefore cannot decide a point-light shadow test  */
+#define TRT_CERT_BLOCKS 2 /* the reference returns true with a hit closer than `near_limit`                 */
+
+/*
+ * Classify sphere (cx,cy,cz, r_pad) against ray r.  r_pad >= r * (1 + 2^-20), rounded up (host).
+ *   tc = (c - o) . d             position of the centre along the ray
+ *   w  = (c - o) - tc d          offset of the centre from the ray's line;  h = |w|
+ * (h is formed from w and not as |c-o|^2 - tc^2: the latter cancels catastrophically for far origins, w does
+ * not — its float error is ~u |c - o| per component, i.e. |h_f - h| <= 16uS <= slack_t / 2.)
+ * MISS   if  h > r_pad + slack_t          the line passes the sphere: discriminant < 0 (TRT.c:651)
+ *        or  tc < -slack_t                centre behind the origin: b = -2 tc > 0, so the near root
+ *                                         t0 = (-b - sqrt(disc)) / 2a is negative whatever disc is (TRT.c:657-659)
+ *        or  tc - r_pad > far_limit       every point of the sphere is farther than far_limit along the ray
+ * BLOCKS if  h < r_pad (1 - 2^-17) - slack_t   the line passes well inside the sphere (disc > 0)
+ *        and tc - r_pad > slack_t               the whole sphere is in front: both roots positive, t0 > 0
+ *        and tc < near_limit                    t0 <= tc: the hit is closer than near_limit
+ * Pass far_limit = +inf, near_limit = +inf for rays without a length (bounce rays, directional lights).
+ * The caller must ignore the answer when !r->usable.
+ */
+TRT_HD int trt_cert_sphere(const trt_cert_ray *r, float cx, float cy, float cz, float r_pad, float near_limit, float far_limit)
+{
+    const float ocx = cx - r->ox, ocy = cy - r->oy, ocz = cz - r->oz;
+    const float tc = fmaf(ocz, r->dz, fmaf(ocy, r->dy, ocx * r->dx));
+    const float wx = fmaf(-tc, r->dx, ocx), wy = fmaf(-tc, r->dy, ocy), wz = fmaf(-tc, r->dz, ocz);
+    const float h2 = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+    const float outer = r_pad + r->slack_t;
+    const float inner = fmaf(r_pad, 0.99999237060546875f, -r->slack_t);
+    const float front = tc - r_pad;
+    int out = 0;
+    if ((h2 > outer * outer) || (tc < -r->slack_t) || (front > far_limit)) out |= TRT_CERT_MISS;
+    if ((inner > 0.0f) && (h2 < inner * inner) && (front > r->slack_t) && (tc < near_limit)) out |= TRT_CERT_BLOCKS;
+    return out;
+}
+
+/* miss-only variant for rays whose hit POINT is needed (bounce rays): 16 float operations */
+TRT_HD int trt_cert_sphere_miss(const trt_cert_ray *r, float cx, float cy, float cz, float r_pad)
+{
+    const float ocx = cx - r->ox, ocy = cy - r->oy, ocz = cz - r->oz;
+    const float tc = fmaf(ocz, r->dz, fmaf(ocy, r->dy, ocx * r->dx));
+    const float wx = fmaf(-tc, r->dx, ocx), wy = fmaf(-tc, r->dy, ocy), wz = fmaf(-tc, r->dz, ocz);
+    const float h2 = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+    const float outer = r_pad + r->slack_t;
+    return (h2 > outer * outer) || (tc < -r->slack_t);
+}
+
+/*
+ * Ground plane, TRT.c:677-695: hit iff |denom| > 1e-5 and t = ((p - o) . n) / (d . n) > 1e-5.
+ * When numerator and denominator certainly have opposite signs the quotient is negative: miss.
+ * (px,py,pz) plane point, (nx,ny,nz) plane normal (any length), both rounded to nearest.
+ * Error bounds: |num_f - num| <= 8u * sum_k (|p_k| + |o_k|)|n_k|, |den_f - den| <= 8u * sum_k |d_k||n_k|;
+ * the margins are twice that.
+ */
+TRT_HD int trt_cert_plane_miss(const trt_cert_ray *r, float px, float py, float pz, float nx, float ny, float nz)
+{
+    const float anx = fabsf(nx), any_ = fabsf(ny), anz = fabsf(nz);
+    const float num = fmaf(pz - r->oz, nz, fmaf(py - r->oy, ny, (px - r->ox) * nx));
+    const float den = fmaf(r->dz, nz, fmaf(r->dy, ny, r->dx * nx));
+    const float num_scale = fmaf(fabsf(pz) + fabsf(r->oz), anz, fmaf(fabsf(py) + fabsf(r->oy), any_, (fabsf(px) + fabsf(r->ox)) * anx));
+    const float den_scale = fmaf(fabsf(r->dz), anz, fmaf(fabsf(r->dy), any_, fabsf(r->dx) * anx));
+    const float e_num = (16.0f * TRT_CERT_U) * num_scale;
+    const float e_den = (16.0f * TRT_CERT_U) * den_scale;
+    const int finite = r->usable && (num_scale < 1e30f) && (den_scale < 1e30f);
+    return finite && ((num < -e_num && den > e_den) || (num > e_num && den < -e_den));
+}
+
+/*
+ * Tile-level certificate for PRIMARY rays.  All sample rays of a pixel tile leave the eye with directions
+ * D = Dc + e, |e| <= h (Dc: direction through the tile centre, un-normalised; h: half extent of the tile on the
+ * camera plane times the basis lengths).  For the sphere with centre c (oc = eye - c):
+ *     |oc x D| >= |oc x Dc| - |oc| h      and      |D| <= |Dc| + h
+ * so if  |oc x Dc| - |oc| h  >  r_pad (|Dc| + h) + slack  every such line passes the sphere at more than r_pad:
+ * the discriminant of TRT.c:651 is negative for every sample of the tile.  S = |eye|_1 + max_i |c_i|_1.
+ */
+TRT_HD int trt_cert_tile_sphere_miss(float ex, float ey, float ez, float Dx, float Dy, float Dz, float h,
+                                     float cx, float cy, float cz, float r_pad, float S)
+{
+    const float ocx = ex - cx, ocy = ey - cy, ocz = ez - cz;
+    const float X = fmaf(ocy, Dz, -(ocz * Dy));
+    const float Y = fmaf(ocz, Dx, -(ocx * Dz));
+    const float Z = fmaf(ocx, Dy, -(ocy * Dx));
+    const float nX = sqrtf(fmaf(Z, Z, fmaf(Y, Y, X * X))) * (1.0f - 8.0f * TRT_CERT_U);
+    const float nOC = sqrtf(fmaf(ocz, ocz, fmaf(ocy, ocy, ocx * ocx))) * (1.0f + 8.0f * TRT_CERT_U);
+    const float nD = sqrtf(fmaf(Dz, Dz, fmaf(Dy, Dy, Dx * Dx))) * (1.0f + 8.0f * TRT_CERT_U) + h;
+    const float lhs = nX - nOC * h;
+    const float rhs = fmaf(r_pad, nD, (64.0f * TRT_CERT_U) * S * nD);
+    return (S < 1e15f) && (nD < 1e15f) && (lhs > rhs);
+}
+
+/*
+ * Tile-level ground certificate for primary rays: every D = Dc + ex*bx + ey*by (|ex| <= hx, |ey| <= hy) has
+ * D . n of one certain sign.  Returns +1 (all positive), -1 (all negative) or 0 (unknown).
+ * dn = Dc . n, bxn = bx . n, byn = by . n (float), scale = (|Dc|_1 + hx |bx|_1 + hy |by|_1) * |n|_1.
+ */
+TRT_HD int trt_cert_tile_plane_sign(float dn, float bxn, float byn, float hx, float hy, float scale)
+{
+    const float spread = fmaf(hx, fabsf(bxn), hy * fabsf(byn));
+    const float margin = (64.0f * TRT_CERT_U) * scale;
+    if (!(scale < 1e30f)) return 0;
+    if (dn - spread > margin) return 1;
+    if (dn + spread < -margin) return -1;
+    return 0;
+}
+
+/* ---- host-side preparation shared by the library (trt_api.cu) and the CPU checker ----------------------- */
+
+/* smallest float >= v */
+TRT_HD float trt_cert_round_up(double v)
+{
+    float f = (float)v;
+    if ((double)f < v) f = nextafterf(f, INFINITY);
+    return f;
+}
+
+/* padded radius of a cull record: >= r (1 + 2^-20), rounded up; r = sqrt(fl(radius*radius)) covers negative radii */
+TRT_HD float trt_cert_pad_radius(double radius)
+{
+    const double r = sqrt(radius * radius);
+    return trt_cert_round_up(r * (1.0 + 1.0 / 1048576.0));
+}
+
+/* camera as the tile certificates see it (all float, rounded to nearest unless stated) */
+typedef struct {
+    float ex, ey, ez;             /* eye                                                            */
+    float bx[3], by[3], bz[3];    /* camera basis                                                   */
+    float nbx, nby;               /* |bx|_2, |by|_2 rounded up                                      */
+    float sw, sh, dist;           /* screen width, height, distance                                 */
+    float off_x, off_y;           /* largest sub-pixel offset in x and y, in pixels (TRT.c:992-993) */
+} trt_cert_camera;
+
+/* Direction through the centre of the tile [col0,col0+tw) x [row0,row0+th) of a W x H screen, and the half
+ * extents (hx, hy, in camera-plane units) of the tile's sample positions around it, as the primary-ray
+ * construction of TRT.c:987-1005 places them (top-left pixel corner + offset in [0, off] pixels; screen_y negated
+ * before the offset is added).  Every sample direction of the tile is Dc + ex*bx + ey*by, |ex| <= hx, |ey| <= hy;
+ * the sphere certificate takes h = hx*|bx| + hy*|by|. */
+TRT_HD void trt_cert_tile_cone(const trt_cert_camera *c, int col0, int row0, int tw, int th, int W, int H,
+                               float *Dx, float *Dy, float *Dz, float *hx, float *hy)
+{
+    const float pw = c->sw / (float)W, ph = c->sh / (float)H;
+    const float half_w = 0.5f * ((float)(tw - 1) + c->off_x), half_h = 0.5f * ((float)(th - 1) + c->off_y);
+    const float scx = fmaf((float)col0 + half_w, pw, -0.5f * c->sw);
+    const float syc = fmaf(-((float)(row0 + th - 1) - half_h), ph, 0.5f * c->sh);
+    *hx = fmaf(half_w + 0.01f, pw, (16.0f * TRT_CERT_U) * c->sw);
+    *hy = fmaf(half_h + 0.01f, ph, (16.0f * TRT_CERT_U) * c->sh);
+    *Dx = fmaf(c->bz[0], -c->dist, fmaf(c->by[0], syc, c->bx[0] * scx)) - c->ex;
+    *Dy = fmaf(c->bz[1], -c->dist, fmaf(c->by[1], syc, c->bx[1] * scx)) - c->ey;
+    *Dz = fmaf(c->bz[2], -c->dist, fmaf(c->by[2], syc, c->bx[2] * scx)) - c->ez;
+}
+
+/* Point-light shadow ray vs the ground plane (TRT.c:677-695 through 936-941).  num = (plane point - origin) . n
+ * in double, as the reference evaluates it; light_height = (light - plane point) . n; margin > 0 scales with |n|.
+ * When origin and light are on the same side of the plane the ray cannot reach the plane before it reaches the
+ * light, and any hit behind the light is farther than the light by at least margin/|n|: it cannot block. */
+TRT_HD int trt_cert_ground_cannot_block(double num, double light_height, double margin)
+{
+    return (num < 0.0 && light_height > margin) || (num > 0.0 && light_height < -margin);
+}
+
+#endif /* TRT_CERT_H */

@@ -9,19 +9,24 @@
 // bit-identical to the reference's.  What is NOT reproduced is work that cannot influence a pixel:
 //   * the skybox lookup the reference performs when a SHADOW ray misses (TRT.c:907, 937 -> 858-867),
 //   * the reflect/normalise the reference performs after a sample has already hit the sky (1054-1055),
-//   * the `view` vector (1029) and the specularity field (118), both never read.
+//   * the `view` vector (1029) and the specularity field (118), both never read,
+//   * intersection tests whose outcome a single-precision certificate (trt_cert.h) proves in advance.
 //
-// Execution model (why it looks nothing like the reference's call tree):
-//   * persistent CTAs, one per SM slot; each WARP pulls 8x4-pixel tiles from a global atomic counter,
-//     lane = pixel, so the 32 rays of a warp are spatially coherent;
-//   * every lane runs ONE loop whose body starts with the closest-hit query (the sphere loop is ~half
-//     of all work) and then advances a small per-lane state machine: primary/bounce ray -> one shadow
-//     ray per light -> shade/reflect -> next bounce or next sample.  Primary, bounce and shadow rays of
-//     different lanes therefore share the same sphere-loop instructions instead of serialising three
-//     inlined copies of trace_ray, and a lane that finishes a sample immediately starts its next one;
-//   * the scene sits in __constant__ memory (warp-uniform index in the sphere loop -> one broadcast
-//     LDC per operand); the skybox is an RGBA8 repack read through the read-only path and stays
-//     L2-resident; the k/255.0 colour table is in shared memory.
+// Execution model — a per-warp WAVEFRONT, so that every instruction stream is uniform across the warp:
+//   * persistent CTAs; each WARP pulls 8x4-pixel tiles (x 10 samples = 320 primary rays) from an atomic counter;
+//   * PRODUCE step (one per sample index k, lane = pixel): primary ray -> closest hit.  Spheres are tested
+//     exactly, but only those the TILE certificate could not rule out for the whole tile (usually none or one),
+//     with the eye-relative terms of the quadratic precomputed on the host.  A sample that sees the sky is
+//     finished on the spot; a sample that hits a surface becomes a 104-byte HIT RECORD in a warp-private
+//     shared-memory ring;
+//   * CONSUME step (whenever 32 records are queued, lane = record): push-back, normal, one shadow query per
+//     light (float certificates decide open / blocked for most of them; the rest walk their few surviving
+//     spheres exactly), shading, reflection, and the closest-hit query of the reflected ray, whose hit becomes
+//     the next record and whose miss finishes the sample with a sky lookup;
+//   * finished samples are parked in shared memory and summed per pixel in sample order at the end of the tile
+//     (TRT.c:1063 adds them in that order; floating-point addition is not associative).
+// Compared with one-ray-per-trip state machines, no lane ever executes another lane's phase under predication:
+// the ring keeps full warps of like work together however the bounce counts diverge.
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -31,7 +36,7 @@
 namespace trt {
 
 __constant__ DevScene c_scene;
-__constant__ float4 c_sphere_cull[TRT_MAX_CONST_SPHERES + 2]; // (cx, cy, cz, r_pad) in float, see sphere_cull()
+__constant__ float4 c_sphere_cull[TRT_MAX_CONST_SPHERES + 2]; // (cx, cy, cz, r_pad) in float, see trt_cert.h
 
 constexpr int TILE_W = 8;
 constexpr int TILE_H = 4;
@@ -39,15 +44,39 @@ constexpr int TILE_H = 4;
 #define TRT_WARPS_PER_CTA 4
 #endif
 #ifndef TRT_MIN_CTAS_PER_SM
-#define TRT_MIN_CTAS_PER_SM 6
+#define TRT_MIN_CTAS_PER_SM 3
 #endif
 constexpr int WARPS_PER_CTA = TRT_WARPS_PER_CTA;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+constexpr int QCAP = 64;                                  // ring capacity: at most 31 queued + 32 pushed by one step
+constexpr int TILE_SAMPLES = 32 * TRT_RAYS_PER_PIXEL;
+constexpr int TMASK_WORDS = TRT_MAX_CONST_SPHERES / 32;   // tile certificate masks (scenes up to TRT_MAX_CONST_SPHERES)
 
-enum Phase : int { PH_MAIN = 0, PH_SHADOW = 1 };
+// what a closest-hit query is for
+enum QueryMode : int {
+    Q_CLOSEST = 0, // bounce rays: the hit itself is needed
+    Q_DIR = 1,     // directional-light shadow ray: any hit blocks (TRT.c:907-908)
+    Q_POINT = 2    // point-light shadow ray: only a hit closer than the light blocks (TRT.c:936-941)
+};
 
-// (cx,cy,cz,r*r) of sphere i through the read-only path (scenes too large for __constant__)
-__device__ __forceinline__ double4 ldg_geom(const double4 *geom, int i)
+// warp-private shared memory: the hit-record ring (structure of arrays: conflict-free for lane = slot),
+// the finished samples of the current tile and the tile certificate mask
+struct WarpShared {
+    double ox[QCAP], oy[QCAP], oz[QCAP];   // origin of the ray that hit
+    double dx[QCAP], dy[QCAP], dz[QCAP];   // its unit direction
+    double t[QCAP];                        // hit parameter: hit point = o + t d (TRT.c:663-665 / 690-692)
+    double sr[QCAP], sg[QCAP], sb[QCAP];   // colour accumulated by the sample so far (TRT.c:1051)
+    double w[QCAP], ws[QCAP];              // weight, weight_sum (TRT.c:1017, 1034)
+    unsigned int meta[QCAP];               // pixel lane | sample k << 5 | bounces << 9 | object kind << 13
+    int index[QCAP];                       // sphere index of the hit
+    double res[3][TILE_SAMPLES];           // finished samples, [channel][k * 32 + pixel lane]
+    unsigned int tmask[TMASK_WORDS];       // spheres the tile certificate could not rule out
+};
+constexpr size_t SMEM_TABLE_BYTES = 256 * sizeof(double);
+constexpr size_t SMEM_BYTES = SMEM_TABLE_BYTES + WARPS_PER_CTA * sizeof(WarpShared);
+
+// (cx,cy,cz,r*r) of sphere i through the read-only path
+__device__ __forceinline__ double4 ldg4(const double4 *geom, int i)
 {
     const double2 *p = reinterpret_cast<const double2 *>(geom + i);
     const double2 lo = __ldg(p), hi = __ldg(p + 1);
@@ -57,9 +86,9 @@ __device__ __forceinline__ double4 ldg_geom(const double4 *geom, int i)
 template <bool COUNT>
 struct Tally {
     unsigned long long *g;
-    __device__ __forceinline__ void add(int id) const
+    __device__ __forceinline__ void add(int id, unsigned long long n = 1ull) const
     {
-        if (COUNT) atomicAdd(&g[id], 1ull);
+        if (COUNT) atomicAdd(&g[id], n);
     }
 };
 
@@ -106,84 +135,24 @@ __device__ __forceinline__ int sky_texel_index(const d3 &dir, int dim, int &face
     return ui + vi * dim;
 }
 
-// ---- conservative FP32 miss test ---------------------------------------------------------------------
-// ~90% of all ray/sphere tests of this path end at `discriminant < 0` (TRT.c:651).  That outcome is a
-// geometric fact — the line passes the centre at more than r — which single precision can CERTIFY for
-// all but the rays that graze the silhouette.  A sphere is culled only when
-//        |oc_f x d_f|^2  >  ( |d_f| * r_pad  +  |d_f| * CULL_EPS * (|o|_1 + max_i |c_i|_1) )^2
-// evaluated in float, where r_pad >= r*(1+2^-20) (host, rounded up) and CULL_EPS = 64 * 2^-24.
-// Error budget (DESIGN.md "FP32 cull"): rounding o, c, d to float and the float evaluation of the
-// cross product move |oc x d| by at most 9*2^-24*|d|*(|o|_1+|c|_1); the reference's own FP64 rounding
-// of the discriminant is below 2^-50 of the same scale.  With the 64*2^-24 margin the inequality above
-// implies the reference's COMPUTED discriminant is negative, i.e. the reference returns "miss" for this
-// sphere; everything else (and any NaN/inf, which makes the comparison false) goes to the exact FP64
-// test below, so results stay bit-identical.  The counting build re-checks every culled sphere exactly
-// (CTR_CULL_VIOLATIONS must be 0; tests/test_gpu_parity.py).
-constexpr float CULL_EPS = 64.0f * 5.9604644775390625e-08f;
-
-struct RayF32 {
-    float ox, oy, oz, dx, dy, dz;
-    float norm_d;     // |d_f|
-    float slack;      // |d_f| * CULL_EPS * (|o|_1 + max_i |c_i|_1)
-    bool usable;      // magnitudes inside the range the bound was derived for
-};
-
-__device__ __forceinline__ RayF32 ray_to_f32(const d3 &o, const d3 &d)
+// colour of the sky in direction d (a unit vector; the reference normalises it once more, TRT.c:702)
+__device__ __forceinline__ d3 sky_colour(const RenderParams &P, const double *s_byte_to_unit, const d3 &d)
 {
-    RayF32 r;
-    r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
-    r.dx = (float)d.x; r.dy = (float)d.y; r.dz = (float)d.z;
-    r.norm_d = __fsqrt_rn(__fmaf_rn(r.dz, r.dz, __fmaf_rn(r.dy, r.dy, r.dx * r.dx)));
-    const float l1 = (fabsf(r.ox) + fabsf(r.oy)) + (fabsf(r.oz) + c_scene.filter_centre_l1);
-    r.slack = r.norm_d * (CULL_EPS * l1);
-    r.usable = c_scene.filter_enabled && (l1 < 1e15f) && (r.norm_d > 1e-15f) && (r.norm_d < 1e15f);
-    return r;
+    int face;
+    const int texel = sky_texel_index(unit(d), c_scene.sky_dim, face);
+    const uchar4 t = __ldg(&P.sky[(size_t)face * (size_t)c_scene.sky_face_stride + (size_t)texel]);
+    return mk3(s_byte_to_unit[t.x], s_byte_to_unit[t.y], s_byte_to_unit[t.z]);   // TRT.c:866
 }
 
-// true = the reference certainly computes discriminant < 0 for this sphere
-__device__ __forceinline__ bool sphere_cull(const RayF32 &r, const float4 g)
-{
-    const float ocx = r.ox - g.x, ocy = r.oy - g.y, ocz = r.oz - g.z;
-    const float cx = __fmaf_rn(ocy, r.dz, -(ocz * r.dy));
-    const float cy = __fmaf_rn(ocz, r.dx, -(ocx * r.dz));
-    const float cz = __fmaf_rn(ocx, r.dy, -(ocy * r.dx));
-    const float q = __fmaf_rn(cz, cz, __fmaf_rn(cy, cy, cx * cx));
-    const float t = __fmaf_rn(r.norm_d, g.w, r.slack);
-    return q > t * t;
-}
+// ---- exact tests: the reference's operations in the reference's order -------------------------------------
 
-// Conservative FP32 miss test for the ground plane (TRT.c:677-695): the reference reports a hit only if
-// t = ((point - origin) . n) / (direction . n) > 1e-5.  When numerator and denominator have opposite signs
-// the quotient is negative (or -0), so the test is a miss; single precision certifies the two signs unless
-// either value is within its rounding error of zero.  Error bounds: every product of the two 3-term dot
-// products is computed from float-rounded inputs (relative error 2^-24 each) and accumulated in float, so
-// |num_f - num| <= 8*2^-24 * sum_k (|p_k| + |o_k|)|n_k| and |den_f - den| <= 8*2^-24 * sum_k |d_k||n_k|;
-// the margins below are twice that, and the reference's own FP64 rounding is ~2^-29 of them.
-// NaN/inf make the comparisons false.
-__device__ __forceinline__ bool plane_cull(const RayF32 &r)
-{
-    const float nx = c_scene.ground_normal_f[0], ny = c_scene.ground_normal_f[1], nz = c_scene.ground_normal_f[2];
-    const float px = c_scene.ground_point_f[0], py = c_scene.ground_point_f[1], pz = c_scene.ground_point_f[2];
-    const float anx = fabsf(nx), any = fabsf(ny), anz = fabsf(nz);
-    const float num = __fmaf_rn(pz - r.oz, nz, __fmaf_rn(py - r.oy, ny, (px - r.ox) * nx));
-    const float den = __fmaf_rn(r.dz, nz, __fmaf_rn(r.dy, ny, r.dx * nx));
-    const float num_scale = __fmaf_rn(fabsf(pz) + fabsf(r.oz), anz, __fmaf_rn(fabsf(py) + fabsf(r.oy), any, (fabsf(px) + fabsf(r.ox)) * anx));
-    const float den_scale = __fmaf_rn(fabsf(r.dz), anz, __fmaf_rn(fabsf(r.dy), any, fabsf(r.dx) * anx));
-    const float e_num = (16.0f * 5.9604644775390625e-08f) * num_scale;
-    const float e_den = (16.0f * 5.9604644775390625e-08f) * den_scale;
-    const bool finite = r.usable && (num_scale < 1e30f) && (den_scale < 1e30f);
-    return finite && ((num < -e_num && den > e_den) || (num > e_num && den < -e_den));
-}
-
-// ---- ray_intersects_sphere (TRT.c:638-672) + the closest-so-far update of trace_ray (TRT.c:807-827) ----
+// ray_intersects_sphere (TRT.c:638-672) with oc = origin - centre and c = oc.oc - r*r given, plus the
+// closest-so-far update of trace_ray (TRT.c:807-827).  Keeps the hit PARAMETER; the point is o + t d.
 template <bool COUNT>
-__device__ __forceinline__ void sphere_exact(const double4 g, int i, const d3 &o, const d3 &d, double two_a, double four_a,
-                                             double &closest, int &obj, int &index, d3 &hit, const Tally<COUNT> &tally)
+__device__ __forceinline__ void sphere_exact_oc(const d3 &oc, double c, int i, const d3 &o, const d3 &d, double two_a, double four_a,
+                                                double &closest, int &obj, int &index, double &t_hit, const Tally<COUNT> &tally)
 {
-    tally.add(CTR_EXACT_SPHERE_TESTS);
-    const d3 oc = mk3(o.x - g.x, o.y - g.y, o.z - g.z);
     const double b = 2.0 * dot(oc, d);
-    const double c = dot(oc, oc) - g.w;      // g.w = radius*radius, evaluated on the host in double
     const double disc = b * b - four_a * c;  // (4.0*a)*c, scaling by 4 is exact
     if (!(disc < 0.0)) {                     // TRT.c:651
         tally.add(CTR_SPHERE_DISC_OK);
@@ -198,82 +167,32 @@ __device__ __forceinline__ void sphere_exact(const double4 g, int i, const d3 &o
                 closest = d2;
                 obj = 1;
                 index = i;
-                hit = p;
+                t_hit = t0;
             }
         }
     }
 }
 
-// exact discriminant sign only — used by the counting build to audit the cull
-__device__ __forceinline__ bool exact_disc_negative(const double4 g, const d3 &o, const d3 &d, double four_a)
+template <bool COUNT>
+__device__ __forceinline__ void sphere_exact(const double4 g, int i, const d3 &o, const d3 &d, double two_a, double four_a,
+                                             double &closest, int &obj, int &index, double &t_hit, const Tally<COUNT> &tally)
 {
     const d3 oc = mk3(o.x - g.x, o.y - g.y, o.z - g.z);
-    const double b = 2.0 * dot(oc, d);
-    const double c = dot(oc, oc) - g.w;
-    return (b * b - four_a * c) < 0.0;
+    const double c = dot(oc, oc) - g.w;      // g.w = radius*radius, evaluated on the host in double
+    sphere_exact_oc<COUNT>(oc, c, i, o, d, two_a, four_a, closest, obj, index, t_hit, tally);
 }
 
-// ---- closest-hit query, the geometric half of trace_ray (TRT.c:805-853) -------------------------------
-// obj: 0 none, 1 sphere, 2 ground.  hit = un-pushed intersection point of the closest object.
-// Spheres are visited in index order (ties keep the lowest index, strict <), the ground last.
-// CULL: 0 = every test in FP64; 1 = FP32 cull records in __constant__; 2 = cull records in global memory.
-template <bool COUNT, int CULL>
-__device__ __forceinline__ void closest_hit(const RenderParams &P, const d3 &o, const d3 &d, int &obj, int &index,
-                                            d3 &hit, const Tally<COUNT> &tally)
+// ray_intersects_plane (TRT.c:677-695) + the ground branch of trace_ray (TRT.c:831-853); `num` is
+// dot(ground point - origin, normal) (TRT.c:684-685), passed in because several callers share it
+template <bool COUNT>
+__device__ __forceinline__ void plane_exact_num(double num, const d3 &o, const d3 &d, double &closest, int &obj, double &t_hit,
+                                                const Tally<COUNT> &tally)
 {
-    double closest = INFINITY;
-    obj = 0;
-    index = -1;
-    const double a = dot(d, d);                  // TRT.c:646, loop-invariant
-    const double two_a = 2.0 * a;
-    const double four_a = 4.0 * a;
-    const int n = c_scene.num_spheres;
-    if (COUNT) atomicAdd(&P.counters[CTR_SPHERE_TESTS], (unsigned long long)n);
-    bool ground_culled = false;
-    if (CULL) {
-        const RayF32 rf = ray_to_f32(o, d);
-        ground_culled = !COUNT && plane_cull(rf);   // the counting build runs the exact plane test: it counts its branches
-        for (int base = 0; base < n; base += 32) {
-            const int cnt = min(32, n - base);
-            // pass 1 (FP32, branch-free, warp-uniform operands): which spheres of this chunk survive.
-            // The records are padded to an even count (pad records are masked off below), so the loop
-            // needs no remainder handling: two independent tests per trip.
-            unsigned int survivors = 0;
-#pragma unroll 1
-            for (int j = 0; j < cnt; j += 2) {
-                const float4 g0 = CULL == 1 ? c_sphere_cull[base + j] : __ldg(&P.sphere_cull[base + j]);
-                const float4 g1 = CULL == 1 ? c_sphere_cull[base + j + 1] : __ldg(&P.sphere_cull[base + j + 1]);
-                const unsigned int s0 = sphere_cull(rf, g0) ? 0u : 1u;
-                const unsigned int s1 = sphere_cull(rf, g1) ? 0u : 2u;
-                survivors |= (s0 | s1) << j;
-            }
-            const unsigned int valid = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
-            survivors = rf.usable ? (survivors & valid) : valid;
-            if (COUNT) {
-                for (int j = 0; j < cnt; j++)
-                    if (!((survivors >> j) & 1u) && !exact_disc_negative(ldg_geom(P.sphere_geom, base + j), o, d, four_a))
-                        atomicAdd(&P.counters[CTR_CULL_VIOLATIONS], 1ull);
-            }
-            // pass 2 (FP64, exact): each lane walks its own survivors in index order
-            while (survivors) {
-                const int j = __ffs(survivors) - 1;
-                survivors &= survivors - 1;
-                sphere_exact<COUNT>(ldg_geom(P.sphere_geom, base + j), base + j, o, d, two_a, four_a, closest, obj, index, hit, tally);
-            }
-        }
-    } else {
-        for (int i = 0; i < n; i++)
-            sphere_exact<COUNT>(ldg_geom(P.sphere_geom, i), i, o, d, two_a, four_a, closest, obj, index, hit, tally);
-    }
-    // ground, TRT.c:677-695 and 831-853
-    tally.add(CTR_PLANE_TESTS);
-    if (ground_culled) return;
     const d3 gn = mk3(c_scene.ground_normal[0], c_scene.ground_normal[1], c_scene.ground_normal[2]);
     const double denom = dot(d, gn);
     if (fabs(denom) > 0.00001) {
         tally.add(CTR_PLANE_DENOM_OK);
-        const d3 to_plane = mk3(c_scene.ground_point[0] - o.x, c_scene.ground_point[1] - o.y, c_scene.ground_point[2] - o.z);
-        const double t = ieee_div(dot(to_plane, gn), denom);
+        const double t = ieee_div(num, denom);
         if (t > 0.00001) {
             tally.add(CTR_PLANE_T_POS);
             const d3 p = mk3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
@@ -281,13 +200,120 @@ __device__ __forceinline__ void closest_hit(const RenderParams &P, const d3 &o, 
             const double d2 = dot(back, back);
             if (d2 < closest) {
                 tally.add(CTR_PLANE_CLOSEST);
+                closest = d2;
                 obj = 2;
-                // checker parity, TRT.c:850
-                index = x86_int(floor(p.x) + floor(p.z)) & 1;
-                hit = p;
+                t_hit = t;
             }
         }
     }
+}
+
+__device__ __forceinline__ double plane_numerator(const d3 &o)
+{
+    const d3 gn = mk3(c_scene.ground_normal[0], c_scene.ground_normal[1], c_scene.ground_normal[2]);
+    const d3 to_plane = mk3(c_scene.ground_point[0] - o.x, c_scene.ground_point[1] - o.y, c_scene.ground_point[2] - o.z);
+    return dot(to_plane, gn);
+}
+
+// trace_ray's geometric half (TRT.c:805-853) over ALL objects in the reference's order: spheres by index
+// (strict <, so ties keep the lowest index), the ground last.  obj: 0 none, 1 sphere, 2 ground.
+// This is the all-FP64 path: the counting build, trt_set_cull(0) and the audit of the certificates use it.
+template <bool COUNT>
+__device__ __noinline__ void query_reference(const RenderParams &P, const d3 &o, const d3 &d, int &obj, int &index, double &t_hit,
+                                             const Tally<COUNT> &tally)
+{
+    double closest = INFINITY;
+    obj = 0;
+    index = -1;
+    t_hit = 0.0;
+    const double a = dot(d, d);                  // TRT.c:646, loop-invariant
+    const double two_a = 2.0 * a, four_a = 4.0 * a;
+    const int n = c_scene.num_spheres;
+    tally.add(CTR_SPHERE_TESTS, (unsigned long long)n);
+    for (int i = 0; i < n; i++)
+        sphere_exact<COUNT>(ldg4(P.sphere_geom, i), i, o, d, two_a, four_a, closest, obj, index, t_hit, tally);
+    tally.add(CTR_PLANE_TESTS);
+    plane_exact_num<COUNT>(plane_numerator(o), o, d, closest, obj, t_hit, tally);
+}
+
+// ---- certificate-guided query ---------------------------------------------------------------------------
+// Float certificates (trt_cert.h) classify every sphere against the ray; only the spheres they cannot decide
+// are evaluated exactly, each lane walking its own survivors in index order (tie-breaking preserved).
+//   Q_CLOSEST: returns false; (obj, index, t_hit) = the closest hit over all objects, as trace_ray finds it.
+//   Q_DIR / Q_POINT: returns true when a certificate proves the light BLOCKED.  Otherwise (obj, t_hit) is the
+//     closest hit among the objects that can still matter — every other object is proven either not hit or,
+//     for a point light, hit only beyond the light (farther than any hit that could block) — so the caller's
+//     decision on it equals the reference's decision on the closest hit over all objects.
+// num_g = plane_numerator(o) (shadow queries; ignored by Q_CLOSEST).  CONST_RECORDS: records in __constant__.
+template <int MODE, bool CONST_RECORDS>
+__device__ __forceinline__ bool query_certified(const RenderParams &P, const trt_cert_ray &rf, const d3 &o, const d3 &d, float near_limit,
+                                                float far_limit, double num_g, double dir_plane_denom, bool ground_candidate, int &obj,
+                                                int &index, double &t_hit, unsigned int *exact_tests)
+{
+    const Tally<false> no_tally{nullptr};
+    double closest = INFINITY;
+    obj = 0;
+    index = -1;
+    t_hit = 0.0;
+    const double a = dot(d, d);
+    const double two_a = 2.0 * a, four_a = 4.0 * a;
+    const int n = c_scene.num_spheres;
+    const bool usable = rf.usable != 0;
+    bool blocked = false;
+    for (int base = 0; base < n; base += 32) {
+        const int cnt = min(32, n - base);
+        // pass 1 (float, branch-free, warp-uniform record addresses): classify the spheres of this chunk.
+        // The records are padded to an even count (pad records are masked off below): two tests per trip.
+        unsigned int survivors = 0;
+#pragma unroll 1
+        for (int j = 0; j < cnt; j += 2) {
+            const float4 g0 = CONST_RECORDS ? c_sphere_cull[base + j] : __ldg(&P.sphere_cull[base + j]);
+            const float4 g1 = CONST_RECORDS ? c_sphere_cull[base + j + 1] : __ldg(&P.sphere_cull[base + j + 1]);
+            unsigned int s0, s1;
+            if (MODE == Q_CLOSEST) {
+                s0 = trt_cert_sphere_miss(&rf, g0.x, g0.y, g0.z, g0.w) ? 0u : 1u;
+                s1 = trt_cert_sphere_miss(&rf, g1.x, g1.y, g1.z, g1.w) ? 0u : 2u;
+            } else {
+                const int k0 = trt_cert_sphere(&rf, g0.x, g0.y, g0.z, g0.w, near_limit, far_limit);
+                const int k1 = trt_cert_sphere(&rf, g1.x, g1.y, g1.z, g1.w, near_limit, far_limit);
+                s0 = (k0 & TRT_CERT_MISS) ? 0u : 1u;
+                s1 = (k1 & TRT_CERT_MISS) ? 0u : 2u;
+                // a pad record (j + 1 == cnt, radius 0) cannot block: inner = -slack < 0
+                blocked = blocked || ((k0 | k1) & TRT_CERT_BLOCKS);
+            }
+            survivors |= (s0 | s1) << j;
+        }
+        const unsigned int valid = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+        survivors = usable ? (survivors & valid) : valid;
+        if (MODE != Q_CLOSEST && usable && blocked) survivors = 0;
+        if (exact_tests) *exact_tests += (unsigned int)__popc(survivors);
+        // pass 2 (double, exact): each lane walks its own survivors in index order
+        while (survivors) {
+            const int j = __ffs(survivors) - 1;
+            survivors &= survivors - 1;
+            sphere_exact<false>(ldg4(P.sphere_geom, base + j), base + j, o, d, two_a, four_a, closest, obj, index, t_hit, no_tally);
+        }
+    }
+    blocked = blocked && usable;
+    if (MODE == Q_CLOSEST) {
+        if (!trt_cert_plane_miss(&rf, c_scene.ground_point_f[0], c_scene.ground_point_f[1], c_scene.ground_point_f[2],
+                                 c_scene.ground_normal_f[0], c_scene.ground_normal_f[1], c_scene.ground_normal_f[2]))
+            plane_exact_num<false>(plane_numerator(o), o, d, closest, obj, t_hit, no_tally);
+        return false;
+    }
+    if (MODE == Q_DIR) {
+        // any hit blocks.  The ground (TRT.c:677-695): numerator and denominator are the reference's own doubles
+        // (the denominator is a per-light constant); opposite signs or a zero numerator give t <= 0, a miss,
+        // without the division.
+        if (!blocked && obj == 0 && fabs(dir_plane_denom) > 0.00001 && num_g != 0.0 && ((num_g < 0.0) == (dir_plane_denom < 0.0))) {
+            const double t = ieee_div(num_g, dir_plane_denom);
+            if (t > 0.00001) obj = 2;
+        }
+        return blocked;
+    }
+    // Q_POINT
+    if (!blocked && ground_candidate) plane_exact_num<false>(num_g, o, d, closest, obj, t_hit, no_tally);
+    return blocked;
 }
 
 // hit point pushed back toward the ray origin by EPSILON, TRT.c:871-874
@@ -298,29 +324,148 @@ __device__ __forceinline__ d3 push_back(const d3 &o, const d3 &hit)
     return hit + back;
 }
 
-__device__ __forceinline__ const DevMaterial *surface_material(const RenderParams &P, int obj, int index)
+// The three kinds of queries the light loop and the bounce need, in every build flavour:
+//   CULL == 0 or COUNT: all-FP64 reference-order query (COUNT tallies the reference's work counters);
+//   otherwise the certificate-guided query.  COUNT with CULL != 0 runs BOTH and reports any disagreement of the
+//   final answers in CTR_CULL_VIOLATIONS (the on-device audit of the certificates and of the survivor logic).
+struct ShadowOrigin {
+    trt_cert_ray rf;     // origin filled in, direction per query
+    float S0;            // |origin|_1 + max centre |.|_1
+    double num_g;        // plane_numerator(origin)
+};
+
+template <bool COUNT, int CULL>
+__device__ __forceinline__ void closest_hit_bounce(const RenderParams &P, const ShadowOrigin &so, const d3 &o, const d3 &d, int &obj, int &index,
+                                                   double &t_hit, const Tally<COUNT> &tally)
 {
-    return (obj == 1) ? &P.sphere_mat[index] : (index ? &c_scene.ground_odd : &c_scene.ground_even);
+    if (COUNT || CULL == 0) query_reference<COUNT>(P, o, d, obj, index, t_hit, tally);
+    if (CULL != 0) {
+        trt_cert_ray rf = so.rf;
+        trt_cert_set_unit_dir(&rf, d.x, d.y, d.z, so.S0);
+        int obj2, index2;
+        double t2;
+        unsigned int exact = 0;
+        query_certified<Q_CLOSEST, CULL == 1>(P, rf, o, d, 0.f, 0.f, 0.0, 0.0, false, obj2, index2, t2, COUNT ? &exact : nullptr);
+        if (COUNT) {
+            tally.add(CTR_EXACT_SPHERE_TESTS, exact);
+            if (obj2 != obj || (obj && (__double_as_longlong(t2) != __double_as_longlong(t_hit) || (obj == 1 && index2 != index))))
+                tally.add(CTR_CULL_VIOLATIONS);
+        } else {
+            obj = obj2;
+            index = index2;
+            t_hit = t2;
+        }
+    }
+}
+
+// is directional light `l` visible from o?  (TRT.c:903-908)
+template <bool COUNT, int CULL>
+__device__ __forceinline__ bool dir_light_open(const RenderParams &P, const ShadowOrigin &so, const d3 &o, int l, const Tally<COUNT> &tally)
+{
+    const DevLightDir &Ld = c_scene.dir[l];
+    const d3 L = mk3(Ld.L[0], Ld.L[1], Ld.L[2]);
+    bool open = false;
+    if (COUNT || CULL == 0) {
+        int obj, index;
+        double t_hit;
+        tally.add(CTR_TRACE_CALLS);
+        query_reference<COUNT>(P, o, L, obj, index, t_hit, tally);
+        if (obj) tally.add(CTR_TRACE_HITS);
+        else { tally.add(CTR_SKY_LOOKUPS); tally.add(CTR_SKY_SKIPPED); }
+        open = obj == 0;
+    }
+    if (CULL != 0) {
+        trt_cert_ray rf = so.rf;
+        rf.dx = Ld.Lf[0]; rf.dy = Ld.Lf[1]; rf.dz = Ld.Lf[2];
+        const float dd = fmaf(rf.dz, rf.dz, fmaf(rf.dy, rf.dy, rf.dx * rf.dx));
+        rf.slack_t = (32.0f * TRT_CERT_U) * so.S0;
+        rf.usable = (so.S0 < 1e15f) && (dd > 0.99999f) && (dd < 1.00001f);
+        int obj2, index2;
+        double t2;
+        unsigned int exact = 0;
+        const bool blocked = query_certified<Q_DIR, CULL == 1>(P, rf, o, L, INFINITY, INFINITY, so.num_g, Ld.plane_denom, false, obj2, index2, t2,
+                                                              COUNT ? &exact : nullptr);
+        const bool open2 = !blocked && obj2 == 0;
+        if (COUNT) {
+            tally.add(CTR_EXACT_SPHERE_TESTS, exact);
+            if (open2 != open) tally.add(CTR_CULL_VIOLATIONS);
+        } else {
+            open = open2;
+        }
+    }
+    return open;
+}
+
+// is point light `l` visible from o?  d = unit(light - o), light_d2 = |light - o|^2 (TRT.c:929-941)
+template <bool COUNT, int CULL>
+__device__ __forceinline__ bool point_light_open(const RenderParams &P, const ShadowOrigin &so, const d3 &o, const d3 &d, double light_d2, int l,
+                                                 const Tally<COUNT> &tally)
+{
+    const DevLightPoint &Lp = c_scene.point[l];
+    bool open = false;
+    if (COUNT || CULL == 0) {
+        int obj, index;
+        double t_hit;
+        tally.add(CTR_TRACE_CALLS);
+        query_reference<COUNT>(P, o, d, obj, index, t_hit, tally);
+        if (obj) tally.add(CTR_TRACE_HITS);
+        else { tally.add(CTR_SKY_LOOKUPS); tally.add(CTR_SKY_SKIPPED); }
+        open = obj == 0;
+        if (!open) {
+            const d3 hit = mk3(o.x + t_hit * d.x, o.y + t_hit * d.y, o.z + t_hit * d.z);
+            const d3 to_blocker = push_back(o, hit) - o;
+            open = light_d2 < dot(to_blocker, to_blocker);
+        }
+    }
+    if (CULL != 0) {
+        trt_cert_ray rf = so.rf;
+        const float S = so.S0 + Lp.pos_l1;
+        const float dist = trt_cert_set_dir_toward(&rf, Lp.pos_f[0], Lp.pos_f[1], Lp.pos_f[2], S);
+        const float guard = fmaf(2.0f, rf.slack_t, 1e-5f);
+        const bool ground_candidate = !trt_cert_ground_cannot_block(so.num_g, Lp.height, c_scene.ground_margin);
+        int obj2, index2;
+        double t2;
+        unsigned int exact = 0;
+        const bool blocked = query_certified<Q_POINT, CULL == 1>(P, rf, o, d, dist - guard, dist + guard, so.num_g, 0.0, ground_candidate, obj2, index2,
+                                                                t2, COUNT ? &exact : nullptr);
+        bool open2 = !blocked && obj2 == 0;
+        if (!blocked && obj2 != 0) {
+            const d3 hit = mk3(o.x + t2 * d.x, o.y + t2 * d.y, o.z + t2 * d.z);
+            const d3 to_blocker = push_back(o, hit) - o;
+            open2 = light_d2 < dot(to_blocker, to_blocker);
+        }
+        if (COUNT) {
+            tally.add(CTR_EXACT_SPHERE_TESTS, exact);
+            if (open2 != open) tally.add(CTR_CULL_VIOLATIONS);
+        } else {
+            open = open2;
+        }
+    }
+    return open;
+}
+
+__device__ __forceinline__ void set_shadow_origin(ShadowOrigin &so, const d3 &o, bool need_plane)
+{
+    so.S0 = trt_cert_set_origin(&so.rf, o.x, o.y, o.z) + c_scene.filter_centre_l1;
+    so.rf.dx = so.rf.dy = so.rf.dz = 0.f;
+    so.rf.slack_t = 0.f;
+    so.rf.usable = 0;
+    so.num_g = need_plane ? plane_numerator(o) : 0.0;
 }
 
 // ---- K1 ------------------------------------------------------------------------------------------------
-// One loop, one ray per trip.  Every step of the trip appears ONCE in the instruction stream (one
-// normalisation of the ray direction, one closest-hit query, one push-back, one normal/sky normalisation,
-// one accumulate, one reflect, one shadow-ray setup) and is predicated by the lane's state, so primary,
-// bounce and shadow rays of different lanes execute the same instructions, and the loop body stays small
-// enough for the instruction caches (an earlier version that inlined trace_ray's callees per call site was
-// 41 KB of SASS and stalled on instruction fetch as soon as occupancy was raised; profiles/).
 template <bool COUNT, int CULL>
 __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(const RenderParams P)
 {
-    __shared__ double s_byte_to_unit[256]; // k/255.0 (TRT.c:866), evaluated on the host in double
-    __shared__ unsigned int s_tile[WARPS_PER_CTA];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_byte_to_unit = reinterpret_cast<double *>(smem_raw);   // k/255.0 (TRT.c:866), evaluated on the host in double
     for (int k = threadIdx.x; k < 256; k += CTA_THREADS) s_byte_to_unit[k] = P.byte_to_unit[k];
     __syncthreads();
 
     const Tally<COUNT> tally{P.counters};
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    WarpShared &W = reinterpret_cast<WarpShared *>(smem_raw + SMEM_TABLE_BYTES)[warp];
     const int band_rows = P.row1 - P.row0;
     const int tiles_x = (P.width + TILE_W - 1) / TILE_W;
     const int tiles_y = (band_rows + TILE_H - 1) / TILE_H;
@@ -329,24 +474,27 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
     const double sw = c_scene.screen_width, sh = c_scene.screen_height;
     const double pixel_w = sw / P.width;   // TRT.c:981
     const double pixel_h = sh / P.height;  // TRT.c:982
-    const int num_dir = c_scene.num_dir;
-    const int num_lights = num_dir + c_scene.num_point;
+    const int num_dir = c_scene.num_dir, num_point = c_scene.num_point;
+    const int num_spheres = c_scene.num_spheres;
+    const d3 eye = mk3(c_scene.eye[0], c_scene.eye[1], c_scene.eye[2]);
     // (double)col / (double)width and (double)row / (double)height (TRT.c:987-988) through shared reciprocals:
     // numerators are integers >= 1 (0 is special-cased), far inside the fast path of the IEEE division
     const Reciprocal inv_w = reciprocal_of((double)P.width), inv_h = reciprocal_of((double)P.height);
+    // tile certificates need the masks to fit; bigger scenes send primary rays through the per-ray certificates
+    const bool tile_certs = CULL != 0 && num_spheres <= 32 * TMASK_WORDS;
+    const int mask_words = (num_spheres + 31) >> 5;
 
     for (;;) {
-        if (lane == 0) s_tile[warp] = atomicAdd(P.tile_counter, 1u);
-        __syncwarp();
-        const unsigned int tile = s_tile[warp];
-        __syncwarp();
+        unsigned int tile = 0;
+        if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= num_tiles) break;
         const int ty = (int)(tile / (unsigned)tiles_x), tx = (int)(tile % (unsigned)tiles_x);
         const int col = tx * TILE_W + (lane & (TILE_W - 1));
         const int brow = ty * TILE_H + (lane >> 3); // band-local row
         const int row = P.row0 + brow;
-        if (col >= P.width || brow >= band_rows) continue; // lane idles for this tile
-        tally.add(CTR_PIXELS);
+        const bool valid = col < P.width && brow < band_rows;
+        if (valid) tally.add(CTR_PIXELS);
 
         // per-pixel part of the primary ray, TRT.c:987-988
         const double fx = col ? div_by_unchecked((double)col, inv_w) : 0.0;
@@ -354,191 +502,290 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
         const double sx0 = (fx * sw - sw / 2.0);
         const double sy0 = -(fy * sh - sh / 2.0);
 
-        d3 average = mk3(0.0, 0.0, 0.0);
-        // ---- per-lane ray state ------------------------------------------------------------------
-        int k = 0;                         // sample index (ray_num)
-        int phase = PH_MAIN;
-        int bounces = 0;
-        int light = 0;                     // index of the light whose shadow ray is in flight
-        int surf_obj = 0, surf_index = 0;  // what the main ray hit
-        double weight = 1.0, weight_sum = 0.0, light_d2 = 0.0, intensity = 0.0;
-        d3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), d_main = d, nrm = d, lit = d, sample = d;
-        bool fresh = true;                 // start the next sample of this pixel
-        bool raw_dir = false;              // d still has to be normalised
-        unsigned int trips = 0;            // closest-hit queries of this pixel (cost estimate for band balancing)
-
-        for (;;) {
-            if (fresh) {
-                if (k == TRT_RAYS_PER_PIXEL) break;
-                // primary ray of sample k, TRT.c:987-1016
-                tally.add(CTR_SAMPLES);
-                const double sx = sx0 + c_scene.sub_dx[k] * pixel_w;
-                const double sy = sy0 + c_scene.sub_dy[k] * pixel_h;
-                const double sz = -c_scene.screen_distance;
-                d3 sp = mk3(0.0, 0.0, 0.0);
-                sp = sp + mk3(c_scene.bx[0] * sx, c_scene.bx[1] * sx, c_scene.bx[2] * sx);
-                sp = sp + mk3(c_scene.by[0] * sy, c_scene.by[1] * sy, c_scene.by[2] * sy);
-                sp = sp + mk3(c_scene.bz[0] * sz, c_scene.bz[1] * sz, c_scene.bz[2] * sz);
-                o = mk3(c_scene.eye[0], c_scene.eye[1], c_scene.eye[2]);
-                d = sp - o;                 // TRT.c:1005 (origin subtracted from an untranslated vector)
-                raw_dir = true;
-                sample = mk3(0.0, 0.0, 0.0);
-                bounces = 0;
-                weight = 1.0;
-                weight_sum = 0.0;
-                phase = PH_MAIN;
-                fresh = false;
+        // ---- tile certificates (float): which spheres can any primary ray of this tile hit at all? the ground?
+        bool tile_ground_miss = false;
+        if (tile_certs) {
+            const trt_cert_camera &cam = c_scene.cam_f;
+            float Dx, Dy, Dz, hx, hy;
+            trt_cert_tile_cone(&cam, tx * TILE_W, P.row0 + ty * TILE_H, TILE_W, TILE_H, P.width, P.height, &Dx, &Dy, &Dz, &hx, &hy);
+            const float h = fmaf(hx, cam.nbx, hy * cam.nby);
+            const float S = c_scene.eye_l1 + c_scene.filter_centre_l1;
+            for (int wd = 0; wd < mask_words; wd++) {
+                const int i = wd * 32 + lane;
+                bool keep = false;
+                if (i < num_spheres) {
+                    const float4 g = __ldg(&P.sphere_cull[i]);
+                    keep = !(c_scene.filter_enabled && trt_cert_tile_sphere_miss(cam.ex, cam.ey, cam.ez, Dx, Dy, Dz, h, g.x, g.y, g.z, g.w, S));
+                }
+                const unsigned int m = __ballot_sync(0xffffffffu, keep);
+                if (lane == 0) W.tmask[wd] = m;
             }
-            // (1) the one normalisation of a ray direction: primary (TRT.c:1008), reflected (1055), point-light (933)
-            if (raw_dir) d = unit(d);
+            const float *gn = c_scene.ground_normal_f;
+            const float dn = fmaf(Dz, gn[2], fmaf(Dy, gn[1], Dx * gn[0]));
+            const float bxn = fmaf(cam.bx[2], gn[2], fmaf(cam.bx[1], gn[1], cam.bx[0] * gn[0]));
+            const float byn = fmaf(cam.by[2], gn[2], fmaf(cam.by[1], gn[1], cam.by[0] * gn[0]));
+            const float scale = (fabsf(Dx) + fabsf(Dy) + fabsf(Dz) + 2.0f * h) * c_scene.ground_normal_l1;
+            const int sgn = c_scene.filter_enabled ? trt_cert_tile_plane_sign(dn, bxn, byn, hx, hy, scale) : 0;
+            // numerator < 0 with every denominator > 0 (or the mirror image): t < 0 for every primary ray of the tile
+            tile_ground_miss = (c_scene.prim_num_sign < 0 && sgn > 0) || (c_scene.prim_num_sign > 0 && sgn < 0);
+        }
+        __syncwarp();
 
-            // (2) the one closest-hit query
-            trips++;
-            int obj, index;
-            d3 hit;
-            const bool is_main = phase == PH_MAIN;
-            tally.add(CTR_TRACE_CALLS);
-            if (is_main) tally.add(CTR_BOUNCE_ITERS);
-            closest_hit<COUNT, CULL>(P, o, d, obj, index, hit, tally);
-            if (obj != 0) tally.add(CTR_TRACE_HITS);
-            else { tally.add(CTR_SKY_LOOKUPS); if (!is_main) tally.add(CTR_SKY_SKIPPED); }
+        int round = 0;            // next sample index to produce
+        int qhead = 0, qcount = 0;
 
-            // (3) the one push-back (TRT.c:871-874); a directional light's shadow ray only needs hit / no hit
-            const bool point_shadow = !is_main && light >= num_dir;
-            d3 at = o;
-            if (obj != 0 && (is_main || point_shadow)) at = push_back(o, hit);
-
-            bool shade_done = false, sample_done = false, have_colour = false;
-            d3 colour = mk3(0.0, 0.0, 0.0);
-            if (is_main) {
-                // (4) the one normal / sky normalisation: unit(hit - centre) or unit(ground normal) on a hit
-                //     (TRT.c:878), unit(direction) once more for the cubemap lookup on a miss (TRT.c:702)
-                d3 v = d;
-                if (obj == 1) {
-                    const double4 g = ldg_geom(P.sphere_geom, index);
-                    v = mk3(hit.x - g.x, hit.y - g.y, hit.z - g.z);   // TRT.c:824
-                } else if (obj == 2) {
-                    v = mk3(c_scene.ground_normal[0], c_scene.ground_normal[1], c_scene.ground_normal[2]);
-                }
-                const d3 u = unit(v);
-                if (obj == 0) {
-                    // sky: TRT.c:858-867; the sample ends here
-                    int face;
-                    const int texel = sky_texel_index(u, c_scene.sky_dim, face);
-                    const uchar4 t = __ldg(&P.sky[(size_t)face * (size_t)c_scene.sky_face_stride + (size_t)texel]);
-                    colour = mk3(s_byte_to_unit[t.x], s_byte_to_unit[t.y], s_byte_to_unit[t.z]);
-                    have_colour = true;
-                    sample_done = true;
-                } else {
-                    // surface hit: remember it, start the light loop (apply_lighting, TRT.c:894-963)
-                    tally.add(CTR_LIGHTING_CALLS);
-                    surf_obj = obj;
-                    surf_index = index;
-                    nrm = u;
-                    d_main = d;
-                    o = at;
-                    lit = mk3(0.0, 0.0, 0.0);
-                    light = 0;
-                    if (num_lights == 0) shade_done = true;
-                    else phase = PH_SHADOW;
-                }
-            } else {
-                // ---- a shadow ray came back: add this light's contribution ---------------------------
-                bool open = (obj == 0);
-                double f = 1.0;
-                const double *lc;
-                if (light < num_dir) {                                    // TRT.c:908-921
-                    lc = c_scene.dir[light].color;
-                } else {                                                  // TRT.c:939-954
-                    if (!open) {
-                        const d3 to_blocker = at - o;
-                        open = light_d2 < dot(to_blocker, to_blocker);
+        while (round < TRT_RAYS_PER_PIXEL || qcount > 0) {
+            if (qcount < 32 && round < TRT_RAYS_PER_PIXEL) {
+                // =========================== PRODUCE: primary rays of sample `round` ==============================
+                const int k = round++;
+                bool hit_surface = false;
+                d3 d = mk3(0.0, 0.0, 0.0);
+                double t_hit = 0.0;
+                int obj = 0, index = -1;
+                if (valid) {
+                    tally.add(CTR_SAMPLES);
+                    tally.add(CTR_BOUNCE_ITERS);
+                    tally.add(CTR_TRACE_CALLS);
+                    const double sx = sx0 + c_scene.sub_dx[k] * pixel_w;      // TRT.c:992
+                    const double sy = sy0 + c_scene.sub_dy[k] * pixel_h;      // TRT.c:993
+                    const double sz = -c_scene.screen_distance;
+                    d3 sp = mk3(0.0, 0.0, 0.0);
+                    sp = sp + mk3(c_scene.bx[0] * sx, c_scene.bx[1] * sx, c_scene.bx[2] * sx);
+                    sp = sp + mk3(c_scene.by[0] * sy, c_scene.by[1] * sy, c_scene.by[2] * sy);
+                    sp = sp + mk3(c_scene.bz[0] * sz, c_scene.bz[1] * sz, c_scene.bz[2] * sz);
+                    d = unit(sp - eye);         // TRT.c:1005 (origin subtracted from an untranslated vector), 1008
+                    if (COUNT || CULL == 0) query_reference<COUNT>(P, eye, d, obj, index, t_hit, tally);
+                    if (CULL != 0) {
+                        int obj2 = 0, index2 = -1;
+                        double t2 = 0.0;
+                        unsigned int exact = 0;
+                        if (tile_certs) {
+                            // exact tests of the tile's candidate spheres; oc and c of TRT.c:640-648 are per-frame
+                            // constants for rays leaving the eye (host-evaluated with the reference's operations)
+                            const Tally<false> no_tally{nullptr};
+                            double closest = INFINITY;
+                            const double a = dot(d, d);
+                            const double two_a = 2.0 * a, four_a = 4.0 * a;
+                            for (int wd = 0; wd < mask_words; wd++) {
+                                unsigned int m = W.tmask[wd];
+                                exact += (unsigned int)__popc(m);
+                                while (m) {
+                                    const int i = wd * 32 + __ffs(m) - 1;
+                                    m &= m - 1;
+                                    const double4 g = ldg4(P.sphere_prim, i);
+                                    sphere_exact_oc<false>(mk3(g.x, g.y, g.z), g.w, i, eye, d, two_a, four_a, closest, obj2, index2, t2, no_tally);
+                                }
+                            }
+                            if (!tile_ground_miss) plane_exact_num<false>(c_scene.prim_num, eye, d, closest, obj2, t2, no_tally);
+                        } else {
+                            trt_cert_ray rf;
+                            const float S = trt_cert_set_origin(&rf, eye.x, eye.y, eye.z) + c_scene.filter_centre_l1;
+                            trt_cert_set_unit_dir(&rf, d.x, d.y, d.z, S);
+                            rf.usable = rf.usable && c_scene.filter_enabled;
+                            query_certified<Q_CLOSEST, false>(P, rf, eye, d, 0.f, 0.f, 0.0, 0.0, false, obj2, index2, t2, COUNT ? &exact : nullptr);
+                        }
+                        if (COUNT) {
+                            tally.add(CTR_EXACT_SPHERE_TESTS, exact);
+                            if (obj2 != obj || (obj && (__double_as_longlong(t2) != __double_as_longlong(t_hit) || (obj == 1 && index2 != index))))
+                                tally.add(CTR_CULL_VIOLATIONS);
+                        } else {
+                            obj = obj2;
+                            index = index2;
+                            t_hit = t2;
+                        }
                     }
-                    lc = c_scene.point[light - num_dir].color;
-                    f = intensity;
+                    if (obj == 0) {
+                        // the sample sees the sky: weight 1, weight_sum 1, so the sample IS the texel colour
+                        // (c*1.0, 0.0 + c, c*(1.0/1.0) are exact), TRT.c:1034-1035, 1051, 1061
+                        tally.add(CTR_SKY_LOOKUPS);
+                        if (COUNT) atomicAdd(&P.counters[CTR_BOUNCE_HIST0], 1ull);
+                        const d3 c = sky_colour(P, s_byte_to_unit, d);
+                        W.res[0][k * 32 + lane] = c.x;
+                        W.res[1][k * 32 + lane] = c.y;
+                        W.res[2][k * 32 + lane] = c.z;
+                    } else {
+                        tally.add(CTR_TRACE_HITS);
+                        hit_surface = true;
+                    }
                 }
-                if (open) {
-                    const DevMaterial *m = surface_material(P, surf_obj, surf_index);
-                    const double lambert = fmin(dot(nrm, d), 1.0);
-                    if (light >= num_dir) f = f * lambert; else f = lambert;
-                    d3 diffuse = mk3(lc[0] * f, lc[1] * f, lc[2] * f);
-                    diffuse = hadamard(diffuse, mk3(m->color[0], m->color[1], m->color[2]));
-                    lit = lit + diffuse;
+                const unsigned int pushers = __ballot_sync(0xffffffffu, hit_surface);
+                if (hit_surface) {
+                    const int slot = (qhead + qcount + __popc(pushers & ((1u << lane) - 1u))) & (QCAP - 1);
+                    W.ox[slot] = eye.x; W.oy[slot] = eye.y; W.oz[slot] = eye.z;
+                    W.dx[slot] = d.x; W.dy[slot] = d.y; W.dz[slot] = d.z;
+                    W.t[slot] = t_hit;
+                    W.sr[slot] = 0.0; W.sg[slot] = 0.0; W.sb[slot] = 0.0;
+                    W.w[slot] = 1.0; W.ws[slot] = 0.0;
+                    W.meta[slot] = (unsigned)lane | ((unsigned)k << 5) | ((unsigned)obj << 13);
+                    W.index[slot] = index;
                 }
-                light++;
-                if (light == num_lights) shade_done = true;
-            }
+                qcount += __popc(pushers);
+                __syncwarp();
+            } else {
+                // =========================== CONSUME: up to 32 queued surface hits ================================
+                const int n_rec = min(32, qcount);
+                const bool active = lane < n_rec;
+                const int slot = (qhead + lane) & (QCAP - 1);
+                d3 o = mk3(0, 0, 0), d = o, sample = o;
+                double t_hit = 0.0, weight = 0.0, weight_sum = 0.0;
+                unsigned int meta = 0;
+                int index = 0;
+                if (active) {
+                    o = mk3(W.ox[slot], W.oy[slot], W.oz[slot]);
+                    d = mk3(W.dx[slot], W.dy[slot], W.dz[slot]);
+                    t_hit = W.t[slot];
+                    sample = mk3(W.sr[slot], W.sg[slot], W.sb[slot]);
+                    weight = W.w[slot];
+                    weight_sum = W.ws[slot];
+                    meta = W.meta[slot];
+                    index = W.index[slot];
+                }
+                qhead = (qhead + n_rec) & (QCAP - 1);
+                qcount -= n_rec;
+                __syncwarp();     // every pop is done before any push below may reuse a slot
 
-            if (shade_done) {
-                colour.x = clampd(lit.x, 0.0, 1.0);                       // TRT.c:960
-                colour.y = clampd(lit.y, 0.0, 1.0);
-                colour.z = clampd(lit.z, 0.0, 1.0);
-                have_colour = true;
-            }
-            // (5) the one accumulate, TRT.c:1034-1035, 1051
-            if (have_colour) {
-                weight_sum += weight;
-                colour = colour * weight;
-                sample = sample + colour;
-            }
-            if (shade_done) {
-                weight *= surface_material(P, surf_obj, surf_index)->reflectivity;   // TRT.c:1041-1042
-                bounces++;
-                if (bounces < TRT_BOUNCE_LIMIT && weight > 0.00001) {      // loop condition, TRT.c:1018
-                    // (6) the one reflect, TRT.c:627-633; normalised at the top of the next trip
-                    const double dn = dot(d_main, nrm);
-                    d = mk3(d_main.x - 2.0 * dn * nrm.x, d_main.y - 2.0 * dn * nrm.y, d_main.z - 2.0 * dn * nrm.z);
-                    raw_dir = true;
-                    phase = PH_MAIN;                                      // the origin o already is the surface point
-                } else {
-                    sample_done = true;
+                bool push = false;
+                if (active) {
+                    const int pix = (int)(meta & 31u), k = (int)((meta >> 5) & 15u);
+                    int bounces = (int)((meta >> 9) & 15u);
+                    const int obj = (int)((meta >> 13) & 3u);
+                    if (P.row_cost) atomicAdd(&P.row_cost[ty * TILE_H + (pix >> 3)], 25u);
+                    tally.add(CTR_LIGHTING_CALLS);
+
+                    // the surface point (TRT.c:663-665 / 690-692), pushed back by EPSILON (871-874), and its normal (878)
+                    const d3 hit = mk3(o.x + t_hit * d.x, o.y + t_hit * d.y, o.z + t_hit * d.z);
+                    const d3 at = push_back(o, hit);
+                    d3 nrm;
+                    const DevMaterial *mat;
+                    if (obj == 1) {
+                        const double4 g = ldg4(P.sphere_geom, index);
+                        nrm = unit(mk3(hit.x - g.x, hit.y - g.y, hit.z - g.z));   // TRT.c:824, 878
+                        mat = &P.sphere_mat[index];
+                    } else {
+                        nrm = mk3(c_scene.ground_unit_normal[0], c_scene.ground_unit_normal[1], c_scene.ground_unit_normal[2]);
+                        const int odd = x86_int(floor(hit.x) + floor(hit.z)) & 1;  // checker parity, TRT.c:850
+                        mat = odd ? &c_scene.ground_odd : &c_scene.ground_even;
+                    }
+                    const d3 mcol = mk3(mat->color[0], mat->color[1], mat->color[2]);
+
+                    // ---- apply_lighting, TRT.c:894-963 ---------------------------------------------------------
+                    ShadowOrigin so;
+                    set_shadow_origin(so, at, (num_dir + num_point) > 0);
+                    if (!c_scene.filter_enabled) so.S0 = INFINITY;    // makes every certificate ray unusable
+                    d3 lit = mk3(0.0, 0.0, 0.0);
+                    for (int l = 0; l < num_dir; l++) {
+                        if (dir_light_open<COUNT, CULL>(P, so, at, l, tally)) {
+                            const DevLightDir &Ld = c_scene.dir[l];
+                            const double f = fmin(dot(nrm, mk3(Ld.L[0], Ld.L[1], Ld.L[2])), 1.0);         // TRT.c:910
+                            d3 diffuse = mk3(Ld.color[0] * f, Ld.color[1] * f, Ld.color[2] * f);
+                            diffuse = hadamard(diffuse, mcol);
+                            lit = lit + diffuse;
+                        }
+                    }
+                    for (int l = 0; l < num_point; l++) {
+                        const DevLightPoint &Lp = c_scene.point[l];
+                        d3 ld = mk3(Lp.pos[0] - at.x, Lp.pos[1] - at.y, Lp.pos[2] - at.z);                // TRT.c:929
+                        const double light_d2 = dot(ld, ld);
+                        ld = unit(ld);                                                                    // TRT.c:933
+                        if (point_light_open<COUNT, CULL>(P, so, at, ld, light_d2, l, tally)) {
+                            const double intensity = clampd(ieee_div(Lp.intensity, light_d2), 0.0, 1.0);  // TRT.c:931
+                            const double f = intensity * fmin(dot(nrm, ld), 1.0);                         // TRT.c:943
+                            d3 diffuse = mk3(Lp.color[0] * f, Lp.color[1] * f, Lp.color[2] * f);
+                            diffuse = hadamard(diffuse, mcol);
+                            lit = lit + diffuse;
+                        }
+                    }
+                    d3 colour = mk3(clampd(lit.x, 0.0, 1.0), clampd(lit.y, 0.0, 1.0), clampd(lit.z, 0.0, 1.0));   // TRT.c:960
+
+                    // ---- accumulate, TRT.c:1034-1051 -----------------------------------------------------------
+                    weight_sum += weight;
+                    colour = colour * weight;
+                    sample = sample + colour;
+                    weight *= mat->reflectivity;                                     // TRT.c:1041-1042
+                    bounces++;
+                    bool done = true;
+                    if (bounces < TRT_BOUNCE_LIMIT && weight > 0.00001) {            // loop condition, TRT.c:1018
+                        // ---- reflect (TRT.c:627-633, 1054-1055) and trace the bounce ray from the surface point
+                        const double dn = dot(d, nrm);
+                        const d3 rd = unit(mk3(d.x - 2.0 * dn * nrm.x, d.y - 2.0 * dn * nrm.y, d.z - 2.0 * dn * nrm.z));
+                        tally.add(CTR_BOUNCE_ITERS);
+                        tally.add(CTR_TRACE_CALLS);
+                        int obj2, index2;
+                        double t2;
+                        closest_hit_bounce<COUNT, CULL>(P, so, at, rd, obj2, index2, t2, tally);
+                        if (obj2 == 0) {
+                            tally.add(CTR_SKY_LOOKUPS);
+                            d3 c = sky_colour(P, s_byte_to_unit, rd);
+                            weight_sum += weight;
+                            c = c * weight;
+                            sample = sample + c;
+                        } else {
+                            tally.add(CTR_TRACE_HITS);
+                            done = false;
+                            push = true;
+                            o = at;
+                            d = rd;
+                            t_hit = t2;
+                            index = index2;
+                            meta = (unsigned)pix | ((unsigned)k << 5) | ((unsigned)bounces << 9) | ((unsigned)obj2 << 13);
+                        }
+                    }
+                    if (done) {
+                        if (COUNT) atomicAdd(&P.counters[CTR_BOUNCE_HIST0 + bounces], 1ull);
+                        sample = sample * ieee_div(1.0, weight_sum);                 // TRT.c:1061
+                        W.res[0][k * 32 + pix] = sample.x;
+                        W.res[1][k * 32 + pix] = sample.y;
+                        W.res[2][k * 32 + pix] = sample.z;
+                    }
                 }
-            } else if (!sample_done) {
-                // (7) the one shadow-ray setup: aim at light `light` from the surface point o
-                if (light < num_dir) {
-                    const DevLightDir &Ld = c_scene.dir[light];
-                    d = mk3(Ld.L[0], Ld.L[1], Ld.L[2]);                    // unit(-direction), host-evaluated (TRT.c:903-904)
-                    raw_dir = false;
-                } else {
-                    const DevLightPoint &Lp = c_scene.point[light - num_dir];
-                    d = mk3(Lp.pos[0] - o.x, Lp.pos[1] - o.y, Lp.pos[2] - o.z);   // TRT.c:929
-                    light_d2 = dot(d, d);
-                    intensity = clampd(ieee_div(Lp.intensity, light_d2), 0.0, 1.0);         // TRT.c:931
-                    raw_dir = true;
+                const unsigned int pushers = __ballot_sync(0xffffffffu, push);
+                if (push) {
+                    const int ps = (qhead + qcount + __popc(pushers & ((1u << lane) - 1u))) & (QCAP - 1);
+                    W.ox[ps] = o.x; W.oy[ps] = o.y; W.oz[ps] = o.z;
+                    W.dx[ps] = d.x; W.dy[ps] = d.y; W.dz[ps] = d.z;
+                    W.t[ps] = t_hit;
+                    W.sr[ps] = sample.x; W.sg[ps] = sample.y; W.sb[ps] = sample.z;
+                    W.w[ps] = weight; W.ws[ps] = weight_sum;
+                    W.meta[ps] = meta;
+                    W.index[ps] = index;
                 }
-            }
-            if (sample_done) {
-                if (COUNT) atomicAdd(&P.counters[CTR_BOUNCE_HIST0 + bounces], 1ull);
-                sample = sample * ieee_div(1.0, weight_sum);                     // TRT.c:1061
-                average = average + sample;                               // TRT.c:1063
-                k++;
-                fresh = true;
+                qcount += __popc(pushers);
+                __syncwarp();
             }
         }
 
-        if (P.row_cost) atomicAdd(&P.row_cost[brow], trips);
-        average = average * (1.0 / TRT_RAYS_PER_PIXEL);                   // TRT.c:1065
-        const size_t pix = (size_t)brow * (size_t)P.width + (size_t)col;
-        if (P.pixels) {
-            P.pixels[pix * 3 + 0] = average.x;
-            P.pixels[pix * 3 + 1] = average.y;
-            P.pixels[pix * 3 + 2] = average.z;
+        // ---- per pixel: add the samples in order, average, store (TRT.c:1063-1066) ---------------------------
+        if (valid) {
+            d3 average = mk3(0.0, 0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < TRT_RAYS_PER_PIXEL; k++)
+                average = average + mk3(W.res[0][k * 32 + lane], W.res[1][k * 32 + lane], W.res[2][k * 32 + lane]);
+            average = average * (1.0 / TRT_RAYS_PER_PIXEL);
+            if (P.row_cost) atomicAdd(&P.row_cost[brow], 50u);
+            const size_t pix = (size_t)brow * (size_t)P.width + (size_t)col;
+            if (P.pixels) {
+                P.pixels[pix * 3 + 0] = average.x;
+                P.pixels[pix * 3 + 1] = average.y;
+                P.pixels[pix * 3 + 2] = average.z;
+            }
+            if (P.quant) {
+                // the quantisation of buffered_draw_screen, TRT.c:1157-1163: truncation toward zero
+                uchar4 q;
+                q.x = (unsigned char)x86_int(average.x * 255);
+                q.y = (unsigned char)x86_int(average.y * 255);
+                q.z = (unsigned char)x86_int(average.z * 255);
+                q.w = 0;
+                P.quant[pix] = q;
+            }
         }
-        if (P.quant) {
-            // the quantisation of buffered_draw_screen, TRT.c:1157-1163: truncation toward zero
-            uchar4 q;
-            q.x = (unsigned char)x86_int(average.x * 255);
-            q.y = (unsigned char)x86_int(average.y * 255);
-            q.z = (unsigned char)x86_int(average.z * 255);
-            q.w = 0;
-            P.quant[pix] = q;
-        }
+        __syncwarp();   // res and tmask are rewritten by the next tile
     }
 }
 
 // ---- unit-level probe: trace_ray (TRT.c:793-889) for an array of rays, all out-params ---------------
 // Used by the parity tests to compare single queries (hit kind, pushed-back point, unit normal,
-// material incl. the skybox colour on a miss) with the reference, not only whole frames.
+// material incl. the skybox colour on a miss) with the reference, not only whole frames.  Goes through the
+// certificate-guided query when the scene allows it.
 // out: 11 doubles per ray = kind, point[3], normal[3], colour[3], reflectivity
 __global__ void k_probe_trace(const RenderParams P, const double *__restrict__ rays, int n, double *__restrict__ out)
 {
@@ -551,33 +798,36 @@ __global__ void k_probe_trace(const RenderParams P, const double *__restrict__ r
     const d3 d = mk3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
     const Tally<false> tally{nullptr};
     int obj, index;
-    d3 hit;
-    if (c_scene.filter_in_const) closest_hit<false, 1>(P, o, d, obj, index, hit, tally);
-    else closest_hit<false, 2>(P, o, d, obj, index, hit, tally);
+    double t_hit;
+    if (c_scene.filter_enabled) {
+        ShadowOrigin so;
+        set_shadow_origin(so, o, false);
+        if (c_scene.filter_in_const) closest_hit_bounce<false, 1>(P, so, o, d, obj, index, t_hit, tally);
+        else closest_hit_bounce<false, 2>(P, so, o, d, obj, index, t_hit, tally);
+    } else {
+        query_reference<false>(P, o, d, obj, index, t_hit, tally);
+    }
     d3 point, normal, colour;
     double reflectivity = 0.0;
     if (obj == 0) {
         point = o;
-        normal = d;
-        int face;
-        const int texel = sky_texel_index(unit(d), c_scene.sky_dim, face);
-        const uchar4 t = __ldg(&P.sky[(size_t)face * (size_t)c_scene.sky_face_stride + (size_t)texel]);
-        colour = mk3(s_byte_to_unit[t.x], s_byte_to_unit[t.y], s_byte_to_unit[t.z]);
+        normal = unit(d);
+        colour = sky_colour(P, s_byte_to_unit, d);
     } else {
+        const d3 hit = mk3(o.x + t_hit * d.x, o.y + t_hit * d.y, o.z + t_hit * d.z);
         const DevMaterial *m;
         if (obj == 1) {
-            const double4 g = ldg_geom(P.sphere_geom, index);
-            normal = mk3(hit.x - g.x, hit.y - g.y, hit.z - g.z);
+            const double4 g = ldg4(P.sphere_geom, index);
+            normal = unit(mk3(hit.x - g.x, hit.y - g.y, hit.z - g.z));
             m = &P.sphere_mat[index];
         } else {
-            normal = mk3(c_scene.ground_normal[0], c_scene.ground_normal[1], c_scene.ground_normal[2]);
-            m = index ? &c_scene.ground_odd : &c_scene.ground_even;
+            normal = mk3(c_scene.ground_unit_normal[0], c_scene.ground_unit_normal[1], c_scene.ground_unit_normal[2]);
+            m = (x86_int(floor(hit.x) + floor(hit.z)) & 1) ? &c_scene.ground_odd : &c_scene.ground_even;
         }
         colour = mk3(m->color[0], m->color[1], m->color[2]);
         reflectivity = m->reflectivity;
         point = push_back(o, hit);
     }
-    normal = unit(normal);
     double *r = out + (size_t)i * 11;
     r[0] = (double)obj;
     r[1] = point.x; r[2] = point.y; r[3] = point.z;
@@ -684,12 +934,21 @@ void upload_scene_constants(const DevScene &scene, const float4 *cull, int count
         CK(cudaMemcpyToSymbolAsync(c_sphere_cull, cull, sizeof(float4) * (size_t)count, 0, cudaMemcpyHostToDevice, stream));
 }
 
+template <bool COUNT, int CULL>
+static void prepare_kernel()
+{
+    // 58 KB of dynamic shared memory per CTA (ring + finished samples of 4 warps): above the 48 KB default
+    CK(cudaFuncSetAttribute(k_render<COUNT, CULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+}
+
 int render_ctas_per_sm()
 {
     static int cached = 0;
     if (!cached) {
+        prepare_kernel<false, 0>(); prepare_kernel<false, 1>(); prepare_kernel<false, 2>();
+        prepare_kernel<true, 0>(); prepare_kernel<true, 1>(); prepare_kernel<true, 2>();
         int n = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_render<false, 1>, CTA_THREADS, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_render<false, 1>, CTA_THREADS, SMEM_BYTES));
         cached = n > 0 ? n : 1;
     }
     return cached;
@@ -707,13 +966,13 @@ void launch_render(const RenderParams &p, bool count, int cull, int num_sms, cud
     if (grid < 1) grid = 1;
     dim3 g((unsigned)grid), b(CTA_THREADS);
     if (count) {
-        if (cull == 1) k_render<true, 1><<<g, b, 0, stream>>>(p);
-        else if (cull == 2) k_render<true, 2><<<g, b, 0, stream>>>(p);
-        else k_render<true, 0><<<g, b, 0, stream>>>(p);
+        if (cull == 1) k_render<true, 1><<<g, b, SMEM_BYTES, stream>>>(p);
+        else if (cull == 2) k_render<true, 2><<<g, b, SMEM_BYTES, stream>>>(p);
+        else k_render<true, 0><<<g, b, SMEM_BYTES, stream>>>(p);
     } else {
-        if (cull == 1) k_render<false, 1><<<g, b, 0, stream>>>(p);
-        else if (cull == 2) k_render<false, 2><<<g, b, 0, stream>>>(p);
-        else k_render<false, 0><<<g, b, 0, stream>>>(p);
+        if (cull == 1) k_render<false, 1><<<g, b, SMEM_BYTES, stream>>>(p);
+        else if (cull == 2) k_render<false, 2><<<g, b, SMEM_BYTES, stream>>>(p);
+        else k_render<false, 0><<<g, b, SMEM_BYTES, stream>>>(p);
     }
     CK(cudaGetLastError());
 }

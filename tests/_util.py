@@ -11,6 +11,7 @@ from terminalraytracer_b200 import abi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libtrt_oracle.so")
+CERTCHECK_SO = os.path.join(ROOT, "oracle", "_build", "libtrt_certcheck.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libtrt_ref.so")
 REF_ROWS_SO = os.path.join(ROOT, "oracle", "_ref", "libtrt_ref_rows.so")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
@@ -63,6 +64,28 @@ def load_oracle():
     lib.orc_model_flops.restype = C.c_double
     lib.orc_sizeof_counters.restype = C.c_size_t
     return lib
+
+
+CERT_STATS = ("primary", "primary_tile_survivors", "primary_ground_culled", "bounce", "bounce_survivors", "bounce_ground_culled",
+              "bounce_exact_hits", "dir", "dir_open", "dir_blocked", "dir_unknown", "point", "point_open", "point_blocked",
+              "point_unknown", "shadow_exact_tests")
+
+
+def load_certcheck():
+    """oracle/cert_check.c: the product's float certificates (csrc/trt_cert.h) audited on the CPU against the oracle"""
+    if not os.path.exists(CERTCHECK_SO):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    lib = C.CDLL(CERTCHECK_SO)
+    lib.cert_check_rows.restype = C.c_longlong
+    lib.cert_check_rows.argtypes = [C.POINTER(abi.Scene), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+    assert lib.cert_check_num_stats() == len(CERT_STATS)
+    return lib
+
+
+def cert_check(lib, scene, row0=0, row1=None):
+    st = (C.c_longlong * len(CERT_STATS))()
+    bad = lib.cert_check_rows(C.byref(scene.c), scene.width, scene.height, row0, scene.height if row1 is None else row1, st)
+    return bad, dict(zip(CERT_STATS, list(st)))
 
 
 def have_reference_build():
