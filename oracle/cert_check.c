@@ -42,6 +42,7 @@ enum {
     ST_DIR, ST_DIR_OPEN, ST_DIR_BLOCKED, ST_DIR_UNKNOWN,
     ST_POINT, ST_POINT_OPEN, ST_POINT_BLOCKED, ST_POINT_UNKNOWN,
     ST_SHADOW_EXACT_TESTS,
+    ST_TILES, ST_TILES_PATCH, ST_PATCH_DIR_CANDIDATES, ST_PATCH_POINT_CANDIDATES, ST_PATCH_BOUNCE_CANDIDATES, ST_PATCH_RECORDS,
     ST_COUNT
 };
 
@@ -55,6 +56,7 @@ typedef struct {
     float gp[3], gn[3];
     long long *st;
     long long bad;
+    const unsigned char *cand; /* patch certificate: spheres still possible for the query at hand; NULL = all */
 } ctx_t;
 
 /* exact decision of a shadow query as apply_lighting takes it (TRT.c:907, 936-941) */
@@ -81,7 +83,8 @@ static void check_bounce(ctx_t *c, const trt_Ray *ray)
     for (int i = 0; i < s->num_spheres; i++) {
         trt_Point p;
         const int hit = orc_hit_sphere(ray, &s->spheres[i], &p, NULL);
-        const int miss = r.usable && trt_cert_sphere_miss(&r, c->cull[4 * i], c->cull[4 * i + 1], c->cull[4 * i + 2], c->cull[4 * i + 3]);
+        const int miss = (c->cand && !c->cand[i]) ||
+                         (r.usable && trt_cert_sphere_miss(&r, c->cull[4 * i], c->cull[4 * i + 1], c->cull[4 * i + 2], c->cull[4 * i + 3]));
         if (!miss) c->st[ST_BOUNCE_SURVIVORS]++;
         if (hit) c->st[ST_BOUNCE_EXACT_HITS]++;
         if (miss && hit) c->bad++;
@@ -130,7 +133,8 @@ static int cert_dir(ctx_t *c, v3 at, v3 L, int *certified, unsigned char *surviv
     trt_cert_set_unit_dir(&r, L.x, L.y, L.z, S);
     int any_blocks = 0, survivors = 0;
     for (int i = 0; i < s->num_spheres; i++) {
-        const int k = r.usable ? trt_cert_sphere(&r, c->cull[4 * i], c->cull[4 * i + 1], c->cull[4 * i + 2], c->cull[4 * i + 3], INFINITY, INFINITY) : 0;
+        const int k = (c->cand && !c->cand[i]) ? TRT_CERT_MISS :
+                      (r.usable ? trt_cert_sphere(&r, c->cull[4 * i], c->cull[4 * i + 1], c->cull[4 * i + 2], c->cull[4 * i + 3], INFINITY, INFINITY) : 0);
         any_blocks |= (k & TRT_CERT_BLOCKS) != 0;
         survivor[i] = !(k & TRT_CERT_MISS);
         survivors += survivor[i];
@@ -166,7 +170,8 @@ static int cert_point(ctx_t *c, v3 at, const trt_PointLight *pl, int *certified,
     const float near_limit = dist - guard, far_limit = dist + guard;
     int any_blocks = 0, survivors = 0;
     for (int i = 0; i < s->num_spheres; i++) {
-        const int k = r.usable ? trt_cert_sphere(&r, c->cull[4 * i], c->cull[4 * i + 1], c->cull[4 * i + 2], c->cull[4 * i + 3], near_limit, far_limit) : 0;
+        const int k = (c->cand && !c->cand[i]) ? TRT_CERT_MISS :
+                      (r.usable ? trt_cert_sphere(&r, c->cull[4 * i], c->cull[4 * i + 1], c->cull[4 * i + 2], c->cull[4 * i + 3], near_limit, far_limit) : 0);
         any_blocks |= (k & TRT_CERT_BLOCKS) != 0;
         survivor[i] = !(k & TRT_CERT_MISS);
         survivors += survivor[i];
@@ -227,6 +232,7 @@ long long cert_check_rows(const trt_Scene *scene, int W, int H, int row0, int ro
     cc.nbx = trt_cert_round_up(sqrt(dot3(*B[0], *B[0])) * (1.0 + 1e-6));
     cc.nby = trt_cert_round_up(sqrt(dot3(*B[1], *B[1])) * (1.0 + 1e-6));
     cc.sw = (float)cam->screen_width; cc.sh = (float)cam->screen_height; cc.dist = (float)cam->screen_distance;
+    cc.pw = (float)(cam->screen_width / W); cc.ph = (float)(cam->screen_height / H);
     double mx = 0, my = 0;
     for (int k = 0; k < TRT_RAYS_PER_PIXEL; k++) { if (sdx[k] > mx) mx = sdx[k]; if (sdy[k] > my) my = sdy[k]; }
     cc.off_x = trt_cert_round_up(mx); cc.off_y = trt_cert_round_up(my);
@@ -239,6 +245,7 @@ long long cert_check_rows(const trt_Scene *scene, int W, int H, int row0, int ro
     const int prim_sign = prim_num < -1e-9 * gl1 * gnl1 ? -1 : (prim_num > 1e-9 * gl1 * gnl1 ? 1 : 0);
 
     unsigned char *tile_miss = (unsigned char *)malloc(2 * (size_t)(n > 0 ? n : 1)); /* + survivor flags of the shadow queries */
+    unsigned char *patch_cand = (unsigned char *)malloc(33 * 32); /* [16 dir lights | 16 point lights | bounce][32 spheres] */
     for (int ty = row0; ty < row1; ty += TILE_H)
         for (int tx = 0; tx < W; tx += TILE_W) {
             /* tile certificates, as the kernel evaluates them once per tile */
@@ -253,6 +260,50 @@ long long cert_check_rows(const trt_Scene *scene, int W, int H, int row0, int ro
             const float scale = (fabsf(Dx) + fabsf(Dy) + fabsf(Dz) + 2.0f * (hx * cc.nbx + hy * cc.nby)) * (fabsf(c.gn[0]) + fabsf(c.gn[1]) + fabsf(c.gn[2]));
             const int sgn = trt_cert_tile_plane_sign(dn, bxn, byn, hx, hy, scale);
             const int tile_ground_miss = (prim_sign < 0 && sgn > 0) || (prim_sign > 0 && sgn < 0);
+            /* patch certificates: only when no sphere can be hit by the tile's primary rays */
+            int patch_ok = n <= 32 && prim_sign != 0;
+            for (int i = 0; i < n; i++) patch_ok = patch_ok && tile_miss[i];
+            trt_cert_ball ball;
+            ball.ok = 0;
+            stats[ST_TILES]++;
+            if (patch_ok) {
+                trt_cert_patch_ball(&cc, Dx, Dy, Dz, hx, hy, (float)prim_num, c.gn[0], c.gn[1], c.gn[2], S_eye, &ball);
+                patch_ok = ball.ok;
+            }
+            if (patch_ok) {
+                stats[ST_TILES_PATCH]++;
+                const float S_ball = fabsf(ball.cx) + fabsf(ball.cy) + fabsf(ball.cz) + ball.r + c.centre_l1;
+                for (int l = 0; l < scene->num_directional_lights && l < 16; l++) {
+                    v3 L = unit3(scale3(scene->directional_lights[l].direction, -1.0));
+                    for (int i = 0; i < n; i++) {
+                        patch_cand[(size_t)l * 32 + i] = (unsigned char)trt_cert_patch_dir_candidate(&ball, (float)L.x, (float)L.y, (float)L.z, c.cull[4 * i],
+                                                                                                      c.cull[4 * i + 1], c.cull[4 * i + 2], c.cull[4 * i + 3], S_ball);
+                        stats[ST_PATCH_DIR_CANDIDATES] += patch_cand[(size_t)l * 32 + i];
+                    }
+                }
+                for (int l = 0; l < scene->num_point_lights && l < 16; l++) {
+                    const trt_PointLight *pl = &scene->point_lights[l];
+                    const float lx = (float)pl->position.x, ly = (float)pl->position.y, lz = (float)pl->position.z;
+                    for (int i = 0; i < n; i++) {
+                        patch_cand[(size_t)(16 + l) * 32 + i] = (unsigned char)trt_cert_patch_point_candidate(
+                            &ball, lx, ly, lz, c.cull[4 * i], c.cull[4 * i + 1], c.cull[4 * i + 2], c.cull[4 * i + 3], S_ball + fabsf(lx) + fabsf(ly) + fabsf(lz));
+                        stats[ST_PATCH_POINT_CANDIDATES] += patch_cand[(size_t)(16 + l) * 32 + i];
+                    }
+                }
+                {
+                    /* reflection of the tile's central direction about the plane, unit normal in float */
+                    const float nl = sqrtf(fmaf(c.gn[2], c.gn[2], fmaf(c.gn[1], c.gn[1], c.gn[0] * c.gn[0])));
+                    const float ux = c.gn[0] / nl, uy = c.gn[1] / nl, uz = c.gn[2] / nl;
+                    const float dnn = 2.0f * fmaf(Dz, uz, fmaf(Dy, uy, Dx * ux));
+                    const float Rx = fmaf(-dnn, ux, Dx), Ry = fmaf(-dnn, uy, Dy), Rz = fmaf(-dnn, uz, Dz);
+                    const float h = fmaf(hx, cc.nbx, hy * cc.nby) * 1.0001f + (32.0f * TRT_CERT_U) * (fabsf(Dx) + fabsf(Dy) + fabsf(Dz));
+                    for (int i = 0; i < n; i++) {
+                        patch_cand[(size_t)32 * 32 + i] = (unsigned char)trt_cert_patch_bounce_candidate(&ball, Rx, Ry, Rz, h, c.cull[4 * i], c.cull[4 * i + 1],
+                                                                                                          c.cull[4 * i + 2], c.cull[4 * i + 3], S_ball);
+                        stats[ST_PATCH_BOUNCE_CANDIDATES] += patch_cand[(size_t)32 * 32 + i];
+                    }
+                }
+            }
 
             for (int row = ty; row < ty + TILE_H && row < row1; row++)
                 for (int col = tx; col < tx + TILE_W && col < W; col++)
@@ -285,7 +336,10 @@ long long cert_check_rows(const trt_Scene *scene, int W, int H, int row0, int ro
                                     if (orc_hit_plane(&ray, &scene->ground, &p, NULL)) c.bad++;
                                 }
                             } else {
+                                /* the bounce ray of a first-generation ground hit of a patch tile uses the tile's candidates */
+                                c.cand = (patch_ok && bounces == 1) ? patch_cand + (size_t)32 * 32 : NULL;
                                 check_bounce(&c, &ray);
+                                c.cand = NULL;
                             }
                             trt_Point at;
                             v3 nrm;
@@ -293,12 +347,20 @@ long long cert_check_rows(const trt_Scene *scene, int W, int H, int row0, int ro
                             trt_ObjectType what = orc_closest_hit(scene, &ray, &at, &nrm, &m, NULL);
                             if (what != TRT_NONE) {
                                 v3 P = {at.x, at.y, at.z};
+                                const int use_patch = patch_ok && bounces == 0;
+                                if (use_patch) {
+                                    stats[ST_PATCH_RECORDS]++;
+                                    const double ddx = at.x - ball.cx, ddy = at.y - ball.cy, ddz = at.z - ball.cz;
+                                    if (what != TRT_GROUND || sqrt(ddx * ddx + ddy * ddy + ddz * ddz) > ball.r) c.bad++; /* every such hit is a ground hit inside the ball */
+                                }
                                 for (int i = 0; i < scene->num_directional_lights; i++) {
                                     v3 L = unit3(scale3(scene->directional_lights[i].direction, -1.0));
                                     trt_Ray sh = {at, L};
                                     const int want = exact_dir_open(scene, &sh);
                                     int certified;
+                                    c.cand = (use_patch && i < 16) ? patch_cand + (size_t)i * 32 : NULL;
                                     const int got = cert_dir(&c, P, L, &certified, tile_miss + n);
+                                    c.cand = NULL;
                                     stats[ST_DIR]++;
                                     stats[!certified ? ST_DIR_UNKNOWN : (got ? ST_DIR_OPEN : ST_DIR_BLOCKED)]++;
                                     if (got != want) c.bad++;
@@ -311,7 +373,9 @@ long long cert_check_rows(const trt_Scene *scene, int W, int H, int row0, int ro
                                     trt_Ray sh = {at, unit3(Lr)};
                                     const int want = exact_point_open(scene, &sh, P, light_d2);
                                     int certified;
+                                    c.cand = (use_patch && i < 16) ? patch_cand + (size_t)(16 + i) * 32 : NULL;
                                     const int got = cert_point(&c, P, pl, &certified, tile_miss + n);
+                                    c.cand = NULL;
                                     stats[ST_POINT]++;
                                     stats[!certified ? ST_POINT_UNKNOWN : (got ? ST_POINT_OPEN : ST_POINT_BLOCKED)]++;
                                     if (got != want) c.bad++;
@@ -332,6 +396,7 @@ long long cert_check_rows(const trt_Scene *scene, int W, int H, int row0, int ro
                     }
         }
     free(tile_miss);
+    free(patch_cand);
     free(c.cull);
     return c.bad;
 }

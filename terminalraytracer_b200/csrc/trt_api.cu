@@ -79,7 +79,7 @@ struct Context {
     Buffer sky;
     int sky_dim = -1, sky_face_stride = 0;
     // work
-    Buffer tile_counter, counters, byte_to_unit;
+    Buffer tile_counter, counters, byte_to_unit, scratch;
     Buffer pixels, quant, bytes;
     PinnedBuffer stage;
 } g;
@@ -183,6 +183,8 @@ void upload_scene(const trt_Scene *scene)
         const double tol = 1e-9 * scale * nl1;
         s.prim_num_sign = s.prim_num < -tol ? -1 : (s.prim_num > tol ? 1 : 0);
         s.ground_normal_l1 = float_round_up(nl1);
+        s.prim_num_f = (float)s.prim_num;
+        for (int k = 0; k < 3; k++) s.ground_unit_normal_f[k] = (float)s.ground_unit_normal[k];
         // camera in float for the tile certificates (trt_cert.h)
         trt_cert_camera &cf = s.cam_f;
         cf.ex = (float)s.eye[0]; cf.ey = (float)s.eye[1]; cf.ez = (float)s.eye[2];
@@ -196,6 +198,7 @@ void upload_scene(const trt_Scene *scene)
         cf.sw = (float)s.screen_width;
         cf.sh = (float)s.screen_height;
         cf.dist = (float)s.screen_distance;
+        cf.pw = cf.ph = 0.f;    // per launch: RenderParams::pixel_w_f / pixel_h_f
         s.eye_l1 = float_round_up((fabs(s.eye[0]) + fabs(s.eye[1]) + fabs(s.eye[2])) * (1.0 + 1e-6));
         if (!(fabs(s.eye[0]) + fabs(s.eye[1]) + fabs(s.eye[2]) < 1e12) || !(fabs(s.screen_width) + fabs(s.screen_height) + fabs(s.screen_distance) < 1e12))
             ground_in_range = false;
@@ -318,6 +321,8 @@ RenderParams make_params(int width, int height, int row0, int row1, double *d_pi
     p.height = height;
     p.row0 = row0;
     p.row1 = row1;
+    p.pixel_w_f = width > 0 ? (float)(g.scene.screen_width / width) : 0.f;
+    p.pixel_h_f = height > 0 ? (float)(g.scene.screen_height / height) : 0.f;
     p.pixels = d_pixels;
     p.quant = d_quant;
     p.sphere_geom = (const double4 *)g.sphere_geom.p;
@@ -327,6 +332,8 @@ RenderParams make_params(int width, int height, int row0, int row1, double *d_pi
     p.byte_to_unit = (const double *)g.byte_to_unit.p;
     p.sky = (const uchar4 *)g.sky.p;
     p.tile_counter = (unsigned int *)g.tile_counter.p;
+    g.scratch.reserve(render_scratch_bytes(g.num_sms));
+    p.sample_scratch = (double *)g.scratch.p;
     p.counters = count ? (unsigned long long *)g.counters.p : nullptr;
     p.row_cost = nullptr;
     return p;
@@ -385,6 +392,7 @@ void trt_shutdown(void)
     g.sphere_prim.release();
     g.sky.release();
     g.tile_counter.release();
+    g.scratch.release();
     g.byte_to_unit.release();
     g.counters.release();
     g.pixels.release();

@@ -64,10 +64,17 @@ TRT_HD void trt_cert_set_unit_dir(trt_cert_ray *r, double dx, double dy, double 
     r->usable = (S < 1e15f) && (dd > 0.99999f) && (dd < 1.00001f);
 }
 
+/* On the device the square roots and quotients of the certificates use the approximate units (a few ulp off,
+ * 2 instructions instead of ~25 with IEEE fix-up paths); every use pads its result by >= 16 ulp.  sqrt(0) becomes
+ * NaN there, which fails every comparison, i.e. "no certificate" — the safe answer. */
 #if defined(__CUDA_ARCH__)
 #define TRT_CERT_RSQRT(x) rsqrtf(x)
+#define TRT_CERT_SQRT(x) ((x) * rsqrtf(x))
+#define TRT_CERT_DIV(a, b) __fdividef((a), (b))
 #else
 #define TRT_CERT_RSQRT(x) (1.0f / sqrtf(x))
+#define TRT_CERT_SQRT(x) sqrtf(x)
+#define TRT_CERT_DIV(a, b) ((a) / (b))
 #endif
 
 /* direction from the ray's origin toward the point (lx,ly,lz), formed and normalised in float
@@ -108,6 +115,20 @@ TRT_HD float trt_cert_set_dir_toward(trt_cert_ray *r, float lx, float ly, float 
  * Pass far_limit = +inf, near_limit = +inf for rays without a length (bounce rays, directional lights).
  * The caller must ignore the answer when !r->usable.
  */
+TRT_HD void trt_cert_sphere2(const trt_cert_ray *r, float cx, float cy, float cz, float r_pad, float near_limit, float far_limit,
+                             int *miss, int *blocks)
+{
+    const float ocx = cx - r->ox, ocy = cy - r->oy, ocz = cz - r->oz;
+    const float tc = fmaf(ocz, r->dz, fmaf(ocy, r->dy, ocx * r->dx));
+    const float wx = fmaf(-tc, r->dx, ocx), wy = fmaf(-tc, r->dy, ocy), wz = fmaf(-tc, r->dz, ocz);
+    const float h2 = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+    const float outer = r_pad + r->slack_t;
+    const float inner = fmaf(r_pad, 0.99999237060546875f, -r->slack_t);
+    const float front = tc - r_pad;
+    *miss = (h2 > outer * outer) || (tc < -r->slack_t) || (front > far_limit);
+    *blocks = (inner > 0.0f) && (h2 < inner * inner) && (front > r->slack_t) && (tc < near_limit);
+}
+
 TRT_HD int trt_cert_sphere(const trt_cert_ray *r, float cx, float cy, float cz, float r_pad, float near_limit, float far_limit)
 {
     const float ocx = cx - r->ox, ocy = cy - r->oy, ocz = cz - r->oz;
@@ -169,9 +190,9 @@ TRT_HD int trt_cert_tile_sphere_miss(float ex, float ey, float ez, float Dx, flo
     const float X = fmaf(ocy, Dz, -(ocz * Dy));
     const float Y = fmaf(ocz, Dx, -(ocx * Dz));
     const float Z = fmaf(ocx, Dy, -(ocy * Dx));
-    const float nX = sqrtf(fmaf(Z, Z, fmaf(Y, Y, X * X))) * (1.0f - 8.0f * TRT_CERT_U);
-    const float nOC = sqrtf(fmaf(ocz, ocz, fmaf(ocy, ocy, ocx * ocx))) * (1.0f + 8.0f * TRT_CERT_U);
-    const float nD = sqrtf(fmaf(Dz, Dz, fmaf(Dy, Dy, Dx * Dx))) * (1.0f + 8.0f * TRT_CERT_U) + h;
+    const float nX = TRT_CERT_SQRT(fmaf(Z, Z, fmaf(Y, Y, X * X))) * (1.0f - 32.0f * TRT_CERT_U);
+    const float nOC = TRT_CERT_SQRT(fmaf(ocz, ocz, fmaf(ocy, ocy, ocx * ocx))) * (1.0f + 32.0f * TRT_CERT_U);
+    const float nD = TRT_CERT_SQRT(fmaf(Dz, Dz, fmaf(Dy, Dy, Dx * Dx))) * (1.0f + 32.0f * TRT_CERT_U) + h;
     const float lhs = nX - nOC * h;
     const float rhs = fmaf(r_pad, nD, (64.0f * TRT_CERT_U) * S * nD);
     return (S < 1e15f) && (nD < 1e15f) && (lhs > rhs);
@@ -215,6 +236,7 @@ typedef struct {
     float bx[3], by[3], bz[3];    /* camera basis                                                   */
     float nbx, nby;               /* |bx|_2, |by|_2 rounded up                                      */
     float sw, sh, dist;           /* screen width, height, distance                                 */
+    float pw, ph;                 /* sw / W, sh / H for the W x H screen being rendered (rounded to nearest) */
     float off_x, off_y;           /* largest sub-pixel offset in x and y, in pixels (TRT.c:992-993) */
 } trt_cert_camera;
 
@@ -226,7 +248,9 @@ typedef struct {
 TRT_HD void trt_cert_tile_cone(const trt_cert_camera *c, int col0, int row0, int tw, int th, int W, int H,
                                float *Dx, float *Dy, float *Dz, float *hx, float *hy)
 {
-    const float pw = c->sw / (float)W, ph = c->sh / (float)H;
+    const float pw = c->pw, ph = c->ph;
+    (void)W;
+    (void)H;
     const float half_w = 0.5f * ((float)(tw - 1) + c->off_x), half_h = 0.5f * ((float)(th - 1) + c->off_y);
     const float scx = fmaf((float)col0 + half_w, pw, -0.5f * c->sw);
     const float syc = fmaf(-((float)(row0 + th - 1) - half_h), ph, 0.5f * c->sh);
@@ -244,6 +268,100 @@ TRT_HD void trt_cert_tile_cone(const trt_cert_camera *c, int col0, int row0, int
 TRT_HD int trt_cert_ground_cannot_block(double num, double light_height, double margin)
 {
     return (num < 0.0 && light_height > margin) || (num > 0.0 && light_height < -margin);
+}
+
+/* ---- patch certificates: all first-generation ground hits of a pixel tile at once ----------------------------
+ * When no sphere can be hit by a tile's primary rays (tile sphere certificate) every surface hit of the tile is a
+ * GROUND hit, and all of them lie in the quadrilateral the tile's four corner directions cut out of the plane
+ * (the map direction -> plane point is projective, and keeps convexity while direction . n keeps its sign).
+ * trt_cert_patch_ball bounds that quadrilateral, and with it the origins `at` of the tile's shadow and bounce rays,
+ * by a ball; the three functions after it decide once per tile which spheres those rays can reach at all.  Spheres
+ * they rule out are certain misses for every such ray (or, for a point light, certain not to be hit closer than
+ * the light); the rest go through the per-ray certificates as usual. */
+
+typedef struct {
+    float cx, cy, cz;  /* centre                                                                      */
+    float r;           /* radius, padded for float error, for the EPSILON push-back and by a safety term */
+    int ok;            /* 0: the tile reaches the horizon / numbers out of range: no patch certificate  */
+} trt_cert_ball;
+
+/* (Dx,Dy,Dz), hx, hy: trt_cert_tile_cone; num: (plane point - eye) . n as a float (its sign must be robust, the
+ * caller checks that); (nx,ny,nz): plane normal; S: |eye|_1 + scene scale */
+TRT_HD void trt_cert_patch_ball(const trt_cert_camera *c, float Dx, float Dy, float Dz, float hx, float hy, float num,
+                                float nx, float ny, float nz, float S, trt_cert_ball *out)
+{
+    float px[4], py[4], pz[4], reach = 0.0f;
+    int ok = 1;
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (int k = 0; k < 4; k++) {
+        const float sxk = (k & 1) ? hx : -hx, syk = (k & 2) ? hy : -hy;
+        const float dx = fmaf(c->by[0], syk, fmaf(c->bx[0], sxk, Dx));
+        const float dy = fmaf(c->by[1], syk, fmaf(c->bx[1], sxk, Dy));
+        const float dz = fmaf(c->by[2], syk, fmaf(c->bx[2], sxk, Dz));
+        const float dn = fmaf(dz, nz, fmaf(dy, ny, dx * nx));
+        const float dscale = (fabsf(dx) + fabsf(dy) + fabsf(dz)) * (fabsf(nx) + fabsf(ny) + fabsf(nz));
+        /* the corner ray must meet the plane in front of the eye, at a well-conditioned angle */
+        ok = ok && (fabsf(dn) > 1e-3f * dscale) && ((dn < 0.0f) == (num < 0.0f));
+        const float t = TRT_CERT_DIV(num, dn);
+        px[k] = fmaf(t, dx, c->ex);
+        py[k] = fmaf(t, dy, c->ey);
+        pz[k] = fmaf(t, dz, c->ez);
+        const float ax = t * dx, ay = t * dy, az = t * dz;
+        reach = fmaxf(reach, fabsf(ax) + fabsf(ay) + fabsf(az));
+    }
+    out->cx = 0.25f * ((px[0] + px[1]) + (px[2] + px[3]));
+    out->cy = 0.25f * ((py[0] + py[1]) + (py[2] + py[3]));
+    out->cz = 0.25f * ((pz[0] + pz[1]) + (pz[2] + pz[3]));
+    float r2 = 0.0f;
+    for (int k = 0; k < 4; k++) {
+        const float ax = px[k] - out->cx, ay = py[k] - out->cy, az = pz[k] - out->cz;
+        r2 = fmaxf(r2, fmaf(az, az, fmaf(ay, ay, ax * ax)));
+    }
+    /* conditioning 1e-3 => the float quotient t is within ~2^-10 * 1e-2 of the real one; 4e-3 * reach covers it */
+    out->r = TRT_CERT_SQRT(r2) * 1.001f + 4e-3f * reach + 1e-4f * (1.0f + S) * 1e-2f + 1e-5f;
+    out->ok = ok && (S < 1e15f) && (reach < 1e15f) && (out->r < 1e15f);
+}
+
+/* directional light with unit direction (lx,ly,lz): can a ray from some point of the ball hit the sphere? */
+TRT_HD int trt_cert_patch_dir_candidate(const trt_cert_ball *b, float lx, float ly, float lz, float cx, float cy, float cz,
+                                        float r_pad, float S)
+{
+    const float ocx = cx - b->cx, ocy = cy - b->cy, ocz = cz - b->cz;
+    const float tc = fmaf(ocz, lz, fmaf(ocy, ly, ocx * lx));
+    const float wx = fmaf(-tc, lx, ocx), wy = fmaf(-tc, ly, ocy), wz = fmaf(-tc, lz, ocz);
+    const float h2 = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+    const float slack = (64.0f * TRT_CERT_U) * S;
+    const float reach = r_pad + b->r + slack;
+    /* every line passes the centre at more than r, or the centre is behind every origin (per-ray: tc < -slack) */
+    return !((h2 > reach * reach) || (tc + b->r < -slack));
+}
+
+/* point light at (lx,ly,lz): can the sphere come between some point of the ball and the light? */
+TRT_HD int trt_cert_patch_point_candidate(const trt_cert_ball *b, float lx, float ly, float lz, float cx, float cy, float cz,
+                                          float r_pad, float S)
+{
+    const float vx = lx - b->cx, vy = ly - b->cy, vz = lz - b->cz;
+    const float dd = fmaf(vz, vz, fmaf(vy, vy, vx * vx));
+    const float slack = (64.0f * TRT_CERT_U) * S + 2e-5f;
+    const float reach = r_pad + b->r + slack;
+    if (!(dd > 1e-20f)) return 1;
+    /* closest point of the segment [ball centre, light] (stretched by `reach` at both ends) to the sphere centre */
+    const float ocx = cx - b->cx, ocy = cy - b->cy, ocz = cz - b->cz;
+    const float s = TRT_CERT_DIV(fmaf(ocz, vz, fmaf(ocy, vy, ocx * vx)), dd);
+    const float sc = fminf(fmaxf(s, 0.0f), 1.0f);
+    const float wx = fmaf(-sc, vx, ocx), wy = fmaf(-sc, vy, ocy), wz = fmaf(-sc, vz, ocz);
+    const float h2 = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+    return !(h2 > reach * reach);
+}
+
+/* bounce rays off the ground: origins in the ball, directions R(D) for the tile's primary directions D = Dc + e,
+ * |e| <= h, R = reflection about the plane (linear, length-preserving): (Rx,Ry,Rz) = R(Dc). */
+TRT_HD int trt_cert_patch_bounce_candidate(const trt_cert_ball *b, float Rx, float Ry, float Rz, float h, float cx, float cy, float cz,
+                                           float r_pad, float S)
+{
+    return !trt_cert_tile_sphere_miss(b->cx, b->cy, b->cz, Rx, Ry, Rz, h, cx, cy, cz, r_pad + b->r, S);
 }
 
 #endif /* TRT_CERT_H */

@@ -9,6 +9,7 @@ namespace trt {
 void upload_scene_constants(const DevScene &scene, const float4 *cull, int count, cudaStream_t stream);
 void launch_render(const RenderParams &p, bool count, int cull, int num_sms, cudaStream_t stream);
 int render_ctas_per_sm();
+size_t render_scratch_bytes(int num_sms);   // RenderParams::sample_scratch must be at least this big
 unsigned long long run_selftest_division(unsigned long long seed, int ctas, int iters, unsigned long long *d_scratch, cudaStream_t stream);
 void launch_probe_trace(const RenderParams &p, const double *d_rays, int n, double *d_out, cudaStream_t stream);
 void launch_probe_sky(const RenderParams &p, const double *d_dirs, int n, int *d_out, cudaStream_t stream);

@@ -44,13 +44,13 @@ constexpr int TILE_H = 4;
 #define TRT_WARPS_PER_CTA 4
 #endif
 #ifndef TRT_MIN_CTAS_PER_SM
-#define TRT_MIN_CTAS_PER_SM 3
+#define TRT_MIN_CTAS_PER_SM 4
 #endif
 constexpr int WARPS_PER_CTA = TRT_WARPS_PER_CTA;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 constexpr int QCAP = 64;                                  // ring capacity: at most 31 queued + 32 pushed by one step
 constexpr int TILE_SAMPLES = 32 * TRT_RAYS_PER_PIXEL;
-constexpr int TMASK_WORDS = TRT_MAX_CONST_SPHERES / 32;   // tile certificate masks (scenes up to TRT_MAX_CONST_SPHERES)
+constexpr int TMASK_WORDS = 128;                          // tile certificate masks: scenes of up to 4096 spheres
 
 // what a closest-hit query is for
 enum QueryMode : int {
@@ -59,18 +59,28 @@ enum QueryMode : int {
     Q_POINT = 2    // point-light shadow ray: only a hit closer than the light blocks (TRT.c:936-941)
 };
 
-// warp-private shared memory: the hit-record ring (structure of arrays: conflict-free for lane = slot),
-// the finished samples of the current tile and the tile certificate mask
+// warp-private shared memory: two hit-record rings (structure of arrays: conflict-free for lane = slot) and the
+// tile / patch certificate masks.  Ring A holds FIRST-generation hits (primary rays: origin = eye, nothing
+// accumulated yet, so a record is just direction + hit parameter), ring B the hits of bounce rays.  They are
+// consumed separately because a tile's first-generation hits share tile-level (patch) certificates.
+constexpr int PATCH_MAX_SPHERES = 32;                     // patch certificates: one mask word per query
+constexpr int PATCH_QUERIES = 2 * TRT_MAX_LIGHTS + 1;     // every directional light, every point light, the bounce
 struct WarpShared {
+    // ring A
+    double a_dx[QCAP], a_dy[QCAP], a_dz[QCAP];   // unit direction of the primary ray
+    double a_t[QCAP];                            // hit parameter: hit point = eye + t d (TRT.c:663-665 / 690-692)
+    unsigned int a_meta[QCAP];                   // pixel lane | sample k << 5 | object kind << 13
+    int a_index[QCAP];                           // sphere index of the hit
+    // ring B
     double ox[QCAP], oy[QCAP], oz[QCAP];   // origin of the ray that hit
     double dx[QCAP], dy[QCAP], dz[QCAP];   // its unit direction
-    double t[QCAP];                        // hit parameter: hit point = o + t d (TRT.c:663-665 / 690-692)
+    double t[QCAP];                        // hit parameter
     double sr[QCAP], sg[QCAP], sb[QCAP];   // colour accumulated by the sample so far (TRT.c:1051)
     double w[QCAP], ws[QCAP];              // weight, weight_sum (TRT.c:1017, 1034)
     unsigned int meta[QCAP];               // pixel lane | sample k << 5 | bounces << 9 | object kind << 13
-    int index[QCAP];                       // sphere index of the hit
-    double res[3][TILE_SAMPLES];           // finished samples, [channel][k * 32 + pixel lane]
-    unsigned int tmask[TMASK_WORDS];       // spheres the tile certificate could not rule out
+    int index[QCAP];
+    unsigned int tmask[TMASK_WORDS];       // spheres the tile certificate could not rule out for primary rays
+    unsigned int pmask[PATCH_QUERIES + 1]; // patch certificates: spheres each query of a first-generation hit can reach
 };
 constexpr size_t SMEM_TABLE_BYTES = 256 * sizeof(double);
 constexpr size_t SMEM_BYTES = SMEM_TABLE_BYTES + WARPS_PER_CTA * sizeof(WarpShared);
@@ -136,12 +146,19 @@ __device__ __forceinline__ int sky_texel_index(const d3 &dir, int dim, int &face
 }
 
 // colour of the sky in direction d (a unit vector; the reference normalises it once more, TRT.c:702)
-__device__ __forceinline__ d3 sky_colour(const RenderParams &P, const double *s_byte_to_unit, const d3 &d)
+#ifndef TRT_SKY_INLINE
+#define TRT_SKY_INLINE __noinline__
+#endif
+static __device__ TRT_SKY_INLINE d3 sky_colour_of(const uchar4 *sky, const double *s_byte_to_unit, d3 d)
 {
     int face;
     const int texel = sky_texel_index(unit(d), c_scene.sky_dim, face);
-    const uchar4 t = __ldg(&P.sky[(size_t)face * (size_t)c_scene.sky_face_stride + (size_t)texel]);
+    const uchar4 t = __ldg(&sky[(size_t)face * (size_t)c_scene.sky_face_stride + (size_t)texel]);
     return mk3(s_byte_to_unit[t.x], s_byte_to_unit[t.y], s_byte_to_unit[t.z]);   // TRT.c:866
+}
+__device__ __forceinline__ d3 sky_colour(const RenderParams &P, const double *s_byte_to_unit, const d3 &d)
+{
+    return sky_colour_of(P.sky, s_byte_to_unit, d);
 }
 
 // ---- exact tests: the reference's operations in the reference's order -------------------------------------
@@ -244,13 +261,24 @@ __device__ __noinline__ void query_reference(const RenderParams &P, const d3 &o,
 //     closest hit among the objects that can still matter — every other object is proven either not hit or,
 //     for a point light, hit only beyond the light (farther than any hit that could block) — so the caller's
 //     decision on it equals the reference's decision on the closest hit over all objects.
-// num_g = plane_numerator(o) (shadow queries; ignored by Q_CLOSEST).  CONST_RECORDS: records in __constant__.
-template <int MODE, bool CONST_RECORDS>
-__device__ __forceinline__ bool query_certified(const RenderParams &P, const trt_cert_ray &rf, const d3 &o, const d3 &d, float near_limit,
-                                                float far_limit, double num_g, double dir_plane_denom, bool ground_candidate, int &obj,
-                                                int &index, double &t_hit, unsigned int *exact_tests)
+// `mode` is warp-uniform at run time: the consume step runs all of a record's queries through ONE copy of this
+// code (three inlined copies cost more in instruction-cache misses than the uniform branches cost in issue slots).
+struct Query {
+    d3 d;                  // unit direction, exact
+    trt_cert_ray rf;       // the same ray in float, with its error slack
+    float near_limit;      // Q_POINT: a hit closer than this certainly blocks; +inf otherwise
+    float far_limit;       // Q_POINT: a sphere entirely beyond this cannot block; +inf otherwise
+    double plane_denom;    // Q_DIR: dot(direction, ground normal), a per-light constant
+    bool ground_candidate; // Q_POINT: the ground was not ruled out by trt_cert_ground_cannot_block
+    int mode;
+};
+
+template <bool CONST_RECORDS>
+__device__ __forceinline__ bool query_certified(const RenderParams &P, const Query &qy, const d3 &o, double num_g, bool use_patch,
+                                                unsigned int patch_mask, int &obj, int &index, double &t_hit, unsigned int *exact_tests)
 {
     const Tally<false> no_tally{nullptr};
+    const d3 d = qy.d;
     double closest = INFINITY;
     obj = 0;
     index = -1;
@@ -258,34 +286,27 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const trt
     const double a = dot(d, d);
     const double two_a = 2.0 * a, four_a = 4.0 * a;
     const int n = c_scene.num_spheres;
-    const bool usable = rf.usable != 0;
+    const bool usable = qy.rf.usable != 0;
+    const bool shadow = qy.mode != Q_CLOSEST;
     bool blocked = false;
     for (int base = 0; base < n; base += 32) {
         const int cnt = min(32, n - base);
-        // pass 1 (float, branch-free, warp-uniform record addresses): classify the spheres of this chunk.
-        // The records are padded to an even count (pad records are masked off below): two tests per trip.
+        // pass 1 (float, warp-uniform record addresses): classify the candidate spheres of this chunk — all of them,
+        // or, for the first-generation hits of a patch tile, the few the patch certificate left (use_patch, n <= 32)
+        const unsigned int valid = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+        const unsigned int candidates = use_patch ? (patch_mask & valid) : valid;
         unsigned int survivors = 0;
 #pragma unroll 1
-        for (int j = 0; j < cnt; j += 2) {
-            const float4 g0 = CONST_RECORDS ? c_sphere_cull[base + j] : __ldg(&P.sphere_cull[base + j]);
-            const float4 g1 = CONST_RECORDS ? c_sphere_cull[base + j + 1] : __ldg(&P.sphere_cull[base + j + 1]);
-            unsigned int s0, s1;
-            if (MODE == Q_CLOSEST) {
-                s0 = trt_cert_sphere_miss(&rf, g0.x, g0.y, g0.z, g0.w) ? 0u : 1u;
-                s1 = trt_cert_sphere_miss(&rf, g1.x, g1.y, g1.z, g1.w) ? 0u : 2u;
-            } else {
-                const int k0 = trt_cert_sphere(&rf, g0.x, g0.y, g0.z, g0.w, near_limit, far_limit);
-                const int k1 = trt_cert_sphere(&rf, g1.x, g1.y, g1.z, g1.w, near_limit, far_limit);
-                s0 = (k0 & TRT_CERT_MISS) ? 0u : 1u;
-                s1 = (k1 & TRT_CERT_MISS) ? 0u : 2u;
-                // a pad record (j + 1 == cnt, radius 0) cannot block: inner = -slack < 0
-                blocked = blocked || ((k0 | k1) & TRT_CERT_BLOCKS);
-            }
-            survivors |= (s0 | s1) << j;
+        for (unsigned int m = candidates; m; m &= m - 1) {
+            const int j = __ffs(m) - 1;
+            const float4 g = CONST_RECORDS ? c_sphere_cull[base + j] : __ldg(&P.sphere_cull[base + j]);
+            int miss, blocks;
+            trt_cert_sphere2(&qy.rf, g.x, g.y, g.z, g.w, qy.near_limit, qy.far_limit, &miss, &blocks);
+            if (!miss) survivors |= 1u << j;
+            blocked = blocked || blocks;
         }
-        const unsigned int valid = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
-        survivors = usable ? (survivors & valid) : valid;
-        if (MODE != Q_CLOSEST && usable && blocked) survivors = 0;
+        if (!usable) survivors = candidates;
+        if (shadow && usable && blocked) survivors = 0;
         if (exact_tests) *exact_tests += (unsigned int)__popc(survivors);
         // pass 2 (double, exact): each lane walks its own survivors in index order
         while (survivors) {
@@ -294,25 +315,22 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const trt
             sphere_exact<false>(ldg4(P.sphere_geom, base + j), base + j, o, d, two_a, four_a, closest, obj, index, t_hit, no_tally);
         }
     }
-    blocked = blocked && usable;
-    if (MODE == Q_CLOSEST) {
-        if (!trt_cert_plane_miss(&rf, c_scene.ground_point_f[0], c_scene.ground_point_f[1], c_scene.ground_point_f[2],
-                                 c_scene.ground_normal_f[0], c_scene.ground_normal_f[1], c_scene.ground_normal_f[2]))
-            plane_exact_num<false>(plane_numerator(o), o, d, closest, obj, t_hit, no_tally);
-        return false;
-    }
-    if (MODE == Q_DIR) {
+    blocked = blocked && usable && shadow;
+    if (qy.mode == Q_CLOSEST) {
+        if (!(usable && trt_cert_plane_miss(&qy.rf, c_scene.ground_point_f[0], c_scene.ground_point_f[1], c_scene.ground_point_f[2],
+                                            c_scene.ground_normal_f[0], c_scene.ground_normal_f[1], c_scene.ground_normal_f[2])))
+            plane_exact_num<false>(num_g, o, d, closest, obj, t_hit, no_tally);
+    } else if (qy.mode == Q_DIR) {
         // any hit blocks.  The ground (TRT.c:677-695): numerator and denominator are the reference's own doubles
         // (the denominator is a per-light constant); opposite signs or a zero numerator give t <= 0, a miss,
         // without the division.
-        if (!blocked && obj == 0 && fabs(dir_plane_denom) > 0.00001 && num_g != 0.0 && ((num_g < 0.0) == (dir_plane_denom < 0.0))) {
-            const double t = ieee_div(num_g, dir_plane_denom);
+        if (!blocked && obj == 0 && fabs(qy.plane_denom) > 0.00001 && num_g != 0.0 && ((num_g < 0.0) == (qy.plane_denom < 0.0))) {
+            const double t = ieee_div(num_g, qy.plane_denom);
             if (t > 0.00001) obj = 2;
         }
-        return blocked;
+    } else {
+        if (!blocked && qy.ground_candidate) plane_exact_num<false>(num_g, o, d, closest, obj, t_hit, no_tally);
     }
-    // Q_POINT
-    if (!blocked && ground_candidate) plane_exact_num<false>(num_g, o, d, closest, obj, t_hit, no_tally);
     return blocked;
 }
 
@@ -324,136 +342,24 @@ __device__ __forceinline__ d3 push_back(const d3 &o, const d3 &hit)
     return hit + back;
 }
 
-// The three kinds of queries the light loop and the bounce need, in every build flavour:
-//   CULL == 0 or COUNT: all-FP64 reference-order query (COUNT tallies the reference's work counters);
-//   otherwise the certificate-guided query.  COUNT with CULL != 0 runs BOTH and reports any disagreement of the
-//   final answers in CTR_CULL_VIOLATIONS (the on-device audit of the certificates and of the survivor logic).
-struct ShadowOrigin {
-    trt_cert_ray rf;     // origin filled in, direction per query
-    float S0;            // |origin|_1 + max centre |.|_1
-    double num_g;        // plane_numerator(origin)
-};
-
-template <bool COUNT, int CULL>
-__device__ __forceinline__ void closest_hit_bounce(const RenderParams &P, const ShadowOrigin &so, const d3 &o, const d3 &d, int &obj, int &index,
-                                                   double &t_hit, const Tally<COUNT> &tally)
+// Q_CLOSEST query set-up for a ray with a double unit direction; S0 = |o|_1 + max centre |.|_1 (inf: unusable)
+__device__ __forceinline__ void setup_closest_query(Query &qy, const d3 &o, const d3 &d, float S0)
 {
-    if (COUNT || CULL == 0) query_reference<COUNT>(P, o, d, obj, index, t_hit, tally);
-    if (CULL != 0) {
-        trt_cert_ray rf = so.rf;
-        trt_cert_set_unit_dir(&rf, d.x, d.y, d.z, so.S0);
-        int obj2, index2;
-        double t2;
-        unsigned int exact = 0;
-        query_certified<Q_CLOSEST, CULL == 1>(P, rf, o, d, 0.f, 0.f, 0.0, 0.0, false, obj2, index2, t2, COUNT ? &exact : nullptr);
-        if (COUNT) {
-            tally.add(CTR_EXACT_SPHERE_TESTS, exact);
-            if (obj2 != obj || (obj && (__double_as_longlong(t2) != __double_as_longlong(t_hit) || (obj == 1 && index2 != index))))
-                tally.add(CTR_CULL_VIOLATIONS);
-        } else {
-            obj = obj2;
-            index = index2;
-            t_hit = t2;
-        }
-    }
-}
-
-// is directional light `l` visible from o?  (TRT.c:903-908)
-template <bool COUNT, int CULL>
-__device__ __forceinline__ bool dir_light_open(const RenderParams &P, const ShadowOrigin &so, const d3 &o, int l, const Tally<COUNT> &tally)
-{
-    const DevLightDir &Ld = c_scene.dir[l];
-    const d3 L = mk3(Ld.L[0], Ld.L[1], Ld.L[2]);
-    bool open = false;
-    if (COUNT || CULL == 0) {
-        int obj, index;
-        double t_hit;
-        tally.add(CTR_TRACE_CALLS);
-        query_reference<COUNT>(P, o, L, obj, index, t_hit, tally);
-        if (obj) tally.add(CTR_TRACE_HITS);
-        else { tally.add(CTR_SKY_LOOKUPS); tally.add(CTR_SKY_SKIPPED); }
-        open = obj == 0;
-    }
-    if (CULL != 0) {
-        trt_cert_ray rf = so.rf;
-        rf.dx = Ld.Lf[0]; rf.dy = Ld.Lf[1]; rf.dz = Ld.Lf[2];
-        const float dd = fmaf(rf.dz, rf.dz, fmaf(rf.dy, rf.dy, rf.dx * rf.dx));
-        rf.slack_t = (32.0f * TRT_CERT_U) * so.S0;
-        rf.usable = (so.S0 < 1e15f) && (dd > 0.99999f) && (dd < 1.00001f);
-        int obj2, index2;
-        double t2;
-        unsigned int exact = 0;
-        const bool blocked = query_certified<Q_DIR, CULL == 1>(P, rf, o, L, INFINITY, INFINITY, so.num_g, Ld.plane_denom, false, obj2, index2, t2,
-                                                              COUNT ? &exact : nullptr);
-        const bool open2 = !blocked && obj2 == 0;
-        if (COUNT) {
-            tally.add(CTR_EXACT_SPHERE_TESTS, exact);
-            if (open2 != open) tally.add(CTR_CULL_VIOLATIONS);
-        } else {
-            open = open2;
-        }
-    }
-    return open;
-}
-
-// is point light `l` visible from o?  d = unit(light - o), light_d2 = |light - o|^2 (TRT.c:929-941)
-template <bool COUNT, int CULL>
-__device__ __forceinline__ bool point_light_open(const RenderParams &P, const ShadowOrigin &so, const d3 &o, const d3 &d, double light_d2, int l,
-                                                 const Tally<COUNT> &tally)
-{
-    const DevLightPoint &Lp = c_scene.point[l];
-    bool open = false;
-    if (COUNT || CULL == 0) {
-        int obj, index;
-        double t_hit;
-        tally.add(CTR_TRACE_CALLS);
-        query_reference<COUNT>(P, o, d, obj, index, t_hit, tally);
-        if (obj) tally.add(CTR_TRACE_HITS);
-        else { tally.add(CTR_SKY_LOOKUPS); tally.add(CTR_SKY_SKIPPED); }
-        open = obj == 0;
-        if (!open) {
-            const d3 hit = mk3(o.x + t_hit * d.x, o.y + t_hit * d.y, o.z + t_hit * d.z);
-            const d3 to_blocker = push_back(o, hit) - o;
-            open = light_d2 < dot(to_blocker, to_blocker);
-        }
-    }
-    if (CULL != 0) {
-        trt_cert_ray rf = so.rf;
-        const float S = so.S0 + Lp.pos_l1;
-        const float dist = trt_cert_set_dir_toward(&rf, Lp.pos_f[0], Lp.pos_f[1], Lp.pos_f[2], S);
-        const float guard = fmaf(2.0f, rf.slack_t, 1e-5f);
-        const bool ground_candidate = !trt_cert_ground_cannot_block(so.num_g, Lp.height, c_scene.ground_margin);
-        int obj2, index2;
-        double t2;
-        unsigned int exact = 0;
-        const bool blocked = query_certified<Q_POINT, CULL == 1>(P, rf, o, d, dist - guard, dist + guard, so.num_g, 0.0, ground_candidate, obj2, index2,
-                                                                t2, COUNT ? &exact : nullptr);
-        bool open2 = !blocked && obj2 == 0;
-        if (!blocked && obj2 != 0) {
-            const d3 hit = mk3(o.x + t2 * d.x, o.y + t2 * d.y, o.z + t2 * d.z);
-            const d3 to_blocker = push_back(o, hit) - o;
-            open2 = light_d2 < dot(to_blocker, to_blocker);
-        }
-        if (COUNT) {
-            tally.add(CTR_EXACT_SPHERE_TESTS, exact);
-            if (open2 != open) tally.add(CTR_CULL_VIOLATIONS);
-        } else {
-            open = open2;
-        }
-    }
-    return open;
-}
-
-__device__ __forceinline__ void set_shadow_origin(ShadowOrigin &so, const d3 &o, bool need_plane)
-{
-    so.S0 = trt_cert_set_origin(&so.rf, o.x, o.y, o.z) + c_scene.filter_centre_l1;
-    so.rf.dx = so.rf.dy = so.rf.dz = 0.f;
-    so.rf.slack_t = 0.f;
-    so.rf.usable = 0;
-    so.num_g = need_plane ? plane_numerator(o) : 0.0;
+    qy.d = d;
+    trt_cert_set_origin(&qy.rf, o.x, o.y, o.z);
+    trt_cert_set_unit_dir(&qy.rf, d.x, d.y, d.z, S0);
+    qy.near_limit = INFINITY;
+    qy.far_limit = INFINITY;
+    qy.plane_denom = 0.0;
+    qy.ground_candidate = false;
+    qy.mode = Q_CLOSEST;
 }
 
 // ---- K1 ------------------------------------------------------------------------------------------------
+// Build flavours:  CULL == 0 or COUNT: every query is the all-FP64 reference-order query (COUNT tallies the
+// reference's work counters); otherwise the certificate-guided one.  COUNT with CULL != 0 runs BOTH and reports any
+// disagreement of the final answers in CTR_CULL_VIOLATIONS (the on-device audit of the certificates, of the
+// survivor logic and of the host-precomputed primary-ray terms).
 template <bool COUNT, int CULL>
 __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(const RenderParams P)
 {
@@ -466,6 +372,9 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     WarpShared &W = reinterpret_cast<WarpShared *>(smem_raw + SMEM_TABLE_BYTES)[warp];
+    // finished samples of the current tile, [channel][k * 32 + pixel lane]: written once, read once at the end of
+    // the tile by the pixel's lane -> parked in an L2-resident per-warp slice of global memory, not in shared memory
+    double *const res = P.sample_scratch + (size_t)(blockIdx.x * WARPS_PER_CTA + warp) * (size_t)(3 * TILE_SAMPLES);
     const int band_rows = P.row1 - P.row0;
     const int tiles_x = (P.width + TILE_W - 1) / TILE_W;
     const int tiles_y = (band_rows + TILE_H - 1) / TILE_H;
@@ -480,9 +389,10 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
     // (double)col / (double)width and (double)row / (double)height (TRT.c:987-988) through shared reciprocals:
     // numerators are integers >= 1 (0 is special-cased), far inside the fast path of the IEEE division
     const Reciprocal inv_w = reciprocal_of((double)P.width), inv_h = reciprocal_of((double)P.height);
-    // tile certificates need the masks to fit; bigger scenes send primary rays through the per-ray certificates
+    // tile certificates need the masks to fit; bigger scenes test every sphere exactly for primary rays
     const bool tile_certs = CULL != 0 && num_spheres <= 32 * TMASK_WORDS;
     const int mask_words = (num_spheres + 31) >> 5;
+    const float S_max = c_scene.filter_enabled ? c_scene.filter_centre_l1 : INFINITY;   // inf: every certificate ray unusable
 
     for (;;) {
         unsigned int tile = 0;
@@ -504,12 +414,16 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
 
         // ---- tile certificates (float): which spheres can any primary ray of this tile hit at all? the ground?
         bool tile_ground_miss = false;
+        bool patch = false;       // patch certificates available for this tile's first-generation hits
         if (tile_certs) {
-            const trt_cert_camera &cam = c_scene.cam_f;
+            trt_cert_camera cam = c_scene.cam_f;
+            cam.pw = P.pixel_w_f;
+            cam.ph = P.pixel_h_f;
             float Dx, Dy, Dz, hx, hy;
             trt_cert_tile_cone(&cam, tx * TILE_W, P.row0 + ty * TILE_H, TILE_W, TILE_H, P.width, P.height, &Dx, &Dy, &Dz, &hx, &hy);
             const float h = fmaf(hx, cam.nbx, hy * cam.nby);
             const float S = c_scene.eye_l1 + c_scene.filter_centre_l1;
+            unsigned int any_sphere = 0;
             for (int wd = 0; wd < mask_words; wd++) {
                 const int i = wd * 32 + lane;
                 bool keep = false;
@@ -518,6 +432,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                     keep = !(c_scene.filter_enabled && trt_cert_tile_sphere_miss(cam.ex, cam.ey, cam.ez, Dx, Dy, Dz, h, g.x, g.y, g.z, g.w, S));
                 }
                 const unsigned int m = __ballot_sync(0xffffffffu, keep);
+                any_sphere |= m;
                 if (lane == 0) W.tmask[wd] = m;
             }
             const float *gn = c_scene.ground_normal_f;
@@ -528,14 +443,55 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
             const int sgn = c_scene.filter_enabled ? trt_cert_tile_plane_sign(dn, bxn, byn, hx, hy, scale) : 0;
             // numerator < 0 with every denominator > 0 (or the mirror image): t < 0 for every primary ray of the tile
             tile_ground_miss = (c_scene.prim_num_sign < 0 && sgn > 0) || (c_scene.prim_num_sign > 0 && sgn < 0);
+
+            // ---- patch certificates: no sphere in reach of the primary rays => every hit of this tile's primary rays
+            // is a ground hit inside a ball (trt_cert_patch_ball); decide once which spheres its shadow and bounce
+            // rays can reach (lane = sphere), instead of classifying every sphere for every ray
+            if (any_sphere == 0 && !tile_ground_miss && num_spheres <= PATCH_MAX_SPHERES && c_scene.prim_num_sign != 0 && c_scene.filter_enabled) {
+                trt_cert_ball ball;
+                trt_cert_patch_ball(&cam, Dx, Dy, Dz, hx, hy, c_scene.prim_num_f, gn[0], gn[1], gn[2], S, &ball);
+                patch = ball.ok != 0;
+                if (patch) {
+                    const float S_ball = fabsf(ball.cx) + fabsf(ball.cy) + fabsf(ball.cz) + ball.r + c_scene.filter_centre_l1;
+                    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (lane < num_spheres) g = __ldg(&P.sphere_cull[lane]);
+                    for (int l = 0; l < num_dir; l++) {
+                        const float *Lf = c_scene.dir[l].Lf;
+                        const bool cand = lane < num_spheres && trt_cert_patch_dir_candidate(&ball, Lf[0], Lf[1], Lf[2], g.x, g.y, g.z, g.w, S_ball);
+                        const unsigned int m = __ballot_sync(0xffffffffu, cand);
+                        if (lane == 0) W.pmask[l] = m;
+                    }
+                    for (int l = 0; l < num_point; l++) {
+                        const DevLightPoint &Lp = c_scene.point[l];
+                        const bool cand = lane < num_spheres &&
+                                          trt_cert_patch_point_candidate(&ball, Lp.pos_f[0], Lp.pos_f[1], Lp.pos_f[2], g.x, g.y, g.z, g.w, S_ball + Lp.pos_l1);
+                        const unsigned int m = __ballot_sync(0xffffffffu, cand);
+                        if (lane == 0) W.pmask[num_dir + l] = m;
+                    }
+                    {
+                        // reflection of the tile's central direction about the plane (unit normal in float)
+                        const float *un = c_scene.ground_unit_normal_f;
+                        const float dnn = 2.0f * fmaf(Dz, un[2], fmaf(Dy, un[1], Dx * un[0]));
+                        const float Rx = fmaf(-dnn, un[0], Dx), Ry = fmaf(-dnn, un[1], Dy), Rz = fmaf(-dnn, un[2], Dz);
+                        const float hb = h * 1.0001f + (32.0f * TRT_CERT_U) * (fabsf(Dx) + fabsf(Dy) + fabsf(Dz));
+                        const bool cand = lane < num_spheres && trt_cert_patch_bounce_candidate(&ball, Rx, Ry, Rz, hb, g.x, g.y, g.z, g.w, S_ball);
+                        const unsigned int m = __ballot_sync(0xffffffffu, cand);
+                        if (lane == 0) W.pmask[num_dir + num_point] = m;
+                    }
+                }
+            }
         }
         __syncwarp();
 
         int round = 0;            // next sample index to produce
-        int qhead = 0, qcount = 0;
+        int a_head = 0, a_count = 0, qhead = 0, qcount = 0;   // ring A (first-generation hits), ring B (bounce hits)
 
-        while (round < TRT_RAYS_PER_PIXEL || qcount > 0) {
-            if (qcount < 32 && round < TRT_RAYS_PER_PIXEL) {
+        // Full warps first: a ring is consumed as soon as it holds 32 records (so neither can exceed 63), primary
+        // rays are produced while both are short, and the remainders are drained at the end of the tile.
+        while (round < TRT_RAYS_PER_PIXEL || a_count > 0 || qcount > 0) {
+            const bool consume_b = qcount >= 32 || (a_count == 0 && round == TRT_RAYS_PER_PIXEL);
+            const bool consume_a = !consume_b && (a_count >= 32 || round == TRT_RAYS_PER_PIXEL);
+            if (!consume_a && !consume_b) {
                 // =========================== PRODUCE: primary rays of sample `round` ==============================
                 const int k = round++;
                 bool hit_surface = false;
@@ -554,36 +510,28 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                     sp = sp + mk3(c_scene.by[0] * sy, c_scene.by[1] * sy, c_scene.by[2] * sy);
                     sp = sp + mk3(c_scene.bz[0] * sz, c_scene.bz[1] * sz, c_scene.bz[2] * sz);
                     d = unit(sp - eye);         // TRT.c:1005 (origin subtracted from an untranslated vector), 1008
-                    if (COUNT || CULL == 0) query_reference<COUNT>(P, eye, d, obj, index, t_hit, tally);
-                    if (CULL != 0) {
+                    if (COUNT || !tile_certs) query_reference<COUNT>(P, eye, d, obj, index, t_hit, tally);
+                    if (tile_certs) {
+                        // exact tests of the tile's candidate spheres; oc and c of TRT.c:640-648 are per-frame
+                        // constants for rays leaving the eye (host-evaluated with the reference's operations)
                         int obj2 = 0, index2 = -1;
                         double t2 = 0.0;
                         unsigned int exact = 0;
-                        if (tile_certs) {
-                            // exact tests of the tile's candidate spheres; oc and c of TRT.c:640-648 are per-frame
-                            // constants for rays leaving the eye (host-evaluated with the reference's operations)
-                            const Tally<false> no_tally{nullptr};
-                            double closest = INFINITY;
-                            const double a = dot(d, d);
-                            const double two_a = 2.0 * a, four_a = 4.0 * a;
-                            for (int wd = 0; wd < mask_words; wd++) {
-                                unsigned int m = W.tmask[wd];
-                                exact += (unsigned int)__popc(m);
-                                while (m) {
-                                    const int i = wd * 32 + __ffs(m) - 1;
-                                    m &= m - 1;
-                                    const double4 g = ldg4(P.sphere_prim, i);
-                                    sphere_exact_oc<false>(mk3(g.x, g.y, g.z), g.w, i, eye, d, two_a, four_a, closest, obj2, index2, t2, no_tally);
-                                }
+                        const Tally<false> no_tally{nullptr};
+                        double closest = INFINITY;
+                        const double a = dot(d, d);
+                        const double two_a = 2.0 * a, four_a = 4.0 * a;
+                        for (int wd = 0; wd < mask_words; wd++) {
+                            unsigned int m = W.tmask[wd];
+                            exact += (unsigned int)__popc(m);
+                            while (m) {
+                                const int i = wd * 32 + __ffs(m) - 1;
+                                m &= m - 1;
+                                const double4 g = ldg4(P.sphere_prim, i);
+                                sphere_exact_oc<false>(mk3(g.x, g.y, g.z), g.w, i, eye, d, two_a, four_a, closest, obj2, index2, t2, no_tally);
                             }
-                            if (!tile_ground_miss) plane_exact_num<false>(c_scene.prim_num, eye, d, closest, obj2, t2, no_tally);
-                        } else {
-                            trt_cert_ray rf;
-                            const float S = trt_cert_set_origin(&rf, eye.x, eye.y, eye.z) + c_scene.filter_centre_l1;
-                            trt_cert_set_unit_dir(&rf, d.x, d.y, d.z, S);
-                            rf.usable = rf.usable && c_scene.filter_enabled;
-                            query_certified<Q_CLOSEST, false>(P, rf, eye, d, 0.f, 0.f, 0.0, 0.0, false, obj2, index2, t2, COUNT ? &exact : nullptr);
                         }
+                        if (!tile_ground_miss) plane_exact_num<false>(c_scene.prim_num, eye, d, closest, obj2, t2, no_tally);
                         if (COUNT) {
                             tally.add(CTR_EXACT_SPHERE_TESTS, exact);
                             if (obj2 != obj || (obj && (__double_as_longlong(t2) != __double_as_longlong(t_hit) || (obj == 1 && index2 != index))))
@@ -600,9 +548,9 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                         tally.add(CTR_SKY_LOOKUPS);
                         if (COUNT) atomicAdd(&P.counters[CTR_BOUNCE_HIST0], 1ull);
                         const d3 c = sky_colour(P, s_byte_to_unit, d);
-                        W.res[0][k * 32 + lane] = c.x;
-                        W.res[1][k * 32 + lane] = c.y;
-                        W.res[2][k * 32 + lane] = c.z;
+                        __stcg(&res[0 * TILE_SAMPLES + k * 32 + lane], c.x);
+                        __stcg(&res[1 * TILE_SAMPLES + k * 32 + lane], c.y);
+                        __stcg(&res[2 * TILE_SAMPLES + k * 32 + lane], c.z);
                     } else {
                         tally.add(CTR_TRACE_HITS);
                         hit_surface = true;
@@ -610,39 +558,50 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                 }
                 const unsigned int pushers = __ballot_sync(0xffffffffu, hit_surface);
                 if (hit_surface) {
-                    const int slot = (qhead + qcount + __popc(pushers & ((1u << lane) - 1u))) & (QCAP - 1);
-                    W.ox[slot] = eye.x; W.oy[slot] = eye.y; W.oz[slot] = eye.z;
-                    W.dx[slot] = d.x; W.dy[slot] = d.y; W.dz[slot] = d.z;
-                    W.t[slot] = t_hit;
-                    W.sr[slot] = 0.0; W.sg[slot] = 0.0; W.sb[slot] = 0.0;
-                    W.w[slot] = 1.0; W.ws[slot] = 0.0;
-                    W.meta[slot] = (unsigned)lane | ((unsigned)k << 5) | ((unsigned)obj << 13);
-                    W.index[slot] = index;
+                    const int slot = (a_head + a_count + __popc(pushers & ((1u << lane) - 1u))) & (QCAP - 1);
+                    W.a_dx[slot] = d.x; W.a_dy[slot] = d.y; W.a_dz[slot] = d.z;
+                    W.a_t[slot] = t_hit;
+                    W.a_meta[slot] = (unsigned)lane | ((unsigned)k << 5) | ((unsigned)obj << 13);
+                    W.a_index[slot] = index;
                 }
-                qcount += __popc(pushers);
+                a_count += __popc(pushers);
                 __syncwarp();
             } else {
                 // =========================== CONSUME: up to 32 queued surface hits ================================
-                const int n_rec = min(32, qcount);
+                const int n_rec = min(32, consume_a ? a_count : qcount);
                 const bool active = lane < n_rec;
-                const int slot = (qhead + lane) & (QCAP - 1);
-                d3 o = mk3(0, 0, 0), d = o, sample = o;
-                double t_hit = 0.0, weight = 0.0, weight_sum = 0.0;
+                // Only what the first steps need is read now; the accumulated colour and weights stay in the ring slot
+                // until the shading step (registers are what limits the number of resident warps).  The slot cannot
+                // be overwritten before that: pushes happen after the warp-wide ballot at the end of this step.
+                const int slot = ((consume_a ? a_head : qhead) + lane) & (QCAP - 1);
+                d3 o = eye, d = mk3(0, 0, 0);
+                double t_hit = 0.0;
                 unsigned int meta = 0;
                 int index = 0;
-                if (active) {
-                    o = mk3(W.ox[slot], W.oy[slot], W.oz[slot]);
-                    d = mk3(W.dx[slot], W.dy[slot], W.dz[slot]);
-                    t_hit = W.t[slot];
-                    sample = mk3(W.sr[slot], W.sg[slot], W.sb[slot]);
-                    weight = W.w[slot];
-                    weight_sum = W.ws[slot];
-                    meta = W.meta[slot];
-                    index = W.index[slot];
+                if (consume_a) {
+                    // first-generation hit: the ray left the eye, nothing accumulated yet (TRT.c:1014-1017)
+                    if (active) {
+                        d = mk3(W.a_dx[slot], W.a_dy[slot], W.a_dz[slot]);
+                        t_hit = W.a_t[slot];
+                        meta = W.a_meta[slot];
+                        index = W.a_index[slot];
+                    }
+                    a_head = (a_head + n_rec) & (QCAP - 1);
+                    a_count -= n_rec;
+                } else {
+                    if (active) {
+                        o = mk3(W.ox[slot], W.oy[slot], W.oz[slot]);
+                        d = mk3(W.dx[slot], W.dy[slot], W.dz[slot]);
+                        t_hit = W.t[slot];
+                        meta = W.meta[slot];
+                        index = W.index[slot];
+                    }
+                    qhead = (qhead + n_rec) & (QCAP - 1);
+                    qcount -= n_rec;
                 }
-                qhead = (qhead + n_rec) & (QCAP - 1);
-                qcount -= n_rec;
-                __syncwarp();     // every pop is done before any push below may reuse a slot
+                const bool use_patch = consume_a && patch;   // warp-uniform
+                d3 sample = mk3(0.0, 0.0, 0.0);
+                double weight = 1.0, weight_sum = 0.0;
 
                 bool push = false;
                 if (active) {
@@ -666,76 +625,173 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                         const int odd = x86_int(floor(hit.x) + floor(hit.z)) & 1;  // checker parity, TRT.c:850
                         mat = odd ? &c_scene.ground_odd : &c_scene.ground_even;
                     }
-                    const d3 mcol = mk3(mat->color[0], mat->color[1], mat->color[2]);
 
-                    // ---- apply_lighting, TRT.c:894-963 ---------------------------------------------------------
-                    ShadowOrigin so;
-                    set_shadow_origin(so, at, (num_dir + num_point) > 0);
-                    if (!c_scene.filter_enabled) so.S0 = INFINITY;    // makes every certificate ray unusable
+                    // Every query of this record leaves the surface point `at`: one shadow query per light
+                    // (apply_lighting, TRT.c:894-963), then the bounce ray (TRT.c:1054-1057, next trip of 1018).
+                    Query qy;
+                    const float S0 = trt_cert_set_origin(&qy.rf, at.x, at.y, at.z) + S_max;
+                    const double num_g = plane_numerator(at);
                     d3 lit = mk3(0.0, 0.0, 0.0);
-                    for (int l = 0; l < num_dir; l++) {
-                        if (dir_light_open<COUNT, CULL>(P, so, at, l, tally)) {
-                            const DevLightDir &Ld = c_scene.dir[l];
-                            const double f = fmin(dot(nrm, mk3(Ld.L[0], Ld.L[1], Ld.L[2])), 1.0);         // TRT.c:910
-                            d3 diffuse = mk3(Ld.color[0] * f, Ld.color[1] * f, Ld.color[2] * f);
-                            diffuse = hadamard(diffuse, mcol);
-                            lit = lit + diffuse;
-                        }
-                    }
-                    for (int l = 0; l < num_point; l++) {
-                        const DevLightPoint &Lp = c_scene.point[l];
-                        d3 ld = mk3(Lp.pos[0] - at.x, Lp.pos[1] - at.y, Lp.pos[2] - at.z);                // TRT.c:929
-                        const double light_d2 = dot(ld, ld);
-                        ld = unit(ld);                                                                    // TRT.c:933
-                        if (point_light_open<COUNT, CULL>(P, so, at, ld, light_d2, l, tally)) {
-                            const double intensity = clampd(ieee_div(Lp.intensity, light_d2), 0.0, 1.0);  // TRT.c:931
-                            const double f = intensity * fmin(dot(nrm, ld), 1.0);                         // TRT.c:943
-                            d3 diffuse = mk3(Lp.color[0] * f, Lp.color[1] * f, Lp.color[2] * f);
-                            diffuse = hadamard(diffuse, mcol);
-                            lit = lit + diffuse;
-                        }
-                    }
-                    d3 colour = mk3(clampd(lit.x, 0.0, 1.0), clampd(lit.y, 0.0, 1.0), clampd(lit.z, 0.0, 1.0));   // TRT.c:960
-
-                    // ---- accumulate, TRT.c:1034-1051 -----------------------------------------------------------
-                    weight_sum += weight;
-                    colour = colour * weight;
-                    sample = sample + colour;
-                    weight *= mat->reflectivity;                                     // TRT.c:1041-1042
-                    bounces++;
-                    bool done = true;
-                    if (bounces < TRT_BOUNCE_LIMIT && weight > 0.00001) {            // loop condition, TRT.c:1018
-                        // ---- reflect (TRT.c:627-633, 1054-1055) and trace the bounce ray from the surface point
-                        const double dn = dot(d, nrm);
-                        const d3 rd = unit(mk3(d.x - 2.0 * dn * nrm.x, d.y - 2.0 * dn * nrm.y, d.z - 2.0 * dn * nrm.z));
-                        tally.add(CTR_BOUNCE_ITERS);
-                        tally.add(CTR_TRACE_CALLS);
-                        int obj2, index2;
-                        double t2;
-                        closest_hit_bounce<COUNT, CULL>(P, so, at, rd, obj2, index2, t2, tally);
-                        if (obj2 == 0) {
-                            tally.add(CTR_SKY_LOOKUPS);
-                            d3 c = sky_colour(P, s_byte_to_unit, rd);
-                            weight_sum += weight;
-                            c = c * weight;
-                            sample = sample + c;
+                    bool done = false;
+                    const int nq = num_dir + num_point + 1;
+                    for (int q = 0; q < nq; q++) {
+                        // ---- set-up: warp-uniform branch on the kind of query ------------------------------------
+                        bool run = true;
+                        double light_d2 = 0.0;
+                        qy.near_limit = INFINITY;
+                        qy.far_limit = INFINITY;
+                        qy.ground_candidate = false;
+                        qy.plane_denom = 0.0;
+                        if (q < num_dir) {
+                            const DevLightDir &Ld = c_scene.dir[q];
+                            qy.mode = Q_DIR;
+                            qy.d = mk3(Ld.L[0], Ld.L[1], Ld.L[2]);                  // unit(-direction), TRT.c:903-904
+                            qy.rf.dx = Ld.Lf[0]; qy.rf.dy = Ld.Lf[1]; qy.rf.dz = Ld.Lf[2];
+                            const float dd = fmaf(qy.rf.dz, qy.rf.dz, fmaf(qy.rf.dy, qy.rf.dy, qy.rf.dx * qy.rf.dx));
+                            qy.rf.slack_t = (32.0f * TRT_CERT_U) * S0;
+                            qy.rf.usable = (S0 < 1e15f) && (dd > 0.99999f) && (dd < 1.00001f);
+                            qy.plane_denom = Ld.plane_denom;
+                        } else if (q < num_dir + num_point) {
+                            const DevLightPoint &Lp = c_scene.point[q - num_dir];
+                            qy.mode = Q_POINT;
+                            d3 ld = mk3(Lp.pos[0] - at.x, Lp.pos[1] - at.y, Lp.pos[2] - at.z);            // TRT.c:929
+                            light_d2 = dot(ld, ld);
+                            qy.d = unit(ld);                                                              // TRT.c:933
+                            const float dist = trt_cert_set_dir_toward(&qy.rf, Lp.pos_f[0], Lp.pos_f[1], Lp.pos_f[2], S0 + Lp.pos_l1);
+                            const float guard = fmaf(2.0f, qy.rf.slack_t, 1e-5f);
+                            qy.near_limit = dist - guard;
+                            qy.far_limit = dist + guard;
+                            qy.ground_candidate = !trt_cert_ground_cannot_block(num_g, Lp.height, c_scene.ground_margin);
                         } else {
-                            tally.add(CTR_TRACE_HITS);
-                            done = false;
-                            push = true;
-                            o = at;
-                            d = rd;
-                            t_hit = t2;
-                            index = index2;
-                            meta = (unsigned)pix | ((unsigned)k << 5) | ((unsigned)bounces << 9) | ((unsigned)obj2 << 13);
+                            // all lights done: finish apply_lighting (TRT.c:960) and accumulate (TRT.c:1034-1051) ...
+                            qy.mode = Q_CLOSEST;
+                            if (!consume_a) {
+                                sample = mk3(W.sr[slot], W.sg[slot], W.sb[slot]);
+                                weight = W.w[slot];
+                                weight_sum = W.ws[slot];
+                            }
+                            d3 colour = mk3(clampd(lit.x, 0.0, 1.0), clampd(lit.y, 0.0, 1.0), clampd(lit.z, 0.0, 1.0));
+                            weight_sum += weight;
+                            colour = colour * weight;
+                            sample = sample + colour;
+                            weight *= mat->reflectivity;                                     // TRT.c:1041-1042
+                            bounces++;
+                            run = bounces < TRT_BOUNCE_LIMIT && weight > 0.00001;            // loop condition, TRT.c:1018
+                            if (run) {
+                                // ... reflect (TRT.c:627-633, 1054-1055): the bounce ray leaves the surface point
+                                if (consume_a) d = mk3(W.a_dx[slot], W.a_dy[slot], W.a_dz[slot]);
+                                else d = mk3(W.dx[slot], W.dy[slot], W.dz[slot]);
+                                const double dn = dot(d, nrm);
+                                qy.d = unit(mk3(d.x - 2.0 * dn * nrm.x, d.y - 2.0 * dn * nrm.y, d.z - 2.0 * dn * nrm.z));
+                                trt_cert_set_unit_dir(&qy.rf, qy.d.x, qy.d.y, qy.d.z, S0);
+                                tally.add(CTR_BOUNCE_ITERS);
+                            } else {
+                                done = true;
+                            }
+                        }
+                        // ---- the query: one copy of the code for all kinds ----------------------------------------
+                        int obj2 = 0, index2 = -1;
+                        double t2 = 0.0;
+                        bool blocked = false;
+                        if (run) {
+                            if (COUNT || CULL == 0) {
+                                tally.add(CTR_TRACE_CALLS);
+                                query_reference<COUNT>(P, at, qy.d, obj2, index2, t2, tally);
+                            }
+                            if (CULL != 0) {
+                                int obj3, index3;
+                                double t3;
+                                unsigned int exact = 0;
+                                const bool blocked3 = query_certified<CULL == 1>(P, qy, at, num_g, use_patch, use_patch ? W.pmask[q] : 0u, obj3, index3, t3,
+                                                                                 COUNT ? &exact : nullptr);
+                                if (COUNT) {
+                                    // the audit: both paths must lead to the same decision / the same hit
+                                    tally.add(CTR_EXACT_SPHERE_TESTS, exact);
+                                    bool same;
+                                    if (qy.mode == Q_CLOSEST) {
+                                        same = obj3 == obj2 && (!obj2 || (__double_as_longlong(t3) == __double_as_longlong(t2) && (obj2 != 1 || index3 == index2)));
+                                    } else {
+                                        bool open_ref = obj2 == 0, open_cert = !blocked3 && obj3 == 0;
+                                        if (qy.mode == Q_POINT) {
+                                            if (!open_ref) {
+                                                const d3 h2 = mk3(at.x + t2 * qy.d.x, at.y + t2 * qy.d.y, at.z + t2 * qy.d.z);
+                                                const d3 tb = push_back(at, h2) - at;
+                                                open_ref = light_d2 < dot(tb, tb);
+                                            }
+                                            if (!blocked3 && obj3 != 0) {
+                                                const d3 h3 = mk3(at.x + t3 * qy.d.x, at.y + t3 * qy.d.y, at.z + t3 * qy.d.z);
+                                                const d3 tb = push_back(at, h3) - at;
+                                                open_cert = light_d2 < dot(tb, tb);
+                                            }
+                                        }
+                                        same = open_ref == open_cert;
+                                    }
+                                    if (!same) tally.add(CTR_CULL_VIOLATIONS);
+                                } else {
+                                    obj2 = obj3;
+                                    index2 = index3;
+                                    t2 = t3;
+                                    blocked = blocked3;
+                                }
+                            }
+                            if (obj2) tally.add(CTR_TRACE_HITS);
+                            else {
+                                tally.add(CTR_SKY_LOOKUPS);
+                                if (qy.mode != Q_CLOSEST) tally.add(CTR_SKY_SKIPPED);
+                            }
+                        }
+                        // ---- what the answer means ----------------------------------------------------------------
+                        if (qy.mode == Q_CLOSEST) {
+                            if (run) {
+                                if (obj2 == 0) {
+                                    // the bounce ray leaves the scene: sky colour, TRT.c:858-867; the sample ends
+                                    d3 c = sky_colour(P, s_byte_to_unit, qy.d);
+                                    weight_sum += weight;
+                                    c = c * weight;
+                                    sample = sample + c;
+                                    done = true;
+                                } else {
+                                    push = true;
+                                    o = at;
+                                    d = qy.d;
+                                    t_hit = t2;
+                                    index = index2;
+                                    meta = (unsigned)pix | ((unsigned)k << 5) | ((unsigned)bounces << 9) | ((unsigned)obj2 << 13);
+                                }
+                            }
+                        } else {
+                            bool open = !blocked && obj2 == 0;
+                            double f;
+                            const double *lc;
+                            if (qy.mode == Q_DIR) {
+                                lc = c_scene.dir[q].color;
+                                f = 1.0;
+                            } else {
+                                const DevLightPoint &Lp = c_scene.point[q - num_dir];
+                                if (!blocked && obj2 != 0) {
+                                    // a blocker that is farther than the light does not block, TRT.c:936-941
+                                    const d3 bh = mk3(at.x + t2 * qy.d.x, at.y + t2 * qy.d.y, at.z + t2 * qy.d.z);
+                                    const d3 to_blocker = push_back(at, bh) - at;
+                                    open = light_d2 < dot(to_blocker, to_blocker);
+                                }
+                                lc = Lp.color;
+                                f = open ? clampd(ieee_div(Lp.intensity, light_d2), 0.0, 1.0) : 0.0;       // TRT.c:931
+                            }
+                            if (open) {
+                                const double lambert = fmin(dot(nrm, qy.d), 1.0);                          // TRT.c:910, 943
+                                f = qy.mode == Q_DIR ? lambert : f * lambert;
+                                d3 diffuse = mk3(lc[0] * f, lc[1] * f, lc[2] * f);
+                                diffuse = hadamard(diffuse, mk3(mat->color[0], mat->color[1], mat->color[2]));
+                                lit = lit + diffuse;
+                            }
                         }
                     }
                     if (done) {
                         if (COUNT) atomicAdd(&P.counters[CTR_BOUNCE_HIST0 + bounces], 1ull);
                         sample = sample * ieee_div(1.0, weight_sum);                 // TRT.c:1061
-                        W.res[0][k * 32 + pix] = sample.x;
-                        W.res[1][k * 32 + pix] = sample.y;
-                        W.res[2][k * 32 + pix] = sample.z;
+                        __stcg(&res[0 * TILE_SAMPLES + k * 32 + pix], sample.x);
+                        __stcg(&res[1 * TILE_SAMPLES + k * 32 + pix], sample.y);
+                        __stcg(&res[2 * TILE_SAMPLES + k * 32 + pix], sample.z);
                     }
                 }
                 const unsigned int pushers = __ballot_sync(0xffffffffu, push);
@@ -755,11 +811,14 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
         }
 
         // ---- per pixel: add the samples in order, average, store (TRT.c:1063-1066) ---------------------------
+        __threadfence_block();    // the samples were written by other lanes of this warp
+        __syncwarp();
         if (valid) {
             d3 average = mk3(0.0, 0.0, 0.0);
 #pragma unroll
             for (int k = 0; k < TRT_RAYS_PER_PIXEL; k++)
-                average = average + mk3(W.res[0][k * 32 + lane], W.res[1][k * 32 + lane], W.res[2][k * 32 + lane]);
+                average = average + mk3(__ldcg(&res[0 * TILE_SAMPLES + k * 32 + lane]), __ldcg(&res[1 * TILE_SAMPLES + k * 32 + lane]),
+                                        __ldcg(&res[2 * TILE_SAMPLES + k * 32 + lane]));
             average = average * (1.0 / TRT_RAYS_PER_PIXEL);
             if (P.row_cost) atomicAdd(&P.row_cost[brow], 50u);
             const size_t pix = (size_t)brow * (size_t)P.width + (size_t)col;
@@ -778,7 +837,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                 P.quant[pix] = q;
             }
         }
-        __syncwarp();   // res and tmask are rewritten by the next tile
+        __syncwarp();   // the sample slice and tmask are rewritten by the next tile
     }
 }
 
@@ -800,10 +859,10 @@ __global__ void k_probe_trace(const RenderParams P, const double *__restrict__ r
     int obj, index;
     double t_hit;
     if (c_scene.filter_enabled) {
-        ShadowOrigin so;
-        set_shadow_origin(so, o, false);
-        if (c_scene.filter_in_const) closest_hit_bounce<false, 1>(P, so, o, d, obj, index, t_hit, tally);
-        else closest_hit_bounce<false, 2>(P, so, o, d, obj, index, t_hit, tally);
+        Query qy;
+        setup_closest_query(qy, o, d, fabsf((float)o.x) + fabsf((float)o.y) + fabsf((float)o.z) + c_scene.filter_centre_l1);
+        if (c_scene.filter_in_const) query_certified<true>(P, qy, o, plane_numerator(o), false, 0u, obj, index, t_hit, nullptr);
+        else query_certified<false>(P, qy, o, plane_numerator(o), false, 0u, obj, index, t_hit, nullptr);
     } else {
         query_reference<false>(P, o, d, obj, index, t_hit, tally);
     }
@@ -952,6 +1011,12 @@ int render_ctas_per_sm()
         cached = n > 0 ? n : 1;
     }
     return cached;
+}
+
+size_t render_scratch_bytes(int num_sms)
+{
+    // one slice of finished samples (3 channels x 320 samples) per warp of the persistent grid
+    return (size_t)num_sms * (size_t)render_ctas_per_sm() * WARPS_PER_CTA * (size_t)(3 * TILE_SAMPLES) * sizeof(double);
 }
 
 void launch_render(const RenderParams &p, bool count, int cull, int num_sms, cudaStream_t stream)
