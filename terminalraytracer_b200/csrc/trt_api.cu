@@ -74,7 +74,7 @@ struct Context {
     bool have_scene = false;
     bool cull_allowed = true;   // trt_set_cull(); the FP32 miss test can be switched off for A/B runs
     bool cull = true;           // cull_allowed && this scene's magnitudes are inside the bound's range
-    Buffer sphere_geom, sphere_cull, sphere_mat, sphere_prim;
+    Buffer sphere_geom, sphere_cull, sphere_mat, sphere_prim, cull_pairs;
     // skybox
     Buffer sky;
     int sky_dim = -1, sky_face_stride = 0;
@@ -298,7 +298,18 @@ void upload_scene(const trt_Scene *scene)
     // returns: plain (staged) cudaMemcpyAsync from pageable memory is synchronous w.r.t. the host buffer.
     CK(cudaMemcpyAsync(g.sphere_geom.p, geom.data(), sizeof(double4) * geom.size(), cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(g.sphere_mat.p, mats.data(), sizeof(DevMaterial) * mats.size(), cudaMemcpyHostToDevice, g.stream));
-    upload_scene_constants(s, cull.data(), n + 2, g.stream);
+    // the same records two by two for the packed classification; the odd one out is paired with a sphere of radius 0
+    std::vector<CullPair> pairs((size_t)(n / 2 + 1));
+    for (size_t p = 0; p < pairs.size(); p++) {
+        const float4 a = cull[2 * p], b = cull[2 * p + 1];   // cull has n + 2 entries, zero-filled past n
+        pairs[p].cx = make_float2(a.x, b.x);
+        pairs[p].cy = make_float2(a.y, b.y);
+        pairs[p].cz = make_float2(a.z, b.z);
+        pairs[p].r = make_float2(a.w, b.w);
+    }
+    g.cull_pairs.reserve(sizeof(CullPair) * pairs.size());
+    CK(cudaMemcpyAsync(g.cull_pairs.p, pairs.data(), sizeof(CullPair) * pairs.size(), cudaMemcpyHostToDevice, g.stream));
+    upload_scene_constants(s, pairs.data(), (int)pairs.size(), g.stream);
     CK(cudaStreamSynchronize(g.stream));
     g.have_scene = true;
 }
@@ -328,6 +339,7 @@ RenderParams make_params(int width, int height, int row0, int row1, double *d_pi
     p.sphere_geom = (const double4 *)g.sphere_geom.p;
     p.sphere_cull = (const float4 *)g.sphere_cull.p;
     p.sphere_prim = (const double4 *)g.sphere_prim.p;
+    p.cull_pairs = (const CullPair *)g.cull_pairs.p;
     p.sphere_mat = (const DevMaterial *)g.sphere_mat.p;
     p.byte_to_unit = (const double *)g.byte_to_unit.p;
     p.sky = (const uchar4 *)g.sky.p;
@@ -390,6 +402,7 @@ void trt_shutdown(void)
     g.sphere_cull.release();
     g.sphere_mat.release();
     g.sphere_prim.release();
+    g.cull_pairs.release();
     g.sky.release();
     g.tile_counter.release();
     g.scratch.release();
@@ -599,6 +612,7 @@ int trt_probe_skybox(const double *dirs, int n, int *out)
         g.sphere_geom.reserve(sizeof(double4));
         g.sphere_cull.reserve(sizeof(float4));
         g.sphere_prim.reserve(sizeof(double4));
+        g.cull_pairs.reserve(sizeof(CullPair));
         g.sphere_mat.reserve(sizeof(DevMaterial));
         g.have_scene = true;
     } else {

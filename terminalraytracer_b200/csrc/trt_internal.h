@@ -6,7 +6,7 @@
 namespace trt {
 
 // trt_render.cu (owns the __constant__ scene)
-void upload_scene_constants(const DevScene &scene, const float4 *cull, int count, cudaStream_t stream);
+void upload_scene_constants(const DevScene &scene, const CullPair *pairs, int count, cudaStream_t stream);
 void launch_render(const RenderParams &p, bool count, int cull, int num_sms, cudaStream_t stream);
 int render_ctas_per_sm();
 size_t render_scratch_bytes(int num_sms);   // RenderParams::sample_scratch must be at least this big

@@ -36,7 +36,9 @@
 namespace trt {
 
 __constant__ DevScene c_scene;
-__constant__ float4 c_sphere_cull[TRT_MAX_CONST_SPHERES + 2]; // (cx, cy, cz, r_pad) in float, see trt_cert.h
+// Certificate records, two spheres per record so that the classification runs on the packed FP32 pipe
+// (FFMA2/FADD2/FMUL2 of sm_100: one issue slot, two spheres): .x = sphere 2p, .y = sphere 2p+1 (a pad sphere has r = 0)
+__constant__ CullPair c_cull_pairs[TRT_MAX_CONST_SPHERES / 2 + 1];
 
 constexpr int TILE_W = 8;
 constexpr int TILE_H = 4;
@@ -91,6 +93,16 @@ __device__ __forceinline__ double4 ldg4(const double4 *geom, int i)
     const double2 *p = reinterpret_cast<const double2 *>(geom + i);
     const double2 lo = __ldg(p), hi = __ldg(p + 1);
     return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+
+__device__ __forceinline__ CullPair ldg_pair(const CullPair *pairs, int p)
+{
+    const float4 *q = reinterpret_cast<const float4 *>(pairs + p);
+    const float4 lo = __ldg(q), hi = __ldg(q + 1);
+    CullPair g;
+    g.cx = make_float2(lo.x, lo.y); g.cy = make_float2(lo.z, lo.w);
+    g.cz = make_float2(hi.x, hi.y); g.r = make_float2(hi.z, hi.w);
+    return g;
 }
 
 template <bool COUNT>
@@ -289,6 +301,13 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const Que
     const bool usable = qy.rf.usable != 0;
     const bool shadow = qy.mode != Q_CLOSEST;
     bool blocked = false;
+    // the certificate ray in packed form: both halves of every pair carry the same value
+    struct { float2 nox, noy, noz, dx, dy, dz; } rp;
+    rp.nox = make_float2(-qy.rf.ox, -qy.rf.ox); rp.noy = make_float2(-qy.rf.oy, -qy.rf.oy); rp.noz = make_float2(-qy.rf.oz, -qy.rf.oz);
+    rp.dx = make_float2(qy.rf.dx, qy.rf.dx); rp.dy = make_float2(qy.rf.dy, qy.rf.dy); rp.dz = make_float2(qy.rf.dz, qy.rf.dz);
+    const float slack = qy.rf.slack_t;
+    const float2 slack2 = make_float2(slack, slack), nslack2 = make_float2(-slack, -slack);
+    const float2 neg1 = make_float2(-1.0f, -1.0f), shrink2 = make_float2(0.99999237060546875f, 0.99999237060546875f);
     for (int base = 0; base < n; base += 32) {
         const int cnt = min(32, n - base);
         // pass 1 (float, warp-uniform record addresses): classify the candidate spheres of this chunk — all of them,
@@ -296,17 +315,38 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const Que
         const unsigned int valid = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
         const unsigned int candidates = use_patch ? (patch_mask & valid) : valid;
         unsigned int survivors = 0;
+        // two spheres per trip: the arithmetic of trt_cert_sphere2 (same operations, same rounding) on float pairs
 #pragma unroll 1
-        for (unsigned int m = candidates; m; m &= m - 1) {
-            const int j = __ffs(m) - 1;
-            const float4 g = CONST_RECORDS ? c_sphere_cull[base + j] : __ldg(&P.sphere_cull[base + j]);
-            int miss, blocks;
-            trt_cert_sphere2(&qy.rf, g.x, g.y, g.z, g.w, qy.near_limit, qy.far_limit, &miss, &blocks);
-            if (!miss) survivors |= 1u << j;
-            blocked = blocked || blocks;
+        for (unsigned int m = (candidates | (candidates >> 1)) & 0x55555555u; m; m &= m - 1) {
+            const int j = __ffs(m) - 1;             // even: spheres base + j and base + j + 1
+            const CullPair g = CONST_RECORDS ? c_cull_pairs[(base + j) >> 1] : ldg_pair(P.cull_pairs, (base + j) >> 1);
+            const float2 ocx = __fadd2_rn(g.cx, rp.nox), ocy = __fadd2_rn(g.cy, rp.noy), ocz = __fadd2_rn(g.cz, rp.noz);
+            const float2 tc = __ffma2_rn(ocz, rp.dz, __ffma2_rn(ocy, rp.dy, __fmul2_rn(ocx, rp.dx)));
+            const float2 ntc = __fmul2_rn(tc, neg1);
+            const float2 wx = __ffma2_rn(ntc, rp.dx, ocx), wy = __ffma2_rn(ntc, rp.dy, ocy), wz = __ffma2_rn(ntc, rp.dz, ocz);
+            const float2 h2 = __ffma2_rn(wz, wz, __ffma2_rn(wy, wy, __fmul2_rn(wx, wx)));
+            const float2 outer = __fadd2_rn(g.r, slack2);
+            const float2 outer_sq = __fmul2_rn(outer, outer);
+            const float2 front = __ffma2_rn(g.r, neg1, tc);
+            const bool miss0 = (h2.x > outer_sq.x) || (tc.x < -slack) || (front.x > qy.far_limit);
+            const bool miss1 = (h2.y > outer_sq.y) || (tc.y < -slack) || (front.y > qy.far_limit);
+            if (!miss0) survivors |= 1u << j;
+            if (!miss1) survivors |= 2u << j;
+            if (shadow) {
+                const float2 inner = __ffma2_rn(g.r, shrink2, nslack2);
+                const float2 inner_sq = __fmul2_rn(inner, inner);
+                const bool blocks0 = (inner.x > 0.0f) && (h2.x < inner_sq.x) && (front.x > slack) && (tc.x < qy.near_limit);
+                const bool blocks1 = (inner.y > 0.0f) && (h2.y < inner_sq.y) && (front.y > slack) && (tc.y < qy.near_limit);
+                // a pad sphere (r = 0) has inner < 0 and cannot block; a non-candidate of a patch tile that "blocks" is
+                // impossible as well: the patch certificate proved that none of the tile's rays can reach it
+                blocked = blocked || blocks0 || blocks1;
+            }
         }
+        survivors &= candidates;
         if (!usable) survivors = candidates;
         if (shadow && usable && blocked) survivors = 0;
+        // many-sphere scenes: once every lane's light is proven blocked the remaining chunks cannot change anything
+        if (shadow && n > 32 && __all_sync(__activemask(), usable && blocked)) break;
         if (exact_tests) *exact_tests += (unsigned int)__popc(survivors);
         // pass 2 (double, exact): each lane walks its own survivors in index order
         while (survivors) {
@@ -986,11 +1026,11 @@ static void die(cudaError_t e, const char *file, int line)
 }
 #define CK(x) die((x), __FILE__, __LINE__)
 
-void upload_scene_constants(const DevScene &scene, const float4 *cull, int count, cudaStream_t stream)
+void upload_scene_constants(const DevScene &scene, const CullPair *pairs, int count, cudaStream_t stream)
 {
     CK(cudaMemcpyToSymbolAsync(c_scene, &scene, sizeof(DevScene), 0, cudaMemcpyHostToDevice, stream));
-    if (cull && count > 0 && count <= TRT_MAX_CONST_SPHERES + 2)
-        CK(cudaMemcpyToSymbolAsync(c_sphere_cull, cull, sizeof(float4) * (size_t)count, 0, cudaMemcpyHostToDevice, stream));
+    if (pairs && count > 0 && count <= TRT_MAX_CONST_SPHERES / 2 + 1)
+        CK(cudaMemcpyToSymbolAsync(c_cull_pairs, pairs, sizeof(CullPair) * (size_t)count, 0, cudaMemcpyHostToDevice, stream));
 }
 
 template <bool COUNT, int CULL>
