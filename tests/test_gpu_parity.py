@@ -145,6 +145,43 @@ def test_gpu_camera_inside_sphere_and_far_camera(renderer, orc):
     assert np.array_equal(gpu_frame(renderer, sc), U.cpu_render(orc, "orc_project_scene", sc))
 
 
+def test_gpu_patch_tiles_many_lights_and_audit(renderer, orc):
+    """camera high above the ground looking down: every tile is a patch tile (tile-level certificates for the shadow and
+    bounce rays of the ground hits); lights above, below and far from the ground; the counting build's audit (every
+    query answered both ways) must report 0 disagreements and the frame must equal the oracle's"""
+    sc = _custom_scene(120, 68, 3, 4, 6, t=0.0)
+    sc.pls[0].position = abi.Vector(0.3, -5.0, 0.2)       # below the ground plane
+    sc.pls[1].position = abi.Vector(40.0, 0.5, -30.0)     # far away, grazing
+    sc.dls[0].direction = abi.Vector(0.2, 1.0, 0.1)       # shines upward: the ground blocks it everywhere
+    cam = sc.c.camera
+    cam.frame.origin = abi.Vector(0.4, 9.0, 0.3)
+    cam.frame.basis.x = abi.Vector(1.0, 0.0, 0.0)
+    cam.frame.basis.y = abi.Vector(0.0, 0.0, -1.0)
+    cam.frame.basis.z = abi.Vector(0.0, 1.0, 0.0)         # looks along -z of the basis, i.e. straight down
+    got = gpu_frame(renderer, sc)
+    assert np.array_equal(got, U.cpu_render(orc, "orc_project_scene", sc))
+    renderer.set_scene(sc)
+    ctr, _ = renderer.count_rows(sc.width, sc.height, 0, sc.height)
+    assert ctr[28] == 0
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 64, 65], ids=lambda n: f"{n}spheres")
+def test_gpu_sphere_counts_around_chunk_and_patch_limits(renderer, orc, n):
+    """32 spheres per certificate chunk, two per packed record, patch certificates up to 32 spheres"""
+    sc = S.SceneData(72, 40, S.synthetic_cubemap("uv_gradient", 64), kind="stress", num_spheres=65).set_time(3.7)
+    sc.c.num_spheres = n
+    assert np.array_equal(gpu_frame(renderer, sc), U.cpu_render(orc, "orc_project_scene", sc))
+    renderer.set_scene(sc)
+    ctr, _ = renderer.count_rows(sc.width, sc.height, 0, sc.height)
+    assert ctr[28] == 0
+
+
+def test_gpu_more_spheres_than_tile_masks(renderer, orc):
+    """> 4096 spheres: no tile certificates, primary rays test every sphere exactly"""
+    sc = S.SceneData(24, 14, S.synthetic_cubemap("uv_gradient", 64), kind="stress", num_spheres=4100).set_time(3.7)
+    assert np.array_equal(gpu_frame(renderer, sc), U.cpu_render(orc, "orc_project_scene", sc))
+
+
 # ---- unit-level probes ----------------------------------------------------------------------------------
 
 def test_gpu_trace_ray_known_answers(renderer):
