@@ -5,11 +5,9 @@
 // Output layout (TRT.c:1102-1104):  "\033[0;0H"  +  H x ( W x "\033[48;2;RRR;GGG;BBBm  \033[0m" + "\n" )
 // + 3 NUL bytes.  A cell is 25 bytes, a row 25W+1 bytes -> rows start at odd, unaligned addresses.
 //
-// This is pure byte traffic (24 B read per FP64 pixel or 4 B per quantised cell, 25 B written), so the
-// kernel is built around store efficiency: each CTA owns a 16-byte-aligned 8 KB window of the
-// destination, threads format whole cells into shared memory (byte-granular, any alignment), and the
-// window then leaves the SM as full 16-byte vector stores; only the first/last window of a band can be
-// partial and falls back to byte stores.
+// This is pure byte traffic (24 B read per FP64 pixel or 4 B per quantised cell, 25 B written), so the kernel is
+// built around instruction economy and store efficiency: whole words are composed in registers (no per-byte
+// stores, no divisions), staged in shared memory, and leave the SM as 16-byte stores aligned to the destination.
 #include <cstdio>
 #include <cstdlib>
 #include "trt_internal.h"
@@ -17,7 +15,10 @@
 namespace trt {
 
 constexpr int ENC_THREADS = 256;
-constexpr int ENC_WINDOW = ENC_THREADS * 16 * 2; // bytes of destination per CTA
+constexpr int ENC_CELLS_PER_THREAD = 4;                             // 4 cells = 100 bytes = 25 words: word aligned
+constexpr int ENC_CELLS = ENC_THREADS * ENC_CELLS_PER_THREAD;       // cells of one row per CTA
+constexpr int ENC_WORDS = ENC_CELLS * TRT_CELL_BYTES / 4;           // 6400 words staged per CTA
+static_assert((ENC_CELLS_PER_THREAD * TRT_CELL_BYTES) % 4 == 0, "a thread's cells must fill whole words");
 
 // (int)(c*255) as the x86-64 reference build does it, then byte_to_digits' integer arithmetic
 __device__ __forceinline__ int quantise(double c)
@@ -26,9 +27,14 @@ __device__ __forceinline__ int quantise(double c)
     return (v >= -2147483648.0 && v < 2147483648.0) ? (int)v : (int)0x80000000;
 }
 
-__device__ __forceinline__ void put(unsigned char *win, long long at, long long win_len, unsigned char b)
+// byte_to_digits (TRT.c:1134-1139) on an int: value/100, (value/10)%10, value%10, each + '0', truncated to a char.
+// For 0..255 — everything a [0,1] framebuffer produces — the three characters come from a table; other ints
+// (pixels outside [0,1], NaN -> INT_MIN) take the arithmetic, whose wrap-around is what the reference prints.
+__device__ __forceinline__ unsigned int digits_of(int v, const unsigned int *s_lut)
 {
-    if (at >= 0 && at < win_len) win[at] = b;
+    if ((unsigned)v < 256u) return s_lut[v];
+    return (unsigned)(unsigned char)(v / 100 + '0') | ((unsigned)(unsigned char)((v / 10) % 10 + '0') << 8) |
+           ((unsigned)(unsigned char)(v % 10 + '0') << 16);
 }
 
 template <typename Src> struct Load;
@@ -51,72 +57,101 @@ template <> struct Load<uchar4> {
     }
 };
 
+// OR the 32-bit little-endian `word` into out[] at byte offset OFF (compile-time): at most two registers
+template <int OFF>
+__device__ __forceinline__ void put_word(unsigned int (&out)[ENC_CELLS_PER_THREAD * TRT_CELL_BYTES / 4 + 1], unsigned int word)
+{
+    out[OFF >> 2] |= word << (8 * (OFF & 3));
+    if constexpr ((OFF & 3) != 0) out[(OFF >> 2) + 1] |= word >> (32 - 8 * (OFF & 3));
+}
+
+// the 25 bytes of one cell, "\033[48;2;RRR;GGG;BBBm  \033[0m" (TRT.c:1103), as seven words at byte offset OFF
+template <int OFF>
+__device__ __forceinline__ void put_cell(unsigned int (&out)[ENC_CELLS_PER_THREAD * TRT_CELL_BYTES / 4 + 1], unsigned int r3, unsigned int g3,
+                                         unsigned int b3)
+{
+    put_word<OFF + 0>(out, 0x38345b1bu);                                     // ESC [ 4 8
+    put_word<OFF + 4>(out, 0x003b323bu | (r3 << 24));                        // ; 2 ; R
+    put_word<OFF + 8>(out, (r3 >> 8) | 0x003b0000u | (g3 << 24));            // R R ; G
+    put_word<OFF + 12>(out, (g3 >> 8) | 0x003b0000u | (b3 << 24));           // G G ; B
+    put_word<OFF + 16>(out, (b3 >> 8) | 0x206d0000u);                        // B B m ' '
+    put_word<OFF + 20>(out, 0x305b1b20u);                                    // ' ' ESC [ 0
+    out[(OFF + 24) >> 2] |= 0x6du << (8 * ((OFF + 24) & 3));                 // m
+}
+
+// One CTA = up to 1024 consecutive cells of ONE row (no divisions to find rows).  Each thread formats 4 cells —
+// 100 bytes, 25 whole words built in registers with compile-time byte positions — into shared memory; the CTA's bytes
+// then leave as 16-byte stores aligned to the DESTINATION: a row starts at an odd offset (6 + r(25W+1)), so every
+// output word is funnel-shifted out of two staged words (the shift is uniform over the CTA).  Only the first and last
+// 16-byte chunk of a CTA can straddle its neighbours' bytes and are written bytewise.
 template <typename Src>
 __global__ void __launch_bounds__(ENC_THREADS) k_encode(const Src *__restrict__ src, int width, int rows,
                                                         unsigned char *__restrict__ out_base, unsigned long long byte_offset)
 {
-    __shared__ __align__(16) unsigned char win[ENC_WINDOW];
+    __shared__ __align__(16) unsigned int s_win[ENC_WORDS + 8];
+    __shared__ unsigned int s_lut[256];
+    {
+        const int v = threadIdx.x;   // ENC_THREADS == 256
+        s_lut[v] = (unsigned)(v / 100 + '0') | ((unsigned)((v / 10) % 10 + '0') << 8) | ((unsigned)(v % 10 + '0') << 16);
+    }
+    const int row = blockIdx.y;
+    const int c0 = blockIdx.x * ENC_CELLS;
+    const int ncells = min(ENC_CELLS, width - c0);
     const unsigned long long row_bytes = (unsigned long long)TRT_CELL_BYTES * (unsigned long long)width + 1ull;
-    const unsigned long long region0 = byte_offset;
-    const unsigned long long region1 = byte_offset + row_bytes * (unsigned long long)rows;
-    const unsigned long long aligned0 = region0 & ~15ull;
-    const unsigned long long w0 = aligned0 + (unsigned long long)blockIdx.x * ENC_WINDOW; // window start (16B aligned)
-    unsigned long long w1 = w0 + ENC_WINDOW;
-    const unsigned long long lo = w0 > region0 ? w0 : region0; // valid bytes of this window: [lo, hi)
-    const unsigned long long hi = w1 < region1 ? w1 : region1;
-    if (lo >= hi) return;
-    const long long win_len = (long long)(hi - w0);
+    // first byte of this CTA in the stream, and how many it owns (the last CTA of a row also owns the '\n')
+    const unsigned long long g0 = byte_offset + (unsigned long long)row * row_bytes + (unsigned long long)c0 * TRT_CELL_BYTES;
+    const int nbytes = ncells * TRT_CELL_BYTES + ((c0 + ncells == width) ? 1 : 0);
+    __syncthreads();
 
-    // cells (row-major, the last cell of a row also owns the '\n') that intersect [lo, hi)
-    const unsigned long long rel_lo = lo - region0, rel_hi = hi - 1 - region0;
-    const unsigned long long r_lo = rel_lo / row_bytes, r_hi = rel_hi / row_bytes;
-    unsigned long long c_lo = (rel_lo - r_lo * row_bytes) / TRT_CELL_BYTES;
-    unsigned long long c_hi = (rel_hi - r_hi * row_bytes) / TRT_CELL_BYTES;
-    if (c_lo >= (unsigned long long)width) c_lo = width - 1;
-    if (c_hi >= (unsigned long long)width) c_hi = width - 1;
-    const unsigned long long cell0 = r_lo * width + c_lo, cell1 = r_hi * width + c_hi;
-    const int ncells = (int)(cell1 - cell0 + 1);
-
-    for (int i = threadIdx.x; i < ncells; i += ENC_THREADS) {
-        const unsigned long long cid = cell0 + (unsigned long long)i;
-        const unsigned long long row = cid / (unsigned long long)width;
-        const unsigned int cell = (unsigned int)(cid - row * (unsigned long long)width);
-        int v[3];
-        Load<Src>::rgb(src, (size_t)cid, v[0], v[1], v[2]);
-        // position of the cell's first byte relative to the window start
-        const long long at = (long long)(region0 + row * row_bytes + (unsigned long long)cell * TRT_CELL_BYTES) - (long long)w0;
-        unsigned char b[TRT_CELL_BYTES + 1];
-        b[0] = 0x1b; b[1] = '['; b[2] = '4'; b[3] = '8'; b[4] = ';'; b[5] = '2'; b[6] = ';';
+    // ---- format: 4 cells per thread -------------------------------------------------------------------------
+    const int first = threadIdx.x * ENC_CELLS_PER_THREAD;
+    if (first < ncells) {
+        unsigned int out[ENC_CELLS_PER_THREAD * TRT_CELL_BYTES / 4 + 1];
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            b[7 + ch * 4 + 0] = (unsigned char)(v[ch] / 100 + '0');        // TRT.c:1136
-            b[7 + ch * 4 + 1] = (unsigned char)((v[ch] / 10) % 10 + '0');  // TRT.c:1137
-            b[7 + ch * 4 + 2] = (unsigned char)(v[ch] % 10 + '0');         // TRT.c:1138
+        for (int k = 0; k < ENC_CELLS_PER_THREAD * TRT_CELL_BYTES / 4 + 1; k++) out[k] = 0u;
+        unsigned int d[ENC_CELLS_PER_THREAD][3];
+#pragma unroll
+        for (int k = 0; k < ENC_CELLS_PER_THREAD; k++) {
+            int v[3] = {0, 0, 0};
+            if (first + k < ncells) Load<Src>::rgb(src, (size_t)row * (size_t)width + (size_t)(c0 + first + k), v[0], v[1], v[2]);
+            d[k][0] = digits_of(v[0], s_lut);
+            d[k][1] = digits_of(v[1], s_lut);
+            d[k][2] = digits_of(v[2], s_lut);
         }
-        b[10] = ';'; b[14] = ';'; b[18] = 'm'; b[19] = ' '; b[20] = ' ';
-        b[21] = 0x1b; b[22] = '['; b[23] = '0'; b[24] = 'm'; b[25] = '\n';
-        const int nbytes = (cell == (unsigned int)(width - 1)) ? TRT_CELL_BYTES + 1 : TRT_CELL_BYTES;
-        if (at >= 0 && at + TRT_CELL_BYTES + 1 <= win_len) {
+        put_cell<0 * TRT_CELL_BYTES>(out, d[0][0], d[0][1], d[0][2]);
+        put_cell<1 * TRT_CELL_BYTES>(out, d[1][0], d[1][1], d[1][2]);
+        put_cell<2 * TRT_CELL_BYTES>(out, d[2][0], d[2][1], d[2][2]);
+        put_cell<3 * TRT_CELL_BYTES>(out, d[3][0], d[3][1], d[3][2]);
 #pragma unroll
-            for (int j = 0; j < TRT_CELL_BYTES; j++) win[at + j] = b[j];
-            if (nbytes > TRT_CELL_BYTES) win[at + TRT_CELL_BYTES] = b[TRT_CELL_BYTES];
-        } else {
-#pragma unroll
-            for (int j = 0; j < TRT_CELL_BYTES + 1; j++)
-                if (j < nbytes) put(win, at + j, win_len, b[j]);
-        }
+        for (int k = 0; k < ENC_CELLS_PER_THREAD * TRT_CELL_BYTES / 4; k++) s_win[threadIdx.x * 25 + k] = out[k];
+        // end of the row inside this thread's cells: the byte after the last cell is '\n' (TRT.c:1103, 1125).  It lands
+        // on a padding cell of this thread or on the first byte of the next thread's words, which that thread (idle:
+        // the row is over) does not write.
+        const int mine = min(ENC_CELLS_PER_THREAD, ncells - first);
+        if (c0 + first + mine == width) reinterpret_cast<unsigned char *>(s_win)[threadIdx.x * 100 + mine * TRT_CELL_BYTES] = 0x0a;
     }
     __syncthreads();
 
-    // drain the window: full 16-byte stores wherever the whole chunk is valid
-    unsigned char *dst = out_base + w0;
-    for (int chunk = threadIdx.x; chunk < ENC_WINDOW / 16; chunk += ENC_THREADS) {
-        const unsigned long long g0 = w0 + (unsigned long long)chunk * 16, g1 = g0 + 16;
-        if (g0 >= lo && g1 <= hi) {
-            *reinterpret_cast<uint4 *>(dst + chunk * 16) = *reinterpret_cast<const uint4 *>(win + chunk * 16);
-        } else if (g1 > lo && g0 < hi) {
+    // ---- drain: 16-byte chunks aligned to the destination ---------------------------------------------------------
+    const unsigned int a = (unsigned int)(g0 & 15ull);           // window byte 0 sits `a` bytes into its 16-byte chunk
+    unsigned char *const chunk0 = out_base + (g0 - a);            // 16-byte aligned (out_base is)
+    const int nchunks = (int)((a + (unsigned)nbytes + 15u) >> 4);
+    const unsigned char *const s_bytes = reinterpret_cast<const unsigned char *>(s_win);
+    for (int q = threadIdx.x; q < nchunks; q += ENC_THREADS) {
+        const int o = q * 16 - (int)a;                            // window byte offset of this chunk
+        if (o >= 0 && o + 16 <= nbytes) {
+            const int wofs = o >> 2;
+            const unsigned int sh = 8u * (unsigned)(o & 3);
+            const unsigned int w0 = s_win[wofs], w1 = s_win[wofs + 1], w2 = s_win[wofs + 2], w3 = s_win[wofs + 3], w4 = s_win[wofs + 4];
+            uint4 v;
+            v.x = __funnelshift_r(w0, w1, sh);
+            v.y = __funnelshift_r(w1, w2, sh);
+            v.z = __funnelshift_r(w2, w3, sh);
+            v.w = __funnelshift_r(w3, w4, sh);
+            *reinterpret_cast<uint4 *>(chunk0 + (size_t)q * 16) = v;
+        } else {
             for (int j = 0; j < 16; j++)
-                if (g0 + j >= lo && g0 + j < hi) dst[chunk * 16 + j] = win[chunk * 16 + j];
+                if (o + j >= 0 && o + j < nbytes) chunk0[(size_t)q * 16 + j] = s_bytes[o + j];
         }
     }
 }
@@ -145,13 +180,16 @@ static void launch_encode(const Src *src, int width, int rows, char *out_base, s
         fprintf(stderr, "%s:%d: encode destination must be 16-byte aligned\n", __FILE__, __LINE__);
         exit(1);
     }
-    const unsigned long long row_bytes = (unsigned long long)TRT_CELL_BYTES * width + 1ull;
-    const unsigned long long region0 = byte_offset, region1 = byte_offset + row_bytes * rows;
-    const unsigned long long aligned0 = region0 & ~15ull;
-    const unsigned long long windows = (region1 - aligned0 + ENC_WINDOW - 1) / ENC_WINDOW;
-    k_encode<Src><<<(unsigned)windows, ENC_THREADS, 0, stream>>>(src, width, rows, reinterpret_cast<unsigned char *>(out_base),
-                                                               (unsigned long long)byte_offset);
-    ck(cudaGetLastError(), __LINE__);
+    const int blocks_x = (width + ENC_CELLS - 1) / ENC_CELLS;
+    // gridDim.y is limited to 65535: taller bands go in slices
+    for (int r0 = 0; r0 < rows; r0 += 65535) {
+        const int nr = rows - r0 < 65535 ? rows - r0 : 65535;
+        const unsigned long long row_bytes = (unsigned long long)TRT_CELL_BYTES * width + 1ull;
+        k_encode<Src><<<dim3((unsigned)blocks_x, (unsigned)nr), ENC_THREADS, 0, stream>>>(
+            src + (size_t)r0 * (size_t)width * (sizeof(Src) == sizeof(double) ? 3 : 1), width, nr, reinterpret_cast<unsigned char *>(out_base),
+            (unsigned long long)byte_offset + (unsigned long long)r0 * row_bytes);
+        ck(cudaGetLastError(), __LINE__);
+    }
 }
 
 void launch_encode_f64(const double *pixels, int width, int rows, char *out_base, size_t byte_offset, cudaStream_t stream)
