@@ -24,6 +24,7 @@ int orc_hit_plane(const trt_Ray *ray, const trt_Plane *p, trt_Point *hit, void *
 trt_ObjectType orc_closest_hit(const trt_Scene *scene, const trt_Ray *ray, trt_Point *hit_out, trt_Vector *normal_out,
                                trt_Material *material_out, void *ctr);
 void orc_subpixel_offsets(double *dx, double *dy);
+void orc_sky_texel(const trt_Skybox *sky, const trt_Vector *direction, trt_Color *color, int *face_out, long *index_out);
 
 static inline double dot3(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 static inline v3 sub3(v3 a, v3 b) { v3 r = {a.x - b.x, a.y - b.y, a.z - b.z}; return r; }
@@ -42,6 +43,7 @@ enum {
     ST_DIR, ST_DIR_OPEN, ST_DIR_BLOCKED, ST_DIR_UNKNOWN,
     ST_POINT, ST_POINT_OPEN, ST_POINT_BLOCKED, ST_POINT_UNKNOWN,
     ST_SHADOW_EXACT_TESTS,
+    ST_SKY, ST_SKY_CERTIFIED,
     ST_TILES, ST_TILES_PATCH, ST_PATCH_DIR_CANDIDATES, ST_PATCH_POINT_CANDIDATES, ST_PATCH_BOUNCE_CANDIDATES, ST_PATCH_RECORDS,
     ST_COUNT
 };
@@ -383,6 +385,16 @@ long long cert_check_rows(const trt_Scene *scene, int W, int H, int row0, int ro
                                 weight *= m.reflectivity;
                                 bounces++;
                             } else {
+                                /* the sample ends in the sky: face and texel of the lookup, certificate vs reference */
+                                int face = -1, texel = -1, rface = -1;
+                                long rindex = -1;
+                                trt_Color col;
+                                stats[ST_SKY]++;
+                                orc_sky_texel(&scene->skybox, &ray.direction, &col, &rface, &rindex);
+                                if (trt_cert_sky_texel((float)ray.direction.x, (float)ray.direction.y, (float)ray.direction.z, scene->skybox.dim, &face, &texel)) {
+                                    stats[ST_SKY_CERTIFIED]++;
+                                    if (face != rface || (long)texel != rindex) c.bad++;
+                                }
                                 weight = 0.0;
                                 going = 0;
                             }

@@ -364,4 +364,46 @@ TRT_HD int trt_cert_patch_bounce_candidate(const trt_cert_ball *b, float Rx, flo
     return !trt_cert_tile_sphere_miss(b->cx, b->cy, b->cz, Rx, Ry, Rz, h, cx, cy, cz, r_pad + b->r, S);
 }
 
+/* ---- skybox texel certificate ------------------------------------------------------------------------------------
+ * get_skybox_color (TRT.c:700-789) turns a direction into a cube face and a texel index: a DECISION.  Evaluated in
+ * float, face and index are certainly the reference's when (a) the largest |component| beats the runner-up by more
+ * than the float error (face argmax, TRT.c:703-713) and (b) both scaled coordinates (u + 0.5) * dim lie farther from
+ * an integer than their float error (truncation, TRT.c:782-783; this also excludes the clamped edges u, v = +-0.5,
+ * where the reference's index runs into the next row / past the plane).  (dx,dy,dz): the ray's unit direction rounded
+ * to float (the reference normalises once more, TRT.c:702: a change in the last double bit, far below float).
+ * Float error of u, v: <= 8u each (|u|, |v| <= 0.5, quotient and products of rounded inputs); margin 16u * dim + 1e-4.
+ * Returns 1 and sets *face, *texel when certain, else 0. */
+TRT_HD int trt_cert_sky_texel(float dx, float dy, float dz, int dim, int *face, int *texel)
+{
+    const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+    /* candidates in the reference's order +x,-x,+y,-y,+z,-z; with clear margins ties cannot occur */
+    int best;
+    float m, second;
+    if (ax >= ay && ax >= az) { best = dx > 0.0f ? 0 : 1; m = ax; second = fmaxf(ay, az); }
+    else if (ay >= az) { best = dy > 0.0f ? 2 : 3; m = ay; second = fmaxf(ax, az); }
+    else { best = dz > 0.0f ? 4 : 5; m = az; second = fmaxf(ax, ay); }
+    if (!(m - second > 8.0f * TRT_CERT_U) || !(m > 0.5f) || !(m < 1.0001f)) return 0;
+    /* project onto the face (TRT.c:717-727): dir / major component, halved; the two face coordinates are dots with
+     * axes (best+2)%6 and (best+4)%6 — negative axes for the odd faces */
+    const float s = TRT_CERT_DIV(0.5f, m);
+    const float px = dx * s, py = dy * s, pz = dz * s;
+    float u, v;
+    if (best <= 1) { u = py; v = pz; }
+    else if (best <= 3) { u = pz; v = px; }
+    else { u = px; v = py; }
+    if (best & 1) { u = -u; v = -v; }
+    if (best & 1) u = -u;                                         /* :730 */
+    if (best <= 1) { const float t = u; u = v; v = -t; }          /* :735 */
+    else if (best <= 3) { const float t = u; u = -v; v = t; }     /* :742-755 */
+    else if (best == 4) { u = -u; v = -v; }                       /* :756 */
+    const float fu = (u + 0.5f) * (float)dim, fv = (v + 0.5f) * (float)dim;
+    const float margin = fmaf(16.0f * TRT_CERT_U, (float)dim, 1e-4f);
+    const float iu = floorf(fu), iv = floorf(fv);
+    if (!(fu - iu > margin) || !(iu + 1.0f - fu > margin) || !(fv - iv > margin) || !(iv + 1.0f - fv > margin)) return 0;
+    if (!(iu >= 0.0f) || !(iu < (float)dim) || !(iv >= 0.0f) || !(iv < (float)dim) || dim > 16384) return 0;
+    *face = best;
+    *texel = (int)iu + (int)iv * dim;
+    return 1;
+}
+
 #endif /* TRT_CERT_H */
