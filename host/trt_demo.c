@@ -5,6 +5,8 @@
  *
  *   build:  gcc -O2 -Iinclude host/trt_demo.c -Lterminalraytracer_b200 -ltrt_b200 -Wl,-rpath,'$ORIGIN/../terminalraytracer_b200' -lm -o host/trt_demo
  *   run  :  host/trt_demo [skybox-name [width height [frames]]]        (cwd must contain skybox/<name>/, TRT.c:403)
+ *           host/trt_demo --orbit N [skybox-name [width height]]       N frames of one full camera turn, streamed to
+ *                                                                      stdout through trt_render_orbit (BASELINE config 4)
  *
  * `TRT.c` = /root/reference/TerminalRayTracer.c
  */
@@ -21,8 +23,48 @@
 static volatile sig_atomic_t sigint_received = 0; /* TRT.c:1224 */
 static void sigint_handler(int sig) { (void)sig; sigint_received = 1; }
 
+/* sink of trt_render_orbit: the reference's single fwrite per frame (TRT.c:1171) */
+static int write_frame(const char *bytes, size_t n, int frame, void *user)
+{
+    (void)frame;
+    (void)user;
+    fwrite(bytes, sizeof(char), n, stdout);
+    return sigint_received;
+}
+
+static int orbit_mode(int argc, char **argv)
+{
+    const int n_frames = atoi(argv[2]);
+    const char *skybox_name = argc > 3 ? argv[3] : "milky_way";
+    const int width = argc > 5 ? atoi(argv[4]) : 1920, height = argc > 5 ? atoi(argv[5]) : 1080;
+    if (n_frames <= 0) return 1;
+    trt_init(0);
+    Skybox skybox;
+    trt_load_skybox(&skybox, (char *)skybox_name);
+    trt_upload_skybox(&skybox);
+    signal(SIGINT, sigint_handler);
+    Sphere spheres[TRT_DEMO_SPHERES];
+    DirectionalLight directional_light;
+    PointLight point_light;
+    Scene scene;
+    scene.skybox = skybox;
+    trt_demo_scene(&scene, spheres, &directional_light, &point_light, width, height);
+    double *times = (double *)malloc(sizeof(double) * (size_t)n_frames);
+    for (int k = 0; k < n_frames; k++) times[k] = k * (20.0 / n_frames);   /* one yaw turn at 0.05 rev/s, TRT.c:1332 */
+    struct timespec t0, t1;
+    timespec_get(&t0, TIME_UTC);
+    const int done = trt_render_orbit(&scene, width, height, times, n_frames, 0, 1, write_frame, NULL);
+    timespec_get(&t1, TIME_UTC);
+    fprintf(stderr, "%d frames of %dx%d in %.3f s\n", done, width, height, (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
+    free(times);
+    trt_free_skybox(&skybox);
+    trt_shutdown();
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
+    if (argc > 2 && argv[1][0] == '-' && argv[1][1] == '-' && argv[1][2] == 'o') return orbit_mode(argc, argv);
     const char *skybox_name = argc > 1 ? argv[1] : "milky_way"; /* TRT.c:1244 */
     const int width = argc > 3 ? atoi(argv[2]) : TRT_DEFAULT_WIDTH;
     const int height = argc > 3 ? atoi(argv[3]) : TRT_DEFAULT_HEIGHT;

@@ -79,6 +79,18 @@ void trt_buffered_draw_screen(const trt_Screen *screen);
  * `out` needs TRT_STREAM_BYTES(w,h) bytes; returns the byte count (0 if cap is too small). */
 size_t trt_render_ansi(const trt_Scene *scene, int width, int height, char *out, size_t cap);
 
+/* Streaming sink for camera animations — the reference's frame loop (TRT.c:1317-1367) with both hot calls on the GPU.
+ * For every frame k in {first, first+stride, ...} below n_frames the camera is posed as the reference poses it at
+ * wall-clock time times[k] (TRT.c:1327-1336, trt_orbit_camera), the frame is rendered and encoded on the device, and
+ * `sink` receives the finished terminal stream (the bytes buffered_draw_screen would fwrite, TRT.c:1171) in frame
+ * order.  Two device and two pinned host buffers: the device-to-host copy of frame k and the sink's work on it run
+ * while frame k+1 renders.  `bytes` is only valid during the call; a non-zero return from `sink` stops the loop.
+ * first/stride give the frame-index sharding of BASELINE config 4 (rank r of N: first = r, stride = N).
+ * Returns the number of frames delivered.  scene->camera is used as the un-posed camera (trt_demo_scene's). */
+typedef int (*trt_frame_sink)(const char *bytes, size_t n_bytes, int frame, void *user);
+int trt_render_orbit(const trt_Scene *scene, int width, int height, const double *times, int n_frames, int first, int stride,
+                     trt_frame_sink sink, void *user);
+
 /* ---- device-resident pieces (row bands; used by the multi-GPU plumbing and by bench.py) ------- */
 /* Upload scene (spheres, ground, lights, camera) for subsequent *_device calls. */
 int trt_set_scene(const trt_Scene *scene);

@@ -47,7 +47,8 @@ run("config1_3840x2160_uv_checker", S.SceneData(3840, 2160, sky_uv).set_time(3.7
 run("config2_7680x4320_milky_way", S.SceneData(7680, 4320, sky_mw).set_time(3.7), sky_mw, rows=(0, 2100, 4319))
 run("config3_stress1024_3840x2160", S.SceneData(3840, 2160, sky_uv, kind="stress", num_spheres=1024).set_time(3.7), sky_uv, frames=1, rows=())
 run("config3_stress1024_480x270_oracle_checked", S.SceneData(480, 270, sky_uv, kind="stress", num_spheres=1024).set_time(3.7), sky_uv, frames=2, rows=(100, 200))
-# config 4: 360-frame orbit at 1920x1080 on one GPU (frame-sharding across GPUs is exercised by tests / dist.py)
+# config 4: 360-frame orbit at 1920x1080 on one GPU: per-frame calls (trt_render_ansi) and the streaming sink
+# (trt_render_orbit: D2H of frame k overlaps the render of frame k+1); frame-sharding across GPUs is exercised by tests / dist.py
 sc = S.SceneData(1920, 1080, sky_mw)
 rd.upload_skybox(sky_mw)
 times = sharding.orbit_times(360)
@@ -58,8 +59,15 @@ for t in times:
     rd.render_ansi(sc)
     k1 += rd.last_ms()[0] + rd.last_ms()[1]
 wall = time.perf_counter() - t0
+devnull = open(os.devnull, "wb")
+t0 = time.perf_counter()
+n = rd.render_orbit(S.SceneData(1920, 1080, sky_mw), times, lambda f, v: devnull.write(v) and False)
+wall_stream = time.perf_counter() - t0
+assert n == 360
 results["config4_orbit_360x1920x1080_1gpu"] = {"frames": 360, "kernel_fps": 360 / (k1 * 1e-3), "e2e_fps": 360 / wall,
-                                               "Mrays_s_e2e": 360 * 10.0 * 1920 * 1080 / wall / 1e6}
+                                               "e2e_fps_streaming_sink_to_devnull": 360 / wall_stream,
+                                               "Mrays_s_e2e": 360 * 10.0 * 1920 * 1080 / wall / 1e6,
+                                               "Mrays_s_e2e_streaming": 360 * 10.0 * 1920 * 1080 / wall_stream / 1e6}
 print("config4", json.dumps(results["config4_orbit_360x1920x1080_1gpu"]))
 json.dump(results, open(out_path, "w"), indent=1)
 rd.close()

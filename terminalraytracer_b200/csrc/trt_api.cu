@@ -142,7 +142,7 @@ void set_material(DevMaterial &m, const trt_Material &src)
     m.reflectivity = src.reflectivity;
 }
 
-void upload_scene(const trt_Scene *scene)
+void upload_scene(const trt_Scene *scene, bool wait = true)
 {
     if (scene->num_directional_lights > TRT_MAX_LIGHTS || scene->num_point_lights > TRT_MAX_LIGHTS ||
         scene->num_directional_lights < 0 || scene->num_point_lights < 0 || scene->num_spheres < 0) {
@@ -310,7 +310,9 @@ void upload_scene(const trt_Scene *scene)
     g.cull_pairs.reserve(sizeof(CullPair) * pairs.size());
     CK(cudaMemcpyAsync(g.cull_pairs.p, pairs.data(), sizeof(CullPair) * pairs.size(), cudaMemcpyHostToDevice, g.stream));
     upload_scene_constants(s, pairs.data(), (int)pairs.size(), g.stream);
-    CK(cudaStreamSynchronize(g.stream));
+    // every source above is pageable host memory: the copies were staged before the calls returned, so the vectors may
+    // die now; the wait only keeps the historical "scene is resident when this returns" behaviour for callers that time
+    if (wait) CK(cudaStreamSynchronize(g.stream));
     g.have_scene = true;
 }
 
@@ -738,6 +740,69 @@ size_t trt_render_ansi(const trt_Scene *scene, int width, int height, char *out,
         g.last_encode_ms += k2;
     }
     return total;
+}
+
+int trt_render_orbit(const trt_Scene *scene, int width, int height, const double *times, int n_frames, int first, int stride,
+                     trt_frame_sink sink, void *user)
+{
+    require_init("trt_render_orbit");
+    if (width <= 0 || height <= 0 || n_frames <= 0 || stride <= 0 || first < 0 || !sink) return 0;
+    const size_t total = TRT_STREAM_BYTES(width, height);
+    g.quant.reserve(sizeof(uchar4) * (size_t)width * (size_t)height);
+    Buffer d_bytes[2];
+    PinnedBuffer h_bytes[2];
+    cudaEvent_t encoded[2], copied[2];
+    for (int b = 0; b < 2; b++) {
+        d_bytes[b].reserve(total + 16);
+        h_bytes[b].reserve(total);
+        CK(cudaEventCreateWithFlags(&encoded[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+    }
+    trt_Scene posed = *scene;
+    int launched = 0, delivered = 0, pending_frame[2] = {-1, -1};
+    bool stop = false;
+    auto deliver = [&](int b) {
+        // frame pending_frame[b] is on its way to h_bytes[b]: wait for the copy, hand it to the sink
+        CK(cudaEventSynchronize(copied[b]));
+        if (!stop) {
+            if (sink((const char *)h_bytes[b].p, total, pending_frame[b], user) != 0) stop = true;
+            delivered++;
+        }
+        pending_frame[b] = -1;
+    };
+    for (int k = first; k < n_frames && !stop; k += stride) {
+        const int b = launched & 1;
+        if (pending_frame[b] >= 0) deliver(b);          // frame k-2*stride: its buffers are reused now
+        if (stop) break;
+        posed.camera = scene->camera;
+        trt_orbit_camera(&posed.camera, times[k]);
+        upload_scene(&posed, false);
+        RenderParams p = make_params(width, height, 0, height, nullptr, (uchar4 *)g.quant.p, false);
+        launch_render(p, false, cull_mode(), g.num_sms, g.stream);
+        launch_stream_frame((char *)d_bytes[b].p, width, height, g.stream);
+        launch_encode_quant((const uchar4 *)g.quant.p, width, height, (char *)d_bytes[b].p, TRT_HOME_BYTES, g.stream);
+        CK(cudaEventRecord(encoded[b], g.stream));
+        CK(cudaStreamWaitEvent(g.copy_stream, encoded[b], 0));
+        CK(cudaMemcpyAsync(h_bytes[b].p, d_bytes[b].p, total, cudaMemcpyDeviceToHost, g.copy_stream));
+        CK(cudaEventRecord(copied[b], g.copy_stream));
+        // d_bytes[b] / h_bytes[b] are written again two frames from now, after deliver(b) has waited for this copy
+        pending_frame[b] = k;
+        launched++;
+        // while this frame renders, deliver the previous one
+        if (pending_frame[b ^ 1] >= 0) deliver(b ^ 1);
+    }
+    for (int i = 0; i < 2; i++) {
+        const int b = (launched + i) & 1;               // older buffer first
+        if (pending_frame[b] >= 0) deliver(b);
+    }
+    CK(cudaStreamSynchronize(g.stream));
+    for (int b = 0; b < 2; b++) {
+        d_bytes[b].release();
+        h_bytes[b].release();
+        cudaEventDestroy(encoded[b]);
+        cudaEventDestroy(copied[b]);
+    }
+    return delivered;
 }
 
 // ---- small helpers for plain-C callers -----------------------------------------------------------------

@@ -12,6 +12,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # TRT_B200_LIB selects an experiment build of the same library (scripts/ only); the product is libtrt_b200.so
 LIB_PATH = os.path.join(_HERE, os.environ.get("TRT_B200_LIB", "libtrt_b200.so"))
 
+# trt_frame_sink (include/trt_b200.h)
+FRAME_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
+
 # name -> (restype, argtypes); mirrors include/trt_b200.h one to one
 SIGNATURES = {
     "trt_init": (C.c_int, [C.c_int]),
@@ -26,6 +29,7 @@ SIGNATURES = {
     "trt_draw_screen": (C.c_size_t, [C.POINTER(abi.Screen), C.c_void_p]),
     "trt_buffered_draw_screen": (None, [C.POINTER(abi.Screen)]),
     "trt_render_ansi": (C.c_size_t, [C.POINTER(abi.Scene), C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "trt_render_orbit": (C.c_int, [C.POINTER(abi.Scene), C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "trt_set_scene": (C.c_int, [C.POINTER(abi.Scene)]),
     "trt_render_rows_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "trt_encode_rows_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),

@@ -64,6 +64,21 @@ class Renderer:
         assert got == n
         return np.ctypeslib.as_array((C.c_ubyte * n).from_address(buf))
 
+    def render_orbit(self, scene, times, sink, first=0, stride=1):
+        """trt_render_orbit: frames first, first+stride, ... of the camera path `times`, each handed to
+        sink(frame_index, uint8 array view — valid only during the call) in order while the next frame renders.
+        The scene's camera must be un-posed (as SceneData builds it); returns the number of frames delivered."""
+        n = len(times)
+        arr = (C.c_double * n)(*[float(t) for t in times])
+
+        def _cb(ptr, nbytes, frame, _user):
+            view = np.ctypeslib.as_array((C.c_ubyte * nbytes).from_address(ptr))
+            return 1 if sink(frame, view) else 0
+
+        cb = _lib.FRAME_SINK(_cb)
+        return self.L.trt_render_orbit(C.byref(scene.c), scene.width, scene.height, arr, n, int(first), int(stride),
+                                       C.cast(cb, C.c_void_p), None)
+
     # ---- device-resident band API ---------------------------------------------------------------
     def set_scene(self, scene):
         self.L.trt_set_scene(C.byref(scene.c))

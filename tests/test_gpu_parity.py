@@ -369,6 +369,35 @@ def test_gpu_pipeline_single_rank(renderer, orc):
         renderer.use_stream(None)
 
 
+def test_gpu_orbit_sink_streams_frames_in_order(renderer, orc):
+    """trt_render_orbit: frames of a camera path delivered in order (D2H of frame k overlaps the render of frame k+1),
+    every one equal to the oracle's stream for that pose; frame-index sharding; early stop by the sink"""
+    w, h = 96, 54
+    sky = S.synthetic_cubemap("uv_gradient", 64)
+    renderer.upload_skybox(sky)
+    times = sharding.orbit_times(7)
+    want = []
+    for t in times:
+        sc = S.SceneData(w, h, sky).set_time(t)
+        want.append(U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc)))
+    got = {}
+
+    def sink(frame, view):
+        got[frame] = np.array(view)     # the view dies with the call
+        return False
+
+    assert renderer.render_orbit(S.SceneData(w, h, sky), times, sink) == len(times)
+    assert list(got) == list(range(len(times)))
+    for k in range(len(times)):
+        assert np.array_equal(got[k], want[k]), k
+    got.clear()
+    assert renderer.render_orbit(S.SceneData(w, h, sky), times, sink, first=1, stride=3) == 2
+    assert list(got) == [1, 4] and np.array_equal(got[4], want[4])
+    got.clear()
+    assert renderer.render_orbit(S.SceneData(w, h, sky), times, lambda f, v: got.setdefault(f, True) and f >= 2) == 3
+    assert list(got) == [0, 1, 2]
+
+
 # ---- full-size configs: size-independent properties + sampled rows against the oracle -----------------------
 
 @pytest.mark.parametrize("cfg", [("uv_checker", 3840, 2160, 3.7), ("milky_way", 7680, 4320, 3.7)], ids=lambda c: f"{c[1]}x{c[2]}")
