@@ -43,7 +43,7 @@ enum {
     ST_DIR, ST_DIR_OPEN, ST_DIR_BLOCKED, ST_DIR_UNKNOWN,
     ST_POINT, ST_POINT_OPEN, ST_POINT_BLOCKED, ST_POINT_UNKNOWN,
     ST_SHADOW_EXACT_TESTS,
-    ST_SKY, ST_SKY_CERTIFIED,
+    ST_SKY, ST_SKY_CERTIFIED, ST_CLUSTER_TESTS, ST_CLUSTERS_MISSED, ST_SUBCLUSTER_TESTS, ST_SUBCLUSTERS_MISSED,
     ST_TILES, ST_TILES_PATCH, ST_PATCH_DIR_CANDIDATES, ST_PATCH_POINT_CANDIDATES, ST_PATCH_BOUNCE_CANDIDATES, ST_PATCH_RECORDS,
     ST_COUNT
 };
@@ -58,6 +58,7 @@ typedef struct {
     float gp[3], gn[3];
     long long *st;
     long long bad;
+    unsigned char *scratch; int num_clusters; int *order; float *cluster4; float *sub4; /* sub4: balls of 8 inside each cluster */ /* Morton order of the spheres and bounding balls of 32 (many-sphere scenes) */
     const unsigned char *cand; /* patch certificate: spheres still possible for the query at hand; NULL = all */
 } ctx_t;
 
@@ -75,6 +76,30 @@ static int exact_point_open(const trt_Scene *scene, const trt_Ray *ray, v3 P, do
     return what == TRT_NONE || light_d2 < dot3(to_blocker, to_blocker);
 }
 
+/* members of a cluster whose bounding ball the ray certainly misses are certain misses: flags per sphere (reference index) */
+static void cluster_flags(const ctx_t *c, const trt_cert_ray *r, float far_limit, unsigned char *missed)
+{
+    const int n = c->scene->num_spheres;
+    memset(missed, 0, (size_t)(n > 0 ? n : 1));
+    if (!c->num_clusters || !r->usable) return;
+    for (int k = 0; k < c->num_clusters; k++)
+        if (trt_cert_cluster_miss(r, c->cluster4[4 * k], c->cluster4[4 * k + 1], c->cluster4[4 * k + 2], c->cluster4[4 * k + 3], far_limit)) {
+            c->st[ST_CLUSTERS_MISSED]++;
+            for (int j = 32 * k; j < 32 * k + 32 && j < n; j++) missed[c->order[j]] = 1;
+        } else {
+            /* second level: four balls of 8 */
+            for (int q = 0; q < 4 && 32 * k + 8 * q < n; q++) {
+                const float *b = c->sub4 + 4 * (4 * k + q);
+                c->st[ST_SUBCLUSTER_TESTS]++;
+                if (trt_cert_cluster_miss(r, b[0], b[1], b[2], b[3], far_limit)) {
+                    c->st[ST_SUBCLUSTERS_MISSED]++;
+                    for (int j = 32 * k + 8 * q; j < 32 * k + 8 * q + 8 && j < n; j++) missed[c->order[j]] = 1;
+                }
+            }
+        }
+    c->st[ST_CLUSTER_TESTS] += c->num_clusters;
+}
+
 static void check_bounce(ctx_t *c, const trt_Ray *ray)
 {
     const trt_Scene *s = c->scene;
@@ -82,10 +107,12 @@ static void check_bounce(ctx_t *c, const trt_Ray *ray)
     const float S = trt_cert_set_origin(&r, ray->origin.x, ray->origin.y, ray->origin.z) + c->centre_l1;
     trt_cert_set_unit_dir(&r, ray->direction.x, ray->direction.y, ray->direction.z, S);
     c->st[ST_BOUNCE]++;
+    unsigned char *ball_missed = c->scratch;
+    cluster_flags(c, &r, INFINITY, ball_missed);
     for (int i = 0; i < s->num_spheres; i++) {
         trt_Point p;
         const int hit = orc_hit_sphere(ray, &s->spheres[i], &p, NULL);
-        const int miss = (c->cand && !c->cand[i]) ||
+        const int miss = (c->cand && !c->cand[i]) || ball_missed[i] ||
                          (r.usable && trt_cert_sphere_miss(&r, c->cull[4 * i], c->cull[4 * i + 1], c->cull[4 * i + 2], c->cull[4 * i + 3]));
         if (!miss) c->st[ST_BOUNCE_SURVIVORS]++;
         if (hit) c->st[ST_BOUNCE_EXACT_HITS]++;
@@ -134,8 +161,9 @@ static int cert_dir(ctx_t *c, v3 at, v3 L, int *certified, unsigned char *surviv
     const float S = trt_cert_set_origin(&r, at.x, at.y, at.z) + c->centre_l1;
     trt_cert_set_unit_dir(&r, L.x, L.y, L.z, S);
     int any_blocks = 0, survivors = 0;
+    cluster_flags(c, &r, INFINITY, c->scratch);
     for (int i = 0; i < s->num_spheres; i++) {
-        const int k = (c->cand && !c->cand[i]) ? TRT_CERT_MISS :
+        const int k = ((c->cand && !c->cand[i]) || c->scratch[i]) ? TRT_CERT_MISS :
                       (r.usable ? trt_cert_sphere(&r, c->cull[4 * i], c->cull[4 * i + 1], c->cull[4 * i + 2], c->cull[4 * i + 3], INFINITY, INFINITY) : 0);
         any_blocks |= (k & TRT_CERT_BLOCKS) != 0;
         survivor[i] = !(k & TRT_CERT_MISS);
@@ -171,8 +199,9 @@ static int cert_point(ctx_t *c, v3 at, const trt_PointLight *pl, int *certified,
     const float guard = fmaf(2.0f, r.slack_t, 1e-5f);
     const float near_limit = dist - guard, far_limit = dist + guard;
     int any_blocks = 0, survivors = 0;
+    cluster_flags(c, &r, far_limit, c->scratch);
     for (int i = 0; i < s->num_spheres; i++) {
-        const int k = (c->cand && !c->cand[i]) ? TRT_CERT_MISS :
+        const int k = ((c->cand && !c->cand[i]) || c->scratch[i]) ? TRT_CERT_MISS :
                       (r.usable ? trt_cert_sphere(&r, c->cull[4 * i], c->cull[4 * i + 1], c->cull[4 * i + 2], c->cull[4 * i + 3], near_limit, far_limit) : 0);
         any_blocks |= (k & TRT_CERT_BLOCKS) != 0;
         survivor[i] = !(k & TRT_CERT_MISS);
@@ -220,6 +249,25 @@ long long cert_check_rows(const trt_Scene *scene, int W, int H, int row0, int ro
         if (l1 > centre_l1) centre_l1 = l1;
     }
     c.centre_l1 = trt_cert_round_up(centre_l1 * (1.0 + 1.0 / 1048576.0));
+    c.scratch = (unsigned char *)malloc((size_t)(n > 0 ? n : 1));
+    c.order = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    c.num_clusters = n > 64 ? (n + 31) / 32 : 0;          /* TRT_CLUSTER_MIN_SPHERES of the library */
+    c.cluster4 = (float *)malloc(sizeof(float) * 4 * (size_t)(c.num_clusters > 0 ? c.num_clusters : 1));
+    c.sub4 = (float *)malloc(sizeof(float) * 16 * (size_t)(c.num_clusters > 0 ? c.num_clusters : 1));
+    if (c.num_clusters) {
+        trt_cert_morton_order(c.cull, n, c.order);
+        float *sorted = (float *)malloc(sizeof(float) * 4 * (size_t)n);
+        for (int j = 0; j < n; j++) memcpy(sorted + 4 * j, c.cull + 4 * c.order[j], sizeof(float) * 4);
+        for (int k = 0; k < c.num_clusters; k++) {
+            trt_cert_cluster_bound(sorted + 4 * 32 * k, n - 32 * k < 32 ? n - 32 * k : 32, c.cluster4 + 4 * k);
+            for (int q = 0; q < 4; q++) {
+                const int j0 = 32 * k + 8 * q, cnt = n - j0 < 8 ? n - j0 : 8;
+                if (cnt > 0) trt_cert_cluster_bound(sorted + 4 * j0, cnt, c.sub4 + 4 * (4 * k + q));
+                else memset(c.sub4 + 4 * (4 * k + q), 0, sizeof(float) * 4);
+            }
+        }
+        free(sorted);
+    }
     c.gp[0] = (float)scene->ground.point.x; c.gp[1] = (float)scene->ground.point.y; c.gp[2] = (float)scene->ground.point.z;
     c.gn[0] = (float)scene->ground.normal.x; c.gn[1] = (float)scene->ground.normal.y; c.gn[2] = (float)scene->ground.normal.z;
 
@@ -410,6 +458,10 @@ long long cert_check_rows(const trt_Scene *scene, int W, int H, int row0, int ro
     free(tile_miss);
     free(patch_cand);
     free(c.cull);
+    free(c.scratch);
+    free(c.order);
+    free(c.cluster4);
+    free(c.sub4);
     return c.bad;
 }
 

@@ -74,7 +74,7 @@ struct Context {
     bool have_scene = false;
     bool cull_allowed = true;   // trt_set_cull(); the FP32 miss test can be switched off for A/B runs
     bool cull = true;           // cull_allowed && this scene's magnitudes are inside the bound's range
-    Buffer sphere_geom, sphere_cull, sphere_mat, sphere_prim, cull_pairs;
+    Buffer sphere_geom, sphere_cull, sphere_mat, sphere_prim, cull_pairs, sphere_orig, sphere_pos, clusters, subballs;
     // skybox
     Buffer sky;
     int sky_dim = -1, sky_face_stride = 0;
@@ -285,6 +285,57 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
         cull[i] = make_float4((float)sp.center.x, (float)sp.center.y, (float)sp.center.z, trt_cert_pad_radius(sp.radius));
         (void)r;
     }
+    // Many-sphere scenes: the device sees the spheres in Morton order, 32 consecutive ones share a bounding ball
+    // (trt_cert_cluster_miss).  `orig` keeps the reference's index of every sorted sphere for its tie-breaking rule
+    // (TRT.c:810, strict <: the lowest index wins), `pos` is the inverse (the all-FP64 query scans in the reference's order).
+    std::vector<int> orig((size_t)(n > 0 ? n : 1)), pos((size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) orig[i] = pos[i] = i;
+    const int num_clusters = (n + 31) / 32;
+    std::vector<float4> clusters((size_t)(num_clusters > 0 ? num_clusters : 1), make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<CullPair> subballs((size_t)(num_clusters > 0 ? 2 * num_clusters : 2));
+    memset(subballs.data(), 0, sizeof(CullPair) * subballs.size());
+    s.clustered = n > TRT_CLUSTER_MIN_SPHERES ? 1 : 0;
+    if (s.clustered) {
+        trt_cert_morton_order(reinterpret_cast<const float *>(cull.data()), n, orig.data());
+        std::vector<double4> geom2(geom), prim2(prim);
+        std::vector<DevMaterial> mats2(mats);
+        std::vector<float4> cull2(cull);
+        for (int j = 0; j < n; j++) {
+            const int i = orig[j];
+            pos[i] = j;
+            geom[j] = geom2[i];
+            prim[j] = prim2[i];
+            mats[j] = mats2[i];
+            cull[j] = cull2[i];
+        }
+        for (int c = 0; c < num_clusters; c++) {
+            float b[4];
+            const int count = n - 32 * c < 32 ? n - 32 * c : 32;
+            trt_cert_cluster_bound(reinterpret_cast<const float *>(cull.data() + 32 * c), count, b);
+            clusters[c] = make_float4(b[0], b[1], b[2], b[3]);
+            float q[4][4];
+            for (int k = 0; k < 4; k++) {
+                const int j0 = 32 * c + 8 * k, cnt = n - j0 < 8 ? n - j0 : 8;
+                q[k][0] = q[k][1] = q[k][2] = q[k][3] = 0.f;
+                if (cnt > 0) trt_cert_cluster_bound(reinterpret_cast<const float *>(cull.data() + j0), cnt, q[k]);
+            }
+            for (int half = 0; half < 2; half++) {
+                CullPair &sp = subballs[(size_t)(2 * c + half)];
+                sp.cx = make_float2(q[2 * half][0], q[2 * half + 1][0]);
+                sp.cy = make_float2(q[2 * half][1], q[2 * half + 1][1]);
+                sp.cz = make_float2(q[2 * half][2], q[2 * half + 1][2]);
+                sp.r = make_float2(q[2 * half][3], q[2 * half + 1][3]);
+            }
+        }
+    }
+    g.sphere_orig.reserve(sizeof(int) * orig.size());
+    g.sphere_pos.reserve(sizeof(int) * pos.size());
+    g.clusters.reserve(sizeof(float4) * clusters.size());
+    g.subballs.reserve(sizeof(CullPair) * subballs.size());
+    CK(cudaMemcpyAsync(g.subballs.p, subballs.data(), sizeof(CullPair) * subballs.size(), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.sphere_orig.p, orig.data(), sizeof(int) * orig.size(), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.sphere_pos.p, pos.data(), sizeof(int) * pos.size(), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.clusters.p, clusters.data(), sizeof(float4) * clusters.size(), cudaMemcpyHostToDevice, g.stream));
     g.cull = g.cull_allowed && in_range && ground_in_range;
     s.filter_enabled = g.cull ? 1 : 0;
     s.filter_centre_l1 = float_round_up(centre_l1 * (1.0 + 1.0 / 1048576.0));
@@ -309,15 +360,15 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
     }
     g.cull_pairs.reserve(sizeof(CullPair) * pairs.size());
     CK(cudaMemcpyAsync(g.cull_pairs.p, pairs.data(), sizeof(CullPair) * pairs.size(), cudaMemcpyHostToDevice, g.stream));
-    upload_scene_constants(s, pairs.data(), (int)pairs.size(), g.stream);
+    upload_scene_constants(s, pairs.data(), s.clustered ? 0 : (int)pairs.size(), g.stream);   // Morton-sorted scenes read the global copy
     // every source above is pageable host memory: the copies were staged before the calls returned, so the vectors may
     // die now; the wait only keeps the historical "scene is resident when this returns" behaviour for callers that time
     if (wait) CK(cudaStreamSynchronize(g.stream));
     g.have_scene = true;
 }
 
-// 0: all FP64; 1: FP32 cull records in __constant__; 2: cull records in global memory (big scenes)
-int cull_mode() { return !g.cull ? 0 : (g.scene.filter_in_const ? 1 : 2); }
+// 0: all FP64; 1: small scene, certificate records in __constant__; 2: Morton-sorted scene with cluster balls, records in global memory
+int cull_mode() { return !g.cull ? 0 : (g.scene.clustered ? 2 : 1); }
 
 RenderParams make_params(int width, int height, int row0, int row1, double *d_pixels, uchar4 *d_quant, bool count)
 {
@@ -342,6 +393,10 @@ RenderParams make_params(int width, int height, int row0, int row1, double *d_pi
     p.sphere_cull = (const float4 *)g.sphere_cull.p;
     p.sphere_prim = (const double4 *)g.sphere_prim.p;
     p.cull_pairs = (const CullPair *)g.cull_pairs.p;
+    p.sphere_orig = (const int *)g.sphere_orig.p;
+    p.sphere_pos = (const int *)g.sphere_pos.p;
+    p.clusters = (const float4 *)g.clusters.p;
+    p.subballs = (const CullPair *)g.subballs.p;
     p.sphere_mat = (const DevMaterial *)g.sphere_mat.p;
     p.byte_to_unit = (const double *)g.byte_to_unit.p;
     p.sky = (const uchar4 *)g.sky.p;
@@ -405,6 +460,10 @@ void trt_shutdown(void)
     g.sphere_mat.release();
     g.sphere_prim.release();
     g.cull_pairs.release();
+    g.sphere_orig.release();
+    g.sphere_pos.release();
+    g.clusters.release();
+    g.subballs.release();
     g.sky.release();
     g.tile_counter.release();
     g.scratch.release();
@@ -615,6 +674,10 @@ int trt_probe_skybox(const double *dirs, int n, int *out)
         g.sphere_cull.reserve(sizeof(float4));
         g.sphere_prim.reserve(sizeof(double4));
         g.cull_pairs.reserve(sizeof(CullPair));
+        g.sphere_orig.reserve(sizeof(int));
+        g.sphere_pos.reserve(sizeof(int));
+        g.clusters.reserve(sizeof(float4));
+        g.subballs.reserve(sizeof(CullPair) * 2);
         g.sphere_mat.reserve(sizeof(DevMaterial));
         g.have_scene = true;
     } else {

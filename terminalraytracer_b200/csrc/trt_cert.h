@@ -406,4 +406,80 @@ TRT_HD int trt_cert_sky_texel(float dx, float dy, float dz, int dim, int *face, 
     return 1;
 }
 
+/* ---- clusters: many-sphere scenes ---------------------------------------------------------------------------------
+ * Spheres are sorted along a Morton curve (host, once per scene) and every 32 consecutive ones get a bounding ball
+ * (C, R): |c_i - C| + r_pad_i <= R for every member.  A ray that certainly passes the ball, or has the whole ball
+ * behind its origin, or (point-light shadow rays) has the whole ball beyond the light, certainly misses every member
+ * in the sense of trt_cert_sphere2's MISS: with tc = (C - o).d and h = distance of C from the ray's line, member i has
+ * h_i >= h - (R - r_pad_i), tc_i <= tc + (R - r_pad_i) and tc_i - r_pad_i >= tc - R. */
+TRT_HD int trt_cert_cluster_miss(const trt_cert_ray *r, float cx, float cy, float cz, float R, float far_limit)
+{
+    const float ocx = cx - r->ox, ocy = cy - r->oy, ocz = cz - r->oz;
+    const float tc = fmaf(ocz, r->dz, fmaf(ocy, r->dy, ocx * r->dx));
+    const float wx = fmaf(-tc, r->dx, ocx), wy = fmaf(-tc, r->dy, ocy), wz = fmaf(-tc, r->dz, ocz);
+    const float h2 = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+    const float outer = R + r->slack_t;
+    return (h2 > outer * outer) || (tc + R < -r->slack_t) || (tc - R > far_limit);
+}
+
+#include <stdlib.h>
+/* host: bounding ball of `count` certificate records (4 floats each: centre, r_pad), out = (C, R rounded up) */
+static inline void trt_cert_cluster_bound(const float *cull4, int count, float out[4])
+{
+    double c[3] = {0.0, 0.0, 0.0}, R = 0.0;
+    for (int i = 0; i < count; i++)
+        for (int k = 0; k < 3; k++) c[k] += cull4[4 * i + k];
+    for (int k = 0; k < 3; k++) out[k] = (float)(c[k] / (count > 0 ? count : 1));
+    for (int i = 0; i < count; i++) {
+        const double dx = (double)cull4[4 * i] - out[0], dy = (double)cull4[4 * i + 1] - out[1], dz = (double)cull4[4 * i + 2] - out[2];
+        const double reach = sqrt(dx * dx + dy * dy + dz * dz) * (1.0 + 1e-6) + cull4[4 * i + 3];
+        if (reach > R) R = reach;
+    }
+    out[3] = trt_cert_round_up(R * (1.0 + 1e-6));
+}
+
+/* host: order[j] = index of the j-th sphere along a 30-bit Morton curve over the bounding box of the centres */
+typedef struct { unsigned int key; int index; } trt_cert_morton_item;
+static inline int trt_cert_morton_cmp(const void *a, const void *b)
+{
+    const trt_cert_morton_item *x = (const trt_cert_morton_item *)a, *y = (const trt_cert_morton_item *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->index < y->index ? -1 : (x->index > y->index ? 1 : 0);
+}
+static inline unsigned int trt_cert_spread10(unsigned int v)
+{
+    v &= 1023u;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+static inline void trt_cert_morton_order(const float *cull4, int n, int *order)
+{
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) {
+            const float v = cull4[4 * i + k];
+            if (v < lo[k]) lo[k] = v;
+            if (v > hi[k]) hi[k] = v;
+        }
+    trt_cert_morton_item *items = (trt_cert_morton_item *)malloc(sizeof(trt_cert_morton_item) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) {
+        unsigned int q[3];
+        for (int k = 0; k < 3; k++) {
+            const float span = hi[k] - lo[k];
+            float f = span > 0.0f ? (cull4[4 * i + k] - lo[k]) / span : 0.0f;
+            if (!(f >= 0.0f)) f = 0.0f;
+            if (f > 1.0f) f = 1.0f;
+            q[k] = (unsigned int)(f * 1023.0f);
+        }
+        items[i].key = trt_cert_spread10(q[0]) | (trt_cert_spread10(q[1]) << 1) | (trt_cert_spread10(q[2]) << 2);
+        items[i].index = i;
+    }
+    qsort(items, (size_t)n, sizeof(trt_cert_morton_item), trt_cert_morton_cmp);
+    for (int i = 0; i < n; i++) order[i] = items[i].index;
+    free(items);
+}
+
 #endif /* TRT_CERT_H */

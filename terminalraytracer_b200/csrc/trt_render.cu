@@ -188,9 +188,12 @@ __device__ __forceinline__ d3 sky_colour(const RenderParams &P, const double *s_
 
 // ray_intersects_sphere (TRT.c:638-672) with oc = origin - centre and c = oc.oc - r*r given, plus the
 // closest-so-far update of trace_ray (TRT.c:807-827).  Keeps the hit PARAMETER; the point is o + t d.
-template <bool COUNT>
-__device__ __forceinline__ void sphere_exact_oc(const d3 &oc, double c, int i, const d3 &o, const d3 &d, double two_a, double four_a,
-                                                double &closest, int &obj, int &index, double &t_hit, const Tally<COUNT> &tally)
+// Spheres may be visited in any order (Morton-sorted scenes, per-lane survivor walks): `oi` is the sphere's index in
+// the reference's array, and a hit replaces the closest one if it is closer or equally close with a lower reference
+// index — exactly what the reference's index-ordered scan with strict < keeps (TRT.c:810).
+template <bool COUNT, bool ANY_ORDER = true>
+__device__ __forceinline__ void sphere_exact_oc(const d3 &oc, double c, int i, int oi, const d3 &o, const d3 &d, double two_a, double four_a,
+                                                double &closest, int &obj, int &index, int &best_oi, double &t_hit, const Tally<COUNT> &tally)
 {
     const double b = 2.0 * dot(oc, d);
     const double disc = b * b - four_a * c;  // (4.0*a)*c, scaling by 4 is exact
@@ -202,25 +205,30 @@ __device__ __forceinline__ void sphere_exact_oc(const d3 &oc, double c, int i, c
             const d3 p = mk3(o.x + t0 * d.x, o.y + t0 * d.y, o.z + t0 * d.z);
             const d3 back = o - p;
             const double d2 = dot(back, back);
-            if (d2 < closest) {
+            if (d2 < closest || (ANY_ORDER && d2 == closest && obj == 1 && oi < best_oi)) {
                 tally.add(CTR_SPHERE_CLOSEST);
                 closest = d2;
                 obj = 1;
                 index = i;
+                best_oi = oi;
                 t_hit = t0;
             }
         }
     }
 }
 
-template <bool COUNT>
-__device__ __forceinline__ void sphere_exact(const double4 g, int i, const d3 &o, const d3 &d, double two_a, double four_a,
-                                             double &closest, int &obj, int &index, double &t_hit, const Tally<COUNT> &tally)
+template <bool COUNT, bool ANY_ORDER = true>
+__device__ __forceinline__ void sphere_exact(const double4 g, int i, int oi, const d3 &o, const d3 &d, double two_a, double four_a,
+                                             double &closest, int &obj, int &index, int &best_oi, double &t_hit, const Tally<COUNT> &tally)
 {
     const d3 oc = mk3(o.x - g.x, o.y - g.y, o.z - g.z);
     const double c = dot(oc, oc) - g.w;      // g.w = radius*radius, evaluated on the host in double
-    sphere_exact_oc<COUNT>(oc, c, i, o, d, two_a, four_a, closest, obj, index, t_hit, tally);
+    sphere_exact_oc<COUNT, ANY_ORDER>(oc, c, i, oi, o, d, two_a, four_a, closest, obj, index, best_oi, t_hit, tally);
 }
+
+// reference index of the sphere at position i (identity unless the scene is Morton-sorted)
+template <bool CLUSTERED>
+__device__ __forceinline__ int reference_index(const RenderParams &P, int i) { return CLUSTERED ? __ldg(&P.sphere_orig[i]) : i; }
 
 // ray_intersects_plane (TRT.c:677-695) + the ground branch of trace_ray (TRT.c:831-853); `num` is
 // dot(ground point - origin, normal) (TRT.c:684-685), passed in because several callers share it
@@ -270,8 +278,11 @@ __device__ __noinline__ void query_reference(const RenderParams &P, const d3 &o,
     const double two_a = 2.0 * a, four_a = 4.0 * a;
     const int n = c_scene.num_spheres;
     tally.add(CTR_SPHERE_TESTS, (unsigned long long)n);
-    for (int i = 0; i < n; i++)
-        sphere_exact<COUNT>(ldg4(P.sphere_geom, i), i, o, d, two_a, four_a, closest, obj, index, t_hit, tally);
+    int best_oi = -1;
+    for (int oi = 0; oi < n; oi++) {
+        const int i = c_scene.clustered ? __ldg(&P.sphere_pos[oi]) : oi;   // where reference sphere oi lives
+        sphere_exact<COUNT>(ldg4(P.sphere_geom, i), i, oi, o, d, two_a, four_a, closest, obj, index, best_oi, t_hit, tally);
+    }
     tally.add(CTR_PLANE_TESTS);
     plane_exact_num<COUNT>(plane_numerator(o), o, d, closest, obj, t_hit, tally);
 }
@@ -296,6 +307,8 @@ struct Query {
     int mode;
 };
 
+// CONST_RECORDS: small scene (at most TRT_CLUSTER_MIN_SPHERES spheres): records in __constant__, reference order, no
+// clusters.  Otherwise the scene is Morton-sorted with bounding balls and its records are read from global memory.
 template <bool CONST_RECORDS>
 __device__ __forceinline__ bool query_certified(const RenderParams &P, const Query &qy, const d3 &o, double num_g, bool use_patch,
                                                 unsigned int patch_mask, int &obj, int &index, double &t_hit, unsigned int *exact_tests)
@@ -319,12 +332,47 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const Que
     const float slack = qy.rf.slack_t;
     const float2 slack2 = make_float2(slack, slack), nslack2 = make_float2(-slack, -slack);
     const float2 neg1 = make_float2(-1.0f, -1.0f), shrink2 = make_float2(0.99999237060546875f, 0.99999237060546875f);
+    int best_oi = -1;
+    constexpr bool clustered = !CONST_RECORDS;
     for (int base = 0; base < n; base += 32) {
         const int cnt = min(32, n - base);
+        // many-sphere scenes: the chunk is a cluster of the Morton order with a bounding ball, and four balls of 8 inside
+        // it (trt_cert_cluster_miss): skip what no lane's ray can reach, and let every lane drop what its own ray cannot
+        bool ball_missed = false;
+        unsigned int reachable = 0xffffffffu;      // warp-uniform: spheres of this chunk some lane may still hit
+        unsigned int own = 0xffffffffu;            // this lane's
+        if (clustered) {
+            const float4 ball = __ldg(&P.clusters[base >> 5]);
+            ball_missed = usable && trt_cert_cluster_miss(&qy.rf, ball.x, ball.y, ball.z, ball.w, qy.far_limit);
+            const unsigned int lanes = __activemask();
+            if (__all_sync(lanes, ball_missed)) continue;
+            reachable = 0u;
+            own = 0u;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const CullPair g = ldg_pair(P.subballs, 2 * (base >> 5) + half);
+                const float2 ocx = __fadd2_rn(g.cx, rp.nox), ocy = __fadd2_rn(g.cy, rp.noy), ocz = __fadd2_rn(g.cz, rp.noz);
+                const float2 tc = __ffma2_rn(ocz, rp.dz, __ffma2_rn(ocy, rp.dy, __fmul2_rn(ocx, rp.dx)));
+                const float2 ntc = __fmul2_rn(tc, neg1);
+                const float2 wx = __ffma2_rn(ntc, rp.dx, ocx), wy = __ffma2_rn(ntc, rp.dy, ocy), wz = __ffma2_rn(ntc, rp.dz, ocz);
+                const float2 h2 = __ffma2_rn(wz, wz, __ffma2_rn(wy, wy, __fmul2_rn(wx, wx)));
+                const float2 outer = __fadd2_rn(g.r, slack2);
+                const float2 outer_sq = __fmul2_rn(outer, outer);
+                const float2 front = __ffma2_rn(g.r, neg1, tc), back = __fadd2_rn(g.r, tc);
+                const bool m0 = usable && !ball_missed && ((h2.x > outer_sq.x) || (back.x < -slack) || (front.x > qy.far_limit));
+                const bool m1 = usable && !ball_missed && ((h2.y > outer_sq.y) || (back.y < -slack) || (front.y > qy.far_limit));
+                const bool keep0 = !m0 && !ball_missed, keep1 = !m1 && !ball_missed;
+                if (keep0) own |= 0xffu << (16 * half);
+                if (keep1) own |= 0xff00u << (16 * half);
+                if (__any_sync(lanes, keep0)) reachable |= 0xffu << (16 * half);
+                if (__any_sync(lanes, keep1)) reachable |= 0xff00u << (16 * half);
+            }
+            if (reachable == 0u) continue;
+        }
         // pass 1 (float, warp-uniform record addresses): classify the candidate spheres of this chunk — all of them,
         // or, for the first-generation hits of a patch tile, the few the patch certificate left (use_patch, n <= 32)
         const unsigned int valid = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
-        const unsigned int candidates = use_patch ? (patch_mask & valid) : valid;
+        const unsigned int candidates = use_patch ? (patch_mask & valid) : (valid & reachable);
         unsigned int survivors = 0;
         // two spheres per trip: the arithmetic of trt_cert_sphere2 (same operations, same rounding) on float pairs
 #pragma unroll 1
@@ -355,6 +403,7 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const Que
         }
         survivors &= candidates;
         if (!usable) survivors = candidates;
+        survivors &= own;
         if (shadow && usable && blocked) survivors = 0;
         // many-sphere scenes: once every lane's light is proven blocked the remaining chunks cannot change anything
         if (shadow && n > 32 && __all_sync(__activemask(), usable && blocked)) break;
@@ -363,7 +412,8 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const Que
         while (survivors) {
             const int j = __ffs(survivors) - 1;
             survivors &= survivors - 1;
-            sphere_exact<false>(ldg4(P.sphere_geom, base + j), base + j, o, d, two_a, four_a, closest, obj, index, t_hit, no_tally);
+            sphere_exact<false, clustered>(ldg4(P.sphere_geom, base + j), base + j, reference_index<clustered>(P, base + j), o, d, two_a, four_a, closest, obj, index,
+                                best_oi, t_hit, no_tally);
         }
     }
     blocked = blocked && usable && shadow;
@@ -574,6 +624,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                         unsigned int exact = 0;
                         const Tally<false> no_tally{nullptr};
                         double closest = INFINITY;
+                        int best_oi = -1;
                         const double a = dot(d, d);
                         const double two_a = 2.0 * a, four_a = 4.0 * a;
                         for (int wd = 0; wd < mask_words; wd++) {
@@ -583,7 +634,8 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                                 const int i = wd * 32 + __ffs(m) - 1;
                                 m &= m - 1;
                                 const double4 g = ldg4(P.sphere_prim, i);
-                                sphere_exact_oc<false>(mk3(g.x, g.y, g.z), g.w, i, eye, d, two_a, four_a, closest, obj2, index2, t2, no_tally);
+                                sphere_exact_oc<false, CULL == 2>(mk3(g.x, g.y, g.z), g.w, i, reference_index<CULL == 2>(P, i), eye, d, two_a, four_a, closest, obj2, index2, best_oi,
+                                                       t2, no_tally);
                             }
                         }
                         if (!tile_ground_miss) plane_exact_num<false>(c_scene.prim_num, eye, d, closest, obj2, t2, no_tally);
@@ -918,7 +970,7 @@ __global__ void k_probe_trace(const RenderParams P, const double *__restrict__ r
     if (c_scene.filter_enabled) {
         Query qy;
         setup_closest_query(qy, o, d, fabsf((float)o.x) + fabsf((float)o.y) + fabsf((float)o.z) + c_scene.filter_centre_l1);
-        if (c_scene.filter_in_const) query_certified<true>(P, qy, o, plane_numerator(o), false, 0u, obj, index, t_hit, nullptr);
+        if (!c_scene.clustered) query_certified<true>(P, qy, o, plane_numerator(o), false, 0u, obj, index, t_hit, nullptr);
         else query_certified<false>(P, qy, o, plane_numerator(o), false, 0u, obj, index, t_hit, nullptr);
     } else {
         query_reference<false>(P, o, d, obj, index, t_hit, tally);
