@@ -82,7 +82,25 @@ struct Context {
     Buffer tile_counter, counters, byte_to_unit, scratch;
     Buffer pixels, quant, bytes;
     PinnedBuffer stage;
+    // pinned staging for scene uploads: copies from pageable memory make the runtime wait for the stream first, which
+    // would serialise the frames of trt_render_orbit; two arenas so that a frame's upload never overwrites the previous one's
+    PinnedBuffer arena[2];
+    size_t arena_used = 0;
+    int arena_which = 0;
 } g;
+
+// copy `bytes` from (pageable) src into the current staging arena; returns the pinned address (16-byte aligned)
+const void *staged(const void *src, size_t bytes)
+{
+    const size_t at = (g.arena_used + 15) & ~(size_t)15;
+    if (at + bytes > g.arena[g.arena_which].cap) {
+        fprintf(stderr, "libtrt_b200: scene staging arena too small\n");
+        exit(1);
+    }
+    memcpy((char *)g.arena[g.arena_which].p + at, src, bytes);
+    g.arena_used = at + bytes;
+    return (const char *)g.arena[g.arena_which].p + at;
+}
 
 void require_init(const char *who)
 {
@@ -150,6 +168,16 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
         exit(1);
     }
     DevScene &s = g.scene;
+    {
+        const size_t per_sphere = sizeof(double4) * 2 + sizeof(DevMaterial) + sizeof(float4) * 2 + sizeof(CullPair) + sizeof(int) * 2;
+        const size_t need = sizeof(DevScene) + 4096 + per_sphere * ((size_t)scene->num_spheres + 64);
+        g.arena_which = wait ? 0 : (g.arena_which ^ 1);
+        if (g.arena[g.arena_which].cap < need) {
+            CK(cudaStreamSynchronize(g.stream));       // nothing may still be reading the arena that is replaced
+            g.arena[g.arena_which].reserve(need);
+        }
+        g.arena_used = 0;
+    }
     bool ground_in_range = true;
     const trt_Camera &c = scene->camera;
     s.bx[0] = c.frame.basis.x.x; s.bx[1] = c.frame.basis.x.y; s.bx[2] = c.frame.basis.x.z;
@@ -332,10 +360,10 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
     g.sphere_pos.reserve(sizeof(int) * pos.size());
     g.clusters.reserve(sizeof(float4) * clusters.size());
     g.subballs.reserve(sizeof(CullPair) * subballs.size());
-    CK(cudaMemcpyAsync(g.subballs.p, subballs.data(), sizeof(CullPair) * subballs.size(), cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(g.sphere_orig.p, orig.data(), sizeof(int) * orig.size(), cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(g.sphere_pos.p, pos.data(), sizeof(int) * pos.size(), cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(g.clusters.p, clusters.data(), sizeof(float4) * clusters.size(), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.subballs.p, staged(subballs.data(), sizeof(CullPair) * subballs.size()), sizeof(CullPair) * subballs.size(), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.sphere_orig.p, staged(orig.data(), sizeof(int) * orig.size()), sizeof(int) * orig.size(), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.sphere_pos.p, staged(pos.data(), sizeof(int) * pos.size()), sizeof(int) * pos.size(), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.clusters.p, staged(clusters.data(), sizeof(float4) * clusters.size()), sizeof(float4) * clusters.size(), cudaMemcpyHostToDevice, g.stream));
     g.cull = g.cull_allowed && in_range && ground_in_range;
     s.filter_enabled = g.cull ? 1 : 0;
     s.filter_centre_l1 = float_round_up(centre_l1 * (1.0 + 1.0 / 1048576.0));
@@ -343,12 +371,12 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
     g.sphere_mat.reserve(sizeof(DevMaterial) * mats.size());
     g.sphere_cull.reserve(sizeof(float4) * cull.size());
     g.sphere_prim.reserve(sizeof(double4) * prim.size());
-    CK(cudaMemcpyAsync(g.sphere_prim.p, prim.data(), sizeof(double4) * prim.size(), cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(g.sphere_cull.p, cull.data(), sizeof(float4) * cull.size(), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.sphere_prim.p, staged(prim.data(), sizeof(double4) * prim.size()), sizeof(double4) * prim.size(), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.sphere_cull.p, staged(cull.data(), sizeof(float4) * cull.size()), sizeof(float4) * cull.size(), cudaMemcpyHostToDevice, g.stream));
     // The vectors above die at the end of this function, so these copies must complete before it
     // returns: plain (staged) cudaMemcpyAsync from pageable memory is synchronous w.r.t. the host buffer.
-    CK(cudaMemcpyAsync(g.sphere_geom.p, geom.data(), sizeof(double4) * geom.size(), cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(g.sphere_mat.p, mats.data(), sizeof(DevMaterial) * mats.size(), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.sphere_geom.p, staged(geom.data(), sizeof(double4) * geom.size()), sizeof(double4) * geom.size(), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.sphere_mat.p, staged(mats.data(), sizeof(DevMaterial) * mats.size()), sizeof(DevMaterial) * mats.size(), cudaMemcpyHostToDevice, g.stream));
     // the same records two by two for the packed classification; the odd one out is paired with a sphere of radius 0
     std::vector<CullPair> pairs((size_t)(n / 2 + 1));
     for (size_t p = 0; p < pairs.size(); p++) {
@@ -359,8 +387,9 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
         pairs[p].r = make_float2(a.w, b.w);
     }
     g.cull_pairs.reserve(sizeof(CullPair) * pairs.size());
-    CK(cudaMemcpyAsync(g.cull_pairs.p, pairs.data(), sizeof(CullPair) * pairs.size(), cudaMemcpyHostToDevice, g.stream));
-    upload_scene_constants(s, pairs.data(), s.clustered ? 0 : (int)pairs.size(), g.stream);   // Morton-sorted scenes read the global copy
+    CK(cudaMemcpyAsync(g.cull_pairs.p, staged(pairs.data(), sizeof(CullPair) * pairs.size()), sizeof(CullPair) * pairs.size(), cudaMemcpyHostToDevice, g.stream));
+    upload_scene_constants(*(const DevScene *)staged(&s, sizeof s), (const CullPair *)staged(pairs.data(), sizeof(CullPair) * pairs.size()),
+                           s.clustered ? 0 : (int)pairs.size(), g.stream);   // Morton-sorted scenes read the global copy
     // every source above is pageable host memory: the copies were staged before the calls returned, so the vectors may
     // die now; the wait only keeps the historical "scene is resident when this returns" behaviour for callers that time
     if (wait) CK(cudaStreamSynchronize(g.stream));
@@ -473,6 +502,8 @@ void trt_shutdown(void)
     g.quant.release();
     g.bytes.release();
     g.stage.release();
+    g.arena[0].release();
+    g.arena[1].release();
     for (auto &ev : g.ev) {
         if (ev) cudaEventDestroy(ev);
         ev = nullptr;
