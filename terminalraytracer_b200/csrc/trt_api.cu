@@ -414,6 +414,12 @@ RenderParams make_params(int width, int height, int row0, int row1, double *d_pi
     p.height = height;
     p.row0 = row0;
     p.row1 = row1;
+    {
+        volatile double pw = width > 0 ? g.scene.screen_width / (double)width : 0.0;     // one IEEE division each, as TRT.c:981-982
+        volatile double ph = height > 0 ? g.scene.screen_height / (double)height : 0.0;
+        p.pixel_w = pw;
+        p.pixel_h = ph;
+    }
     p.pixel_w_f = width > 0 ? (float)(g.scene.screen_width / width) : 0.f;
     p.pixel_h_f = height > 0 ? (float)(g.scene.screen_height / height) : 0.f;
     p.pixels = d_pixels;

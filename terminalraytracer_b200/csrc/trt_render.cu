@@ -319,8 +319,6 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const Que
     obj = 0;
     index = -1;
     t_hit = 0.0;
-    const double a = dot(d, d);
-    const double two_a = 2.0 * a, four_a = 4.0 * a;
     const int n = c_scene.num_spheres;
     const bool usable = qy.rf.usable != 0;
     const bool shadow = qy.mode != Q_CLOSEST;
@@ -412,6 +410,9 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const Que
         while (survivors) {
             const int j = __ffs(survivors) - 1;
             survivors &= survivors - 1;
+            // a = d.d of TRT.c:646 is evaluated here, per exact test: survivors are rare (0.06-0.3 per query)
+            const double a = dot(d, d);
+            const double two_a = 2.0 * a, four_a = 4.0 * a;
             sphere_exact<false, clustered>(ldg4(P.sphere_geom, base + j), base + j, reference_index<clustered>(P, base + j), o, d, two_a, four_a, closest, obj, index,
                                 best_oi, t_hit, no_tally);
         }
@@ -485,15 +486,9 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
     const int tiles_y = (band_rows + TILE_H - 1) / TILE_H;
     const unsigned int num_tiles = (unsigned int)(tiles_x * tiles_y);
 
-    const double sw = c_scene.screen_width, sh = c_scene.screen_height;
-    const double pixel_w = sw / P.width;   // TRT.c:981
-    const double pixel_h = sh / P.height;  // TRT.c:982
     const int num_dir = c_scene.num_dir, num_point = c_scene.num_point;
     const int num_spheres = c_scene.num_spheres;
     const d3 eye = mk3(c_scene.eye[0], c_scene.eye[1], c_scene.eye[2]);
-    // (double)col / (double)width and (double)row / (double)height (TRT.c:987-988) through shared reciprocals:
-    // numerators are integers >= 1 (0 is special-cased), far inside the fast path of the IEEE division
-    const Reciprocal inv_w = reciprocal_of((double)P.width), inv_h = reciprocal_of((double)P.height);
     // tile certificates need the masks to fit; bigger scenes test every sphere exactly for primary rays
     const bool tile_certs = CULL != 0 && num_spheres <= 32 * TMASK_WORDS;
     const int mask_words = (num_spheres + 31) >> 5;
@@ -511,11 +506,10 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
         const bool valid = col < P.width && brow < band_rows;
         if (valid) tally.add(CTR_PIXELS);
 
-        // per-pixel part of the primary ray, TRT.c:987-988
-        const double fx = col ? div_by_unchecked((double)col, inv_w) : 0.0;
-        const double fy = row ? div_by_unchecked((double)row, inv_h) : 0.0;
-        const double sx0 = (fx * sw - sw / 2.0);
-        const double sy0 = -(fy * sh - sh / 2.0);
+        // per-pixel part of the primary ray, TRT.c:987-988 (two IEEE divisions per tile and lane; nothing of this is
+        // kept in registers across tiles: registers are what limits the resident warps)
+        const double sx0 = ((ieee_div((double)col, (double)P.width)) * c_scene.screen_width - c_scene.screen_width / 2.0);
+        const double sy0 = -((ieee_div((double)row, (double)P.height)) * c_scene.screen_height - c_scene.screen_height / 2.0);
 
         // ---- tile certificates (float): which spheres can any primary ray of this tile hit at all? the ground?
         bool tile_ground_miss = false;
@@ -607,8 +601,8 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                     tally.add(CTR_SAMPLES);
                     tally.add(CTR_BOUNCE_ITERS);
                     tally.add(CTR_TRACE_CALLS);
-                    const double sx = sx0 + c_scene.sub_dx[k] * pixel_w;      // TRT.c:992
-                    const double sy = sy0 + c_scene.sub_dy[k] * pixel_h;      // TRT.c:993
+                    const double sx = sx0 + c_scene.sub_dx[k] * P.pixel_w;    // TRT.c:992 (pixel_w = screen_width / width, host-evaluated)
+                    const double sy = sy0 + c_scene.sub_dy[k] * P.pixel_h;    // TRT.c:993
                     const double sz = -c_scene.screen_distance;
                     d3 sp = mk3(0.0, 0.0, 0.0);
                     sp = sp + mk3(c_scene.bx[0] * sx, c_scene.bx[1] * sx, c_scene.bx[2] * sx);
