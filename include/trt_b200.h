@@ -108,6 +108,19 @@ int trt_encode_rows_device(const double *d_pixels, int width, int rows, char *d_
 int trt_render_rows_quant_device(int width, int height, int row0, int row1, unsigned char *d_quant);
 int trt_encode_rows_quant_device(const unsigned char *d_quant, int width, int rows, char *d_bytes, size_t byte_offset);
 
+/* ---- multi-GPU gather over NVLink peer memory (one process per GPU) ------------------------------------------------
+ * The only exchange step of the path: every rank's encoded row band is written straight into rank 0's stream buffer.
+ * Rank 0 exports its buffer (allocated with trt_device_alloc) as a 64-byte CUDA IPC handle, the other ranks import it
+ * once and then push each finished piece with a copy-engine transfer that runs while their next piece renders; no SM
+ * and no receiver-side kernel is involved.  trt_peer_copies_wait() blocks until this rank's pushes have landed. */
+#define TRT_IPC_HANDLE_BYTES 64
+int trt_ipc_export(const void *d_ptr, unsigned char handle[TRT_IPC_HANDLE_BYTES]);
+void *trt_ipc_import(const unsigned char handle[TRT_IPC_HANDLE_BYTES]);
+int trt_ipc_close(void *d_peer_ptr);
+/* after everything enqueued so far on trt_stream(): copy `bytes` from d_src (this GPU) to d_peer_dst (any GPU) */
+int trt_push_to_peer(void *d_peer_dst, const void *d_src, size_t bytes);
+int trt_peer_copies_wait(void);
+
 /* Write the 6-byte home sequence at d_stream[0..5] and the 3 NUL bytes after the last row of a
  * width x height stream (TRT.c:1102, 1104, 1130). */
 int trt_stream_frame_device(char *d_stream, int width, int height);

@@ -905,6 +905,52 @@ int trt_render_orbit(const trt_Scene *scene, int width, int height, const double
     return delivered;
 }
 
+// ---- gather over NVLink peer memory ------------------------------------------------------------------------
+
+int trt_ipc_export(const void *d_ptr, unsigned char handle[TRT_IPC_HANDLE_BYTES])
+{
+    require_init("trt_ipc_export");
+    static_assert(sizeof(cudaIpcMemHandle_t) == TRT_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+    memcpy(handle, &h, sizeof h);
+    return 0;
+}
+
+void *trt_ipc_import(const unsigned char handle[TRT_IPC_HANDLE_BYTES])
+{
+    require_init("trt_ipc_import");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    return p;
+}
+
+int trt_ipc_close(void *d_peer_ptr)
+{
+    if (d_peer_ptr) CK(cudaIpcCloseMemHandle(d_peer_ptr));
+    return 0;
+}
+
+int trt_push_to_peer(void *d_peer_dst, const void *d_src, size_t bytes)
+{
+    require_init("trt_push_to_peer");
+    if (!bytes) return 0;
+    // order the transfer after the encode that produced the bytes, run it on the copy stream (copy engine, NVLink)
+    CK(cudaEventRecord(g.ev[3], g.stream));
+    CK(cudaStreamWaitEvent(g.copy_stream, g.ev[3], 0));
+    CK(cudaMemcpyAsync(d_peer_dst, d_src, bytes, cudaMemcpyDefault, g.copy_stream));
+    return 0;
+}
+
+int trt_peer_copies_wait(void)
+{
+    require_init("trt_peer_copies_wait");
+    CK(cudaStreamSynchronize(g.copy_stream));
+    return 0;
+}
+
 // ---- small helpers for plain-C callers -----------------------------------------------------------------
 
 void *trt_device_alloc(size_t bytes)

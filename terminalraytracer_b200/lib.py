@@ -30,6 +30,11 @@ SIGNATURES = {
     "trt_buffered_draw_screen": (None, [C.POINTER(abi.Screen)]),
     "trt_render_ansi": (C.c_size_t, [C.POINTER(abi.Scene), C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "trt_render_orbit": (C.c_int, [C.POINTER(abi.Scene), C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "trt_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "trt_ipc_import": (C.c_void_p, [C.c_void_p]),
+    "trt_ipc_close": (C.c_int, [C.c_void_p]),
+    "trt_push_to_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "trt_peer_copies_wait": (C.c_int, []),
     "trt_set_scene": (C.c_int, [C.POINTER(abi.Scene)]),
     "trt_render_rows_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "trt_encode_rows_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),

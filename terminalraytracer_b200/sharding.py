@@ -39,6 +39,38 @@ def row_bands(height, world_size, weights=None):
     return bands
 
 
+def sub_bands(band, pieces, weights=None):
+    """Split one rank's band (r0,r1) into contiguous, non-empty pieces: each piece is pushed to rank 0 while the next one
+    renders (pipeline.FramePipeline), so only the last piece's transfer is exposed.  pieces: an int (equal cost) or a
+    sequence of cost fractions, e.g. (0.7, 0.3) — a big first piece and a small last one keep both the number of
+    kernel launches and the exposed transfer small."""
+    r0, r1 = band
+    if r1 <= r0:
+        return []
+    n = r1 - r0
+    w = [1.0] * n if weights is None else [float(x) for x in weights[r0:r1]]
+    fractions = [1.0 / int(pieces)] * int(pieces) if isinstance(pieces, int) else [float(f) for f in pieces]
+    total, norm = sum(w), sum(fractions)
+    if total <= 0 or norm <= 0:
+        return [(r0, r1)]
+    out, start, acc, cut = [], 0, 0.0, 0.0
+    for k, f in enumerate(fractions):
+        cut += f / norm
+        end = start
+        if k == len(fractions) - 1:
+            end = n
+        else:
+            while end < n and acc + w[end] <= total * cut:
+                acc += w[end]
+                end += 1
+        if end > start:
+            out.append((r0 + start, r0 + end))
+            start = end
+    if start < n:
+        out.append((r0 + start, r1))
+    return out
+
+
 def band_byte_range(width, band):
     """Byte range of a row band inside the terminal stream (home sequence included in the offset)."""
     r0, r1 = band

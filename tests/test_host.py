@@ -171,3 +171,20 @@ def test_synthetic_skyboxes_are_deterministic():
         assert np.array_equal(a.face(f), b.face(f))
     stars = sum(int((a.face(f).max(axis=2) > 50).sum()) for f in range(6))
     assert 0.001 < stars / (6 * 64 * 64) < 0.01
+
+
+def test_sub_bands_partition_a_band_exactly():
+    """pieces of a rank's band (pushed to rank 0 one by one): contiguous, non-empty, covering, cost-proportional"""
+    from terminalraytracer_b200 import sharding
+    for band in [(0, 1), (0, 2), (7, 19), (100, 1100), (5, 5)]:
+        for pieces in (1, 2, 3, 7, (0.7, 0.3), (0.5, 0.3, 0.2)):
+            sb = sharding.sub_bands(band, pieces)
+            if band[1] == band[0]:
+                assert sb == []
+                continue
+            assert sb[0][0] == band[0] and sb[-1][1] == band[1]
+            assert all(a[1] == b[0] for a, b in zip(sb, sb[1:])) and all(b > a for a, b in sb)
+    assert sharding.sub_bands((0, 100), (0.7, 0.3)) == [(0, 70), (70, 100)]
+    w = [1.0] * 50 + [9.0] * 50                     # the second half of the rows costs 9x more
+    (a0, a1), (b0, b1) = sharding.sub_bands((0, 100), (0.5, 0.5), w)
+    assert a0 == 0 and a1 == b0 and b1 == 100 and 70 <= a1 <= 80
