@@ -44,7 +44,7 @@ enum {
     ST_POINT, ST_POINT_OPEN, ST_POINT_BLOCKED, ST_POINT_UNKNOWN,
     ST_SHADOW_EXACT_TESTS,
     ST_SKY, ST_SKY_CERTIFIED, ST_CLUSTER_TESTS, ST_CLUSTERS_MISSED, ST_SUBCLUSTER_TESTS, ST_SUBCLUSTERS_MISSED,
-    ST_TILES, ST_TILES_PATCH, ST_PATCH_DIR_CANDIDATES, ST_PATCH_POINT_CANDIDATES, ST_PATCH_BOUNCE_CANDIDATES, ST_PATCH_RECORDS,
+    ST_TILES, ST_TILES_PATCH, ST_TILES_PATCH_EMPTY, ST_PATCH_DIR_CANDIDATES, ST_PATCH_POINT_CANDIDATES, ST_PATCH_BOUNCE_CANDIDATES, ST_PATCH_RECORDS,
     ST_COUNT
 };
 
@@ -352,6 +352,13 @@ long long cert_check_rows(const trt_Scene *scene, int W, int H, int row0, int ro
                                                                                                           c.cull[4 * i + 2], c.cull[4 * i + 3], S_ball);
                         stats[ST_PATCH_BOUNCE_CANDIDATES] += patch_cand[(size_t)32 * 32 + i];
                     }
+                }
+                {
+                    long long any = 0;
+                    for (int l = 0; l < scene->num_directional_lights && l < 16; l++) for (int i = 0; i < n; i++) any += patch_cand[(size_t)l * 32 + i];
+                    for (int l = 0; l < scene->num_point_lights && l < 16; l++) for (int i = 0; i < n; i++) any += patch_cand[(size_t)(16 + l) * 32 + i];
+                    for (int i = 0; i < n; i++) any += patch_cand[(size_t)32 * 32 + i];
+                    if (!any) stats[ST_TILES_PATCH_EMPTY]++;
                 }
             }
 

@@ -68,7 +68,7 @@ def load_oracle():
 
 CERT_STATS = ("primary", "primary_tile_survivors", "primary_ground_culled", "bounce", "bounce_survivors", "bounce_ground_culled",
               "bounce_exact_hits", "dir", "dir_open", "dir_blocked", "dir_unknown", "point", "point_open", "point_blocked",
-              "point_unknown", "shadow_exact_tests", "sky", "sky_certified", "cluster_tests", "clusters_missed", "subcluster_tests", "subclusters_missed", "tiles", "tiles_patch", "patch_dir_candidates", "patch_point_candidates",
+              "point_unknown", "shadow_exact_tests", "sky", "sky_certified", "cluster_tests", "clusters_missed", "subcluster_tests", "subclusters_missed", "tiles", "tiles_patch", "tiles_patch_empty", "patch_dir_candidates", "patch_point_candidates",
               "patch_bounce_candidates", "patch_records")
 
 
