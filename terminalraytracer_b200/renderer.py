@@ -71,8 +71,10 @@ class Renderer:
         n = len(times)
         arr = (C.c_double * n)(*[float(t) for t in times])
 
+        array_type = C.c_ubyte * abi.stream_bytes(scene.width, scene.height)
+
         def _cb(ptr, nbytes, frame, _user):
-            view = np.ctypeslib.as_array((C.c_ubyte * nbytes).from_address(ptr))
+            view = np.frombuffer(array_type.from_address(ptr), dtype=np.uint8)    # no copy: the library's pinned buffer
             return 1 if sink(frame, view) else 0
 
         cb = _lib.FRAME_SINK(_cb)
