@@ -58,7 +58,7 @@ typedef struct {
     float gp[3], gn[3];
     long long *st;
     long long bad;
-    unsigned char *scratch; int num_clusters; int *order; float *cluster4; float *sub4; /* sub4: balls of 8 inside each cluster */ /* Morton order of the spheres and bounding balls of 32 (many-sphere scenes) */
+    unsigned char *scratch; int num_clusters; int *order; float *cluster4; float *sub4; /* sub4: balls of 8 inside each cluster */ /* k-d order of the spheres and bounding balls of 32 (many-sphere scenes) */
     const unsigned char *cand; /* patch certificate: spheres still possible for the query at hand; NULL = all */
 } ctx_t;
 
@@ -255,7 +255,7 @@ long long cert_check_rows(const trt_Scene *scene, int W, int H, int row0, int ro
     c.cluster4 = (float *)malloc(sizeof(float) * 4 * (size_t)(c.num_clusters > 0 ? c.num_clusters : 1));
     c.sub4 = (float *)malloc(sizeof(float) * 16 * (size_t)(c.num_clusters > 0 ? c.num_clusters : 1));
     if (c.num_clusters) {
-        trt_cert_morton_order(c.cull, n, c.order);
+        trt_cert_kd_order(c.cull, n, c.order);
         float *sorted = (float *)malloc(sizeof(float) * 4 * (size_t)n);
         for (int j = 0; j < n; j++) memcpy(sorted + 4 * j, c.cull + 4 * c.order[j], sizeof(float) * 4);
         for (int k = 0; k < c.num_clusters; k++) {

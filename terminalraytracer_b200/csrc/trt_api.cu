@@ -313,7 +313,7 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
         cull[i] = make_float4((float)sp.center.x, (float)sp.center.y, (float)sp.center.z, trt_cert_pad_radius(sp.radius));
         (void)r;
     }
-    // Many-sphere scenes: the device sees the spheres in Morton order, 32 consecutive ones share a bounding ball
+    // Many-sphere scenes: the device sees the spheres in k-d order, 32 consecutive ones share a bounding ball
     // (trt_cert_cluster_miss).  `orig` keeps the reference's index of every sorted sphere for its tie-breaking rule
     // (TRT.c:810, strict <: the lowest index wins), `pos` is the inverse (the all-FP64 query scans in the reference's order).
     std::vector<int> orig((size_t)(n > 0 ? n : 1)), pos((size_t)(n > 0 ? n : 1));
@@ -324,7 +324,7 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
     memset(subballs.data(), 0, sizeof(CullPair) * subballs.size());
     s.clustered = n > TRT_CLUSTER_MIN_SPHERES ? 1 : 0;
     if (s.clustered) {
-        trt_cert_morton_order(reinterpret_cast<const float *>(cull.data()), n, orig.data());
+        trt_cert_kd_order(reinterpret_cast<const float *>(cull.data()), n, orig.data());
         std::vector<double4> geom2(geom), prim2(prim);
         std::vector<DevMaterial> mats2(mats);
         std::vector<float4> cull2(cull);
@@ -389,14 +389,14 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
     g.cull_pairs.reserve(sizeof(CullPair) * pairs.size());
     CK(cudaMemcpyAsync(g.cull_pairs.p, staged(pairs.data(), sizeof(CullPair) * pairs.size()), sizeof(CullPair) * pairs.size(), cudaMemcpyHostToDevice, g.stream));
     upload_scene_constants(*(const DevScene *)staged(&s, sizeof s), (const CullPair *)staged(pairs.data(), sizeof(CullPair) * pairs.size()),
-                           s.clustered ? 0 : (int)pairs.size(), g.stream);   // Morton-sorted scenes read the global copy
+                           s.clustered ? 0 : (int)pairs.size(), g.stream);   // k-d-sorted scenes read the global copy
     // every source above is pageable host memory: the copies were staged before the calls returned, so the vectors may
     // die now; the wait only keeps the historical "scene is resident when this returns" behaviour for callers that time
     if (wait) CK(cudaStreamSynchronize(g.stream));
     g.have_scene = true;
 }
 
-// 0: all FP64; 1: small scene, certificate records in __constant__; 2: Morton-sorted scene with cluster balls, records in global memory
+// 0: all FP64; 1: small scene, certificate records in __constant__; 2: k-d-sorted scene with cluster balls, records in global memory
 int cull_mode() { return !g.cull ? 0 : (g.scene.clustered ? 2 : 1); }
 
 RenderParams make_params(int width, int height, int row0, int row1, double *d_pixels, uchar4 *d_quant, bool count)

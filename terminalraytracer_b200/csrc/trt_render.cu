@@ -188,7 +188,7 @@ __device__ __forceinline__ d3 sky_colour(const RenderParams &P, const double *s_
 
 // ray_intersects_sphere (TRT.c:638-672) with oc = origin - centre and c = oc.oc - r*r given, plus the
 // closest-so-far update of trace_ray (TRT.c:807-827).  Keeps the hit PARAMETER; the point is o + t d.
-// Spheres may be visited in any order (Morton-sorted scenes, per-lane survivor walks): `oi` is the sphere's index in
+// Spheres may be visited in any order (k-d-sorted scenes, per-lane survivor walks): `oi` is the sphere's index in
 // the reference's array, and a hit replaces the closest one if it is closer or equally close with a lower reference
 // index — exactly what the reference's index-ordered scan with strict < keeps (TRT.c:810).
 template <bool COUNT, bool ANY_ORDER = true>
@@ -226,7 +226,7 @@ __device__ __forceinline__ void sphere_exact(const double4 g, int i, int oi, con
     sphere_exact_oc<COUNT, ANY_ORDER>(oc, c, i, oi, o, d, two_a, four_a, closest, obj, index, best_oi, t_hit, tally);
 }
 
-// reference index of the sphere at position i (identity unless the scene is Morton-sorted)
+// reference index of the sphere at position i (identity unless the scene is k-d-sorted)
 template <bool CLUSTERED>
 __device__ __forceinline__ int reference_index(const RenderParams &P, int i) { return CLUSTERED ? __ldg(&P.sphere_orig[i]) : i; }
 
@@ -308,7 +308,7 @@ struct Query {
 };
 
 // CONST_RECORDS: small scene (at most TRT_CLUSTER_MIN_SPHERES spheres): records in __constant__, reference order, no
-// clusters.  Otherwise the scene is Morton-sorted with bounding balls and its records are read from global memory.
+// clusters.  Otherwise the scene is k-d-sorted with bounding balls and its records are read from global memory.
 template <bool CONST_RECORDS>
 __device__ __forceinline__ bool query_certified(const RenderParams &P, const Query &qy, const d3 &o, double num_g, bool use_patch,
                                                 unsigned int patch_mask, int &obj, int &index, double &t_hit, unsigned int *exact_tests)
@@ -334,7 +334,7 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const Que
     constexpr bool clustered = !CONST_RECORDS;
     for (int base = 0; base < n; base += 32) {
         const int cnt = min(32, n - base);
-        // many-sphere scenes: the chunk is a cluster of the Morton order with a bounding ball, and four balls of 8 inside
+        // many-sphere scenes: the chunk is a cluster of the k-d order with a bounding ball, and four balls of 8 inside
         // it (trt_cert_cluster_miss): skip what no lane's ray can reach, and let every lane drop what its own ray cannot
         bool ball_missed = false;
         unsigned int reachable = 0xffffffffu;      // warp-uniform: spheres of this chunk some lane may still hit

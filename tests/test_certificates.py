@@ -42,7 +42,7 @@ def test_certificates_stress_scene(cc):
     assert bad == 0
     assert st["primary_tile_survivors"] < 0.05 * 1024 * st["primary"]
     assert st["bounce_survivors"] < 0.005 * 1024 * st["bounce"]
-    # Morton-sorted clusters of 32 (and of 8 inside them) with bounding balls: most are certainly missed by a given ray
+    # k-d-sorted clusters of 32 (and of 8 inside them) with bounding balls: most are certainly missed by a given ray
     assert st["cluster_tests"] > 0 and st["clusters_missed"] > 0.4 * st["cluster_tests"]
     assert st["subclusters_missed"] > 0.5 * st["subcluster_tests"]
 
