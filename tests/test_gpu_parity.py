@@ -398,6 +398,52 @@ def test_gpu_orbit_sink_streams_frames_in_order(renderer, orc):
     assert list(got) == [0, 1, 2]
 
 
+def _peer_worker(rank, world, port, w, h, out_path):
+    import torch
+    import torch.distributed as dist
+    from terminalraytracer_b200 import pipeline, renderer as R
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # plumbing only; the bytes travel through CUDA IPC
+    rd = R.Renderer(0)
+    try:
+        sky = S.synthetic_cubemap("uv_gradient", 64)
+        rd.upload_skybox(sky)
+        sc = S.SceneData(w, h, sky).set_time(3.7)
+        weights = rd.estimate_row_costs(sc)
+        pipe = pipeline.FramePipeline(rd, w, h, rank, world, row_weights=weights, peer=True, pieces=(0.6, 0.4))
+        for _ in range(2):                                          # twice: buffers and events are reused
+            stream = pipe.render(sc)
+        torch.cuda.synchronize()
+        if rank == 0:
+            np.save(out_path, stream.cpu().numpy())
+        dist.barrier()
+        if rank != 0:
+            pipe.close()
+        dist.barrier()
+        pipe.close()
+    finally:
+        rd.close()
+        dist.destroy_process_group()
+
+
+def test_gpu_peer_memory_gather_three_ranks(orc, tmp_path):
+    """the multi-GPU exchange (every rank writes its encoded pieces into rank 0's stream through a CUDA IPC mapping,
+    trt_push_to_peer) with three processes — on one device here, one per GPU in bench.py: same code, same bytes"""
+    import socket
+    import torch.multiprocessing as mp
+    w, h = 150, 83
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    out = str(tmp_path / "stream.npy")
+    mp.spawn(_peer_worker, args=(3, port, w, h, out), nprocs=3, join=True)
+    sc = S.SceneData(w, h, S.synthetic_cubemap("uv_gradient", 64)).set_time(3.7)
+    want = U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc))
+    assert np.array_equal(np.load(out), want)
+
+
 # ---- full-size configs: size-independent properties + sampled rows against the oracle -----------------------
 
 @pytest.mark.parametrize("cfg", [("uv_checker", 3840, 2160, 3.7), ("milky_way", 7680, 4320, 3.7)], ids=lambda c: f"{c[1]}x{c[2]}")
