@@ -805,15 +805,29 @@ size_t trt_render_ansi(const trt_Scene *scene, int width, int height, char *out,
     // bytes (829 MB per 7680x4320 frame: PCIe time comparable to K1's) overlaps the rendering of the next one.
     // All kernels are enqueued first; the copies run on a second stream, each behind its chunk's event, so the
     // overlap also happens when `out` is pageable memory (where cudaMemcpyAsync blocks the host).
+    // Chunks shrink geometrically (each ~60 % of the one before): only the LAST chunk's copy is exposed after the last
+    // kernel, and every extra launch costs a kernel tail, so few chunks with a small last one beat many equal ones.
     const size_t pixels = (size_t)width * (size_t)height;
-    int chunks = (int)(pixels >> 21);          // ~2 Mpixel (a few ms of K1) per chunk
-    if (chunks > Context::MAX_CHUNKS) chunks = Context::MAX_CHUNKS;
+    int chunks = 1;
+    for (size_t px = pixels >> 20; px > 1 && chunks < Context::MAX_CHUNKS; px >>= 1) chunks++;   // 1 Mpixel frames: 1 chunk ... 32 Mpixel: 6
     if (chunks > height) chunks = height;
-    if (chunks < 1) chunks = 1;
+    int bounds[Context::MAX_CHUNKS + 1];
+    {
+        double weight[Context::MAX_CHUNKS], total = 0.0, acc = 0.0;
+        for (int c = 0; c < chunks; c++) total += (weight[c] = pow(0.6, c));
+        bounds[0] = 0;
+        for (int c = 0; c < chunks; c++) {
+            acc += weight[c];
+            int r = (int)(height * (acc / total) + 0.5);
+            if (r <= bounds[c]) r = bounds[c] + 1;              // never empty
+            if (r > height - (chunks - 1 - c)) r = height - (chunks - 1 - c);
+            bounds[c + 1] = c == chunks - 1 ? height : r;
+        }
+    }
     const size_t row_bytes = TRT_ROW_BYTES(width);
     launch_stream_frame((char *)g.bytes.p, width, height, g.stream);
     for (int c = 0; c < chunks; c++) {
-        const int r0 = (int)((long long)height * c / chunks), r1 = (int)((long long)height * (c + 1) / chunks);
+        const int r0 = bounds[c], r1 = bounds[c + 1];
         RenderParams p = make_params(width, height, r0, r1, nullptr, (uchar4 *)g.quant.p + (size_t)r0 * (size_t)width, false);
         CK(cudaEventRecord(g.chunk_ev[c][0], g.stream));
         launch_render(p, false, cull_mode(), g.num_sms, g.stream);
@@ -823,7 +837,7 @@ size_t trt_render_ansi(const trt_Scene *scene, int width, int height, char *out,
         CK(cudaEventRecord(g.chunk_ev[c][2], g.stream));
     }
     for (int c = 0; c < chunks; c++) {
-        const int r0 = (int)((long long)height * c / chunks), r1 = (int)((long long)height * (c + 1) / chunks);
+        const int r0 = bounds[c], r1 = bounds[c + 1];
         const size_t b0 = c == 0 ? 0 : TRT_HOME_BYTES + (size_t)r0 * row_bytes;
         const size_t b1 = c == chunks - 1 ? total : TRT_HOME_BYTES + (size_t)r1 * row_bytes;
         CK(cudaStreamWaitEvent(g.copy_stream, g.chunk_ev[c][2], 0));
