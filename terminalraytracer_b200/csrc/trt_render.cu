@@ -166,7 +166,7 @@ static __device__ TRT_SKY_INLINE d3 sky_colour_of(const uchar4 *sky, const doubl
     // face and texel are a decision: certified in float for ~99.6 % of the directions (trt_cert_sky_texel), else
     // the reference's own double arithmetic
     int face, texel;
-    if (!(c_scene.filter_enabled && trt_cert_sky_texel((float)d.x, (float)d.y, (float)d.z, c_scene.sky_dim, &face, &texel)))
+    if (TRT_UNLIKELY(!(c_scene.filter_enabled && trt_cert_sky_texel((float)d.x, (float)d.y, (float)d.z, c_scene.sky_dim, &face, &texel))))
         texel = sky_texel_index(unit(d), c_scene.sky_dim, face);
     const uchar4 t = __ldg(&sky[(size_t)face * (size_t)c_scene.sky_face_stride + (size_t)texel]);
     return mk3(s_byte_to_unit[t.x], s_byte_to_unit[t.y], s_byte_to_unit[t.z]);   // TRT.c:866
@@ -407,7 +407,7 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const Que
         if (shadow && n > 32 && __all_sync(__activemask(), usable && blocked)) break;
         if (exact_tests) *exact_tests += (unsigned int)__popc(survivors);
         // pass 2 (double, exact): each lane walks its own survivors in index order
-        while (survivors) {
+        while (TRT_UNLIKELY(survivors != 0)) {
             const int j = __ffs(survivors) - 1;
             survivors &= survivors - 1;
             // a = d.d of TRT.c:646 is evaluated here, per exact test: survivors are rare (0.06-0.3 per query)
@@ -426,12 +426,12 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const Que
         // any hit blocks.  The ground (TRT.c:677-695): numerator and denominator are the reference's own doubles
         // (the denominator is a per-light constant); opposite signs or a zero numerator give t <= 0, a miss,
         // without the division.
-        if (!blocked && obj == 0 && fabs(qy.plane_denom) > 0.00001 && num_g != 0.0 && ((num_g < 0.0) == (qy.plane_denom < 0.0))) {
+        if (TRT_UNLIKELY(!blocked && obj == 0 && fabs(qy.plane_denom) > 0.00001 && num_g != 0.0 && ((num_g < 0.0) == (qy.plane_denom < 0.0)))) {
             const double t = ieee_div(num_g, qy.plane_denom);
             if (t > 0.00001) obj = 2;
         }
     } else {
-        if (!blocked && qy.ground_candidate) plane_exact_num<false>(num_g, o, d, closest, obj, t_hit, no_tally);
+        if (TRT_UNLIKELY(!blocked && qy.ground_candidate)) plane_exact_num<false>(num_g, o, d, closest, obj, t_hit, no_tally);
     }
     return blocked;
 }
@@ -871,7 +871,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                                 f = 1.0;
                             } else {
                                 const DevLightPoint &Lp = c_scene.point[q - num_dir];
-                                if (!blocked && obj2 != 0) {
+                                if (TRT_UNLIKELY(!blocked && obj2 != 0)) {
                                     // a blocker that is farther than the light does not block, TRT.c:936-941
                                     const d3 bh = mk3(at.x + t2 * qy.d.x, at.y + t2 * qy.d.y, at.z + t2 * qy.d.z);
                                     const d3 to_blocker = push_back(at, bh) - at;
