@@ -17,16 +17,20 @@
 //   * PRODUCE step (one per sample index k, lane = pixel): primary ray -> closest hit.  Spheres are tested
 //     exactly, but only those the TILE certificate could not rule out for the whole tile (usually none or one),
 //     with the eye-relative terms of the quadratic precomputed on the host.  A sample that sees the sky is
-//     finished on the spot; a sample that hits a surface becomes a 104-byte HIT RECORD in a warp-private
-//     shared-memory ring;
-//   * CONSUME step (whenever 32 records are queued, lane = record): push-back, normal, one shadow query per
-//     light (float certificates decide open / blocked for most of them; the rest walk their few surviving
-//     spheres exactly), shading, reflection, and the closest-hit query of the reflected ray, whose hit becomes
-//     the next record and whose miss finishes the sample with a sky lookup;
-//   * finished samples are parked in shared memory and summed per pixel in sample order at the end of the tile
-//     (TRT.c:1063 adds them in that order; floating-point addition is not associative).
+//     finished on the spot; a sample that hits a surface becomes a 40-byte record (direction, hit parameter, ids)
+//     in warp-private shared-memory ring A;
+//   * CONSUME step (whenever a ring holds 32 records, lane = record): push-back, normal, then ONE loop over the
+//     record's queries — a shadow ray per light (float certificates decide open / blocked for most of them; the rest
+//     walk their few surviving spheres exactly), then the reflected ray — shading, accumulation.  The reflected ray's
+//     hit becomes a 104-byte record in ring B; its miss finishes the sample with a sky lookup.  First-generation
+//     hits have their own ring because a tile's ground hits share tile-level ("patch") certificates;
+//   * finished samples are parked in an L2-resident per-warp slice of global memory and summed per pixel in sample
+//     order at the end of the tile (TRT.c:1063 adds them in that order; floating-point addition is not associative);
+//   * scenes of more than 64 spheres are ordered along a k-d tree with bounding balls per 32 and per 8 spheres
+//     (CULL == 2): whole chunks of the query loop are skipped when no lane's ray can reach their ball.
 // Compared with one-ray-per-trip state machines, no lane ever executes another lane's phase under predication:
-// the ring keeps full warps of like work together however the bounce counts diverge.
+// the rings keep full warps of like work together however the bounce counts diverge.  DESIGN.md 4.2 has the
+// measurements and the list of variants that were tried.
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
