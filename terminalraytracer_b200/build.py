@@ -20,7 +20,7 @@ NVCC_COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompi
                "-I", INCLUDE, "-I", CSRC]
 # per-TU extra flags
 CU_SOURCES = {
-    "trt_render.cu": ["-fmad=false", "-Xptxas", "-v"],
+    "trt_render.cu": ["-fmad=false", "-Xptxas", "-v"] + os.environ.get("TRT_EXTRA_NVCC", "").split(),   # TRT_EXTRA_NVCC: experiment builds only
     "trt_encode.cu": ["-fmad=false"],
     "trt_peak.cu": [],
     "trt_api.cu": ["-fmad=false"],
