@@ -182,6 +182,26 @@ def test_gpu_more_spheres_than_tile_masks(renderer, orc):
     assert np.array_equal(gpu_frame(renderer, sc), U.cpu_render(orc, "orc_project_scene", sc))
 
 
+def test_gpu_random_scenes_fuzz(renderer, orc):
+    """60 random scenes (scripts/fuzz_parity.py: sphere counts across the chunk and cluster limits, random lights above
+    and below a tilted ground, cameras inside the sphere cloud): pixels bit-identical, audit silent.  The script was
+    run over 2000 scenes with 0 mismatches when the round closed."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(U.ROOT, "scripts", "fuzz_parity.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    rng = np.random.default_rng(99)
+    sky = S.synthetic_cubemap("uv_gradient", 64)
+    renderer.upload_skybox(sky)
+    for k in range(60):
+        sc = fuzz.random_scene(rng, sky)
+        got = renderer.project_scene(sc)
+        assert np.array_equal(got, U.cpu_render(orc, "orc_project_scene", sc)), k
+        renderer.set_scene(sc)
+        ctr, _ = renderer.count_rows(sc.width, sc.height, 0, sc.height)
+        assert ctr[28] == 0, k
+
+
 # ---- unit-level probes ----------------------------------------------------------------------------------
 
 def test_gpu_trace_ray_known_answers(renderer):
