@@ -553,7 +553,11 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
             if (any_sphere == 0 && !tile_ground_miss && num_spheres <= PATCH_MAX_SPHERES && c_scene.prim_num_sign != 0 && c_scene.filter_enabled) {
                 trt_cert_ball ball;
                 trt_cert_patch_ball(&cam, Dx, Dy, Dz, hx, hy, c_scene.prim_num_f, gn[0], gn[1], gn[2], S, &ball);
+#ifdef TRT_NO_PATCH
+                patch = false;
+#else
                 patch = ball.ok != 0;
+#endif
                 if (patch) {
                     const float S_ball = fabsf(ball.cx) + fabsf(ball.cy) + fabsf(ball.cz) + ball.r + c_scene.filter_centre_l1;
                     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
