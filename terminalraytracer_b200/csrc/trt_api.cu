@@ -399,6 +399,8 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
 // 0: all FP64; 1: small scene, certificate records in __constant__; 2: k-d-sorted scene with cluster balls, records in global memory
 int cull_mode() { return !g.cull ? 0 : (g.scene.clustered ? 2 : 1); }
 
+bool one_plus_one() { return g.scene.num_dir == 1 && g.scene.num_point == 1; }
+
 RenderParams make_params(int width, int height, int row0, int row1, double *d_pixels, uchar4 *d_quant, bool count)
 {
     if (!g.have_scene) {
@@ -594,7 +596,7 @@ int trt_render_rows_device(int width, int height, int row0, int row1, double *d_
 {
     require_init("trt_render_rows_device");
     RenderParams p = make_params(width, height, row0, row1, d_pixels, nullptr, false);
-    launch_render(p, false, cull_mode(), g.num_sms, g.stream);
+    launch_render(p, false, cull_mode(), one_plus_one(), g.num_sms, g.stream);
     return 0;
 }
 
@@ -602,7 +604,7 @@ int trt_render_rows_quant_device(int width, int height, int row0, int row1, unsi
 {
     require_init("trt_render_rows_quant_device");
     RenderParams p = make_params(width, height, row0, row1, nullptr, (uchar4 *)d_quant, false);
-    launch_render(p, false, cull_mode(), g.num_sms, g.stream);
+    launch_render(p, false, cull_mode(), one_plus_one(), g.num_sms, g.stream);
     return 0;
 }
 
@@ -632,7 +634,7 @@ int trt_count_rows_device(int width, int height, int row0, int row1, double *d_p
     require_init("trt_count_rows_device");
     CK(cudaMemsetAsync(g.counters.p, 0, sizeof(unsigned long long) * TRT_NUM_COUNTERS, g.stream));
     RenderParams p = make_params(width, height, row0, row1, d_pixels, nullptr, true);
-    launch_render(p, true, cull_mode(), g.num_sms, g.stream);
+    launch_render(p, true, cull_mode(), one_plus_one(), g.num_sms, g.stream);
     CK(cudaMemcpyAsync(counters, g.counters.p, sizeof(unsigned long long) * TRT_NUM_COUNTERS, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     return 0;
@@ -654,7 +656,7 @@ int trt_estimate_row_costs(const trt_Scene *scene, int width, int height, double
     CK(cudaMemsetAsync(d_cost.p, 0, sizeof(unsigned int) * (size_t)sh, g.stream));
     RenderParams p = make_params(sw, sh, 0, sh, nullptr, (uchar4 *)d_quant.p, false);
     p.row_cost = (unsigned int *)d_cost.p;
-    launch_render(p, false, cull_mode(), g.num_sms, g.stream);
+    launch_render(p, false, cull_mode(), one_plus_one(), g.num_sms, g.stream);
     std::vector<unsigned int> cost((size_t)sh);
     CK(cudaMemcpyAsync(cost.data(), d_cost.p, sizeof(unsigned int) * (size_t)sh, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
@@ -758,7 +760,7 @@ void trt_project_scene(const trt_Scene *scene, trt_Screen *screen)
     g.pixels.reserve(bytes);
     RenderParams p = make_params(w, h, 0, h, (double *)g.pixels.p, nullptr, false);
     CK(cudaEventRecord(g.ev[0], g.stream));
-    launch_render(p, false, cull_mode(), g.num_sms, g.stream);
+    launch_render(p, false, cull_mode(), one_plus_one(), g.num_sms, g.stream);
     CK(cudaEventRecord(g.ev[1], g.stream));
     CK(cudaMemcpyAsync(screen->pixels, g.pixels.p, bytes, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
@@ -830,7 +832,7 @@ size_t trt_render_ansi(const trt_Scene *scene, int width, int height, char *out,
         const int r0 = bounds[c], r1 = bounds[c + 1];
         RenderParams p = make_params(width, height, r0, r1, nullptr, (uchar4 *)g.quant.p + (size_t)r0 * (size_t)width, false);
         CK(cudaEventRecord(g.chunk_ev[c][0], g.stream));
-        launch_render(p, false, cull_mode(), g.num_sms, g.stream);
+        launch_render(p, false, cull_mode(), one_plus_one(), g.num_sms, g.stream);
         CK(cudaEventRecord(g.chunk_ev[c][1], g.stream));
         launch_encode_quant((const uchar4 *)g.quant.p + (size_t)r0 * (size_t)width, width, r1 - r0, (char *)g.bytes.p,
                             TRT_HOME_BYTES + (size_t)r0 * row_bytes, g.stream);
@@ -892,7 +894,7 @@ int trt_render_orbit(const trt_Scene *scene, int width, int height, const double
         trt_orbit_camera(&posed.camera, times[k]);
         upload_scene(&posed, false);
         RenderParams p = make_params(width, height, 0, height, nullptr, (uchar4 *)g.quant.p, false);
-        launch_render(p, false, cull_mode(), g.num_sms, g.stream);
+        launch_render(p, false, cull_mode(), one_plus_one(), g.num_sms, g.stream);
         launch_stream_frame((char *)d_bytes[b].p, width, height, g.stream);
         launch_encode_quant((const uchar4 *)g.quant.p, width, height, (char *)d_bytes[b].p, TRT_HOME_BYTES, g.stream);
         CK(cudaEventRecord(encoded[b], g.stream));

@@ -7,7 +7,8 @@ namespace trt {
 
 // trt_render.cu (owns the __constant__ scene)
 void upload_scene_constants(const DevScene &scene, const CullPair *pairs, int count, cudaStream_t stream);
-void launch_render(const RenderParams &p, bool count, int cull, int num_sms, cudaStream_t stream);
+// one_plus_one: the scene has exactly one directional and one point light (specialised kernel flavour)
+void launch_render(const RenderParams &p, bool count, int cull, bool one_plus_one, int num_sms, cudaStream_t stream);
 int render_ctas_per_sm();
 size_t render_scratch_bytes(int num_sms);   // RenderParams::sample_scratch must be at least this big
 unsigned long long run_selftest_division(unsigned long long seed, int ctas, int iters, unsigned long long *d_scratch, cudaStream_t stream);

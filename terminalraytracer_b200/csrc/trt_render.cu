@@ -466,7 +466,7 @@ __device__ __forceinline__ void setup_closest_query(Query &qy, const d3 &o, cons
 // reference's work counters); otherwise the certificate-guided one.  COUNT with CULL != 0 runs BOTH and reports any
 // disagreement of the final answers in CTR_CULL_VIOLATIONS (the on-device audit of the certificates, of the
 // survivor logic and of the host-precomputed primary-ray terms).
-template <bool COUNT, int CULL>
+template <bool COUNT, int CULL, int LIGHTS>
 #ifdef TRT_MAXNREG
 __global__ void __maxnreg__(TRT_MAXNREG) k_render(const RenderParams P)
 #else
@@ -490,7 +490,9 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
     const int tiles_y = (band_rows + TILE_H - 1) / TILE_H;
     const unsigned int num_tiles = (unsigned int)(tiles_x * tiles_y);
 
-    const int num_dir = c_scene.num_dir, num_point = c_scene.num_point;
+    // LIGHTS == 1: exactly one directional and one point light — the reference's own scene shape (TRT.c:1278-1287) —
+    // known at compile time: the query loop below unrolls into three specialised queries with no mode branches
+    const int num_dir = LIGHTS == 1 ? 1 : c_scene.num_dir, num_point = LIGHTS == 1 ? 1 : c_scene.num_point;
     const int num_spheres = c_scene.num_spheres;
     const d3 eye = mk3(c_scene.eye[0], c_scene.eye[1], c_scene.eye[2]);
     // tile certificates need the masks to fit; bigger scenes test every sphere exactly for primary rays
@@ -744,6 +746,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                     d3 lit = mk3(0.0, 0.0, 0.0);
                     bool done = false;
                     const int nq = num_dir + num_point + 1;
+#pragma unroll(LIGHTS == 1 ? 3 : 1)
                     for (int q = 0; q < nq; q++) {
                         // ---- set-up: warp-uniform branch on the kind of query ------------------------------------
                         bool run = true;
@@ -1107,8 +1110,9 @@ void upload_scene_constants(const DevScene &scene, const CullPair *pairs, int co
 template <bool COUNT, int CULL>
 static void prepare_kernel()
 {
-    // 58 KB of dynamic shared memory per CTA (ring + finished samples of 4 warps): above the 48 KB default
-    CK(cudaFuncSetAttribute(k_render<COUNT, CULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    // dynamic shared memory per CTA (the rings of 4 warps) may exceed the 48 KB default
+    CK(cudaFuncSetAttribute(k_render<COUNT, CULL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_render<COUNT, CULL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
 }
 
 int render_ctas_per_sm()
@@ -1118,7 +1122,7 @@ int render_ctas_per_sm()
         prepare_kernel<false, 0>(); prepare_kernel<false, 1>(); prepare_kernel<false, 2>();
         prepare_kernel<true, 0>(); prepare_kernel<true, 1>(); prepare_kernel<true, 2>();
         int n = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_render<false, 1>, CTA_THREADS, SMEM_BYTES));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_render<false, 1, 0>, CTA_THREADS, SMEM_BYTES));
         cached = n > 0 ? n : 1;
     }
     return cached;
@@ -1130,7 +1134,7 @@ size_t render_scratch_bytes(int num_sms)
     return (size_t)num_sms * (size_t)render_ctas_per_sm() * WARPS_PER_CTA * (size_t)(3 * TILE_SAMPLES) * sizeof(double);
 }
 
-void launch_render(const RenderParams &p, bool count, int cull, int num_sms, cudaStream_t stream)
+void launch_render(const RenderParams &p, bool count, int cull, bool one_plus_one, int num_sms, cudaStream_t stream)
 {
     CK(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), stream));
     const int band_rows = p.row1 - p.row0;
@@ -1141,15 +1145,22 @@ void launch_render(const RenderParams &p, bool count, int cull, int num_sms, cud
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     dim3 g((unsigned)grid), b(CTA_THREADS);
+    // 12 flavours: counting or not, certificates off / small scene / clustered scene, generic lights or exactly 1 + 1
+#define TRT_LAUNCH(COUNT, CULL) \
+    do { \
+        if (one_plus_one) k_render<COUNT, CULL, 1><<<g, b, SMEM_BYTES, stream>>>(p); \
+        else k_render<COUNT, CULL, 0><<<g, b, SMEM_BYTES, stream>>>(p); \
+    } while (0)
     if (count) {
-        if (cull == 1) k_render<true, 1><<<g, b, SMEM_BYTES, stream>>>(p);
-        else if (cull == 2) k_render<true, 2><<<g, b, SMEM_BYTES, stream>>>(p);
-        else k_render<true, 0><<<g, b, SMEM_BYTES, stream>>>(p);
+        if (cull == 1) TRT_LAUNCH(true, 1);
+        else if (cull == 2) TRT_LAUNCH(true, 2);
+        else TRT_LAUNCH(true, 0);
     } else {
-        if (cull == 1) k_render<false, 1><<<g, b, SMEM_BYTES, stream>>>(p);
-        else if (cull == 2) k_render<false, 2><<<g, b, SMEM_BYTES, stream>>>(p);
-        else k_render<false, 0><<<g, b, SMEM_BYTES, stream>>>(p);
+        if (cull == 1) TRT_LAUNCH(false, 1);
+        else if (cull == 2) TRT_LAUNCH(false, 2);
+        else TRT_LAUNCH(false, 0);
     }
+#undef TRT_LAUNCH
     CK(cudaGetLastError());
 }
 
