@@ -251,7 +251,7 @@ long long cert_check_rows(const trt_Scene *scene, int W, int H, int row0, int ro
     c.centre_l1 = trt_cert_round_up(centre_l1 * (1.0 + 1.0 / 1048576.0));
     c.scratch = (unsigned char *)malloc((size_t)(n > 0 ? n : 1));
     c.order = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
-    c.num_clusters = n > 64 ? (n + 31) / 32 : 0;          /* TRT_CLUSTER_MIN_SPHERES of the library */
+    c.num_clusters = n > 32 ? (n + 31) / 32 : 0;          /* TRT_CLUSTER_MIN_SPHERES of the library */
     c.cluster4 = (float *)malloc(sizeof(float) * 4 * (size_t)(c.num_clusters > 0 ? c.num_clusters : 1));
     c.sub4 = (float *)malloc(sizeof(float) * 16 * (size_t)(c.num_clusters > 0 ? c.num_clusters : 1));
     if (c.num_clusters) {

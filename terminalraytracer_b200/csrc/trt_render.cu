@@ -336,8 +336,9 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const Que
     const float2 neg1 = make_float2(-1.0f, -1.0f), shrink2 = make_float2(0.99999237060546875f, 0.99999237060546875f);
     int best_oi = -1;
     constexpr bool clustered = !CONST_RECORDS;
-    for (int base = 0; base < n; base += 32) {
-        const int cnt = min(32, n - base);
+    // small scenes (CONST_RECORDS: at most 32 spheres) are a single chunk: the loop and its index arithmetic fold away
+    for (int base = 0; base < (CONST_RECORDS ? 1 : n); base += 32) {
+        const int cnt = CONST_RECORDS ? n : min(32, n - base);
         // many-sphere scenes: the chunk is a cluster of the k-d order with a bounding ball, and four balls of 8 inside
         // it (trt_cert_cluster_miss): skip what no lane's ray can reach, and let every lane drop what its own ray cannot
         bool ball_missed = false;
@@ -497,7 +498,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
     const d3 eye = mk3(c_scene.eye[0], c_scene.eye[1], c_scene.eye[2]);
     // tile certificates need the masks to fit; bigger scenes test every sphere exactly for primary rays
     const bool tile_certs = CULL != 0 && num_spheres <= 32 * TMASK_WORDS;
-    const int mask_words = (num_spheres + 31) >> 5;
+    const int mask_words = CULL == 1 ? 1 : (num_spheres + 31) >> 5;   // small scenes: one word, loops over it fold away
     const float S_max = c_scene.filter_enabled ? c_scene.filter_centre_l1 : INFINITY;   // inf: every certificate ray unusable
 
     for (;;) {
