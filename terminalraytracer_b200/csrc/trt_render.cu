@@ -291,6 +291,23 @@ __device__ __noinline__ void query_reference(const RenderParams &P, const d3 &o,
     plane_exact_num<COUNT>(plane_numerator(o), o, d, closest, obj, t_hit, tally);
 }
 
+// exact tests of a lane's surviving spheres of one chunk, in index order (TRT.c:805-828 restricted to the survivors)
+struct ClosestHit { double closest, t_hit; int obj, index, best_oi; };
+template <bool CLUSTERED>
+static __device__ __noinline__ ClosestHit walk_survivors(const double4 *geom, const int *orig, unsigned int survivors, int base, d3 o, d3 d, ClosestHit h)
+{
+    const Tally<false> no_tally{nullptr};
+    const double a = dot(d, d);                  // TRT.c:646
+    const double two_a = 2.0 * a, four_a = 4.0 * a;
+    while (survivors) {
+        const int j = __ffs(survivors) - 1;
+        survivors &= survivors - 1;
+        const int oi = CLUSTERED ? __ldg(&orig[base + j]) : base + j;
+        sphere_exact<false, CLUSTERED>(ldg4(geom, base + j), base + j, oi, o, d, two_a, four_a, h.closest, h.obj, h.index, h.best_oi, h.t_hit, no_tally);
+    }
+    return h;
+}
+
 // ---- certificate-guided query ---------------------------------------------------------------------------
 // Float certificates (trt_cert.h) classify every sphere against the ray; only the spheres they cannot decide
 // are evaluated exactly, each lane walking its own survivors in index order (tie-breaking preserved).
@@ -412,14 +429,15 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const Que
         if (shadow && n > 32 && __all_sync(__activemask(), usable && blocked)) break;
         if (exact_tests) *exact_tests += (unsigned int)__popc(survivors);
         // pass 2 (double, exact): each lane walks its own survivors in index order
-        while (TRT_UNLIKELY(survivors != 0)) {
-            const int j = __ffs(survivors) - 1;
-            survivors &= survivors - 1;
-            // a = d.d of TRT.c:646 is evaluated here, per exact test: survivors are rare (0.06-0.3 per query)
-            const double a = dot(d, d);
-            const double two_a = 2.0 * a, four_a = 4.0 * a;
-            sphere_exact<false, clustered>(ldg4(P.sphere_geom, base + j), base + j, reference_index<clustered>(P, base + j), o, d, two_a, four_a, closest, obj, index,
-                                best_oi, t_hit, no_tally);
+        if (TRT_UNLIKELY(survivors != 0)) {
+            // out of line: three unrolled queries would each carry a copy of the exact test, and the kernel's hot code
+            // has to fit the instruction cache (no_instruction was 20 % of the stall samples with the copies inline)
+            const ClosestHit h = walk_survivors<clustered>(P.sphere_geom, P.sphere_orig, survivors, base, o, d, ClosestHit{closest, t_hit, obj, index, best_oi});
+            closest = h.closest;
+            t_hit = h.t_hit;
+            obj = h.obj;
+            index = h.index;
+            best_oi = h.best_oi;
         }
     }
     blocked = blocked && usable && shadow;
