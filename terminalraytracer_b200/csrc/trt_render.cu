@@ -515,9 +515,11 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
     const int num_spheres = c_scene.num_spheres;
     const d3 eye = mk3(c_scene.eye[0], c_scene.eye[1], c_scene.eye[2]);
     // tile certificates need the masks to fit; bigger scenes test every sphere exactly for primary rays
-    const bool tile_certs = CULL != 0 && num_spheres <= 32 * TMASK_WORDS;
+    const bool tile_certs = CULL == 1 || (CULL == 2 && num_spheres <= 32 * TMASK_WORDS);   // compile-time true for small scenes
     const int mask_words = CULL == 1 ? 1 : (num_spheres + 31) >> 5;   // small scenes: one word, loops over it fold away
-    const float S_max = c_scene.filter_enabled ? c_scene.filter_centre_l1 : INFINITY;   // inf: every certificate ray unusable
+    // certificates on (CULL != 0: the host only picks these flavours when the scene's magnitudes are inside the range the error
+    // bounds hold for, DevScene::filter_enabled) or off (inf: every certificate ray unusable) is a compile-time property here
+    const float S_max = CULL != 0 ? c_scene.filter_centre_l1 : INFINITY;
 
     for (;;) {
         unsigned int tile = 0;
@@ -553,7 +555,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                 bool keep = false;
                 if (i < num_spheres) {
                     const float4 g = __ldg(&P.sphere_cull[i]);
-                    keep = !(c_scene.filter_enabled && trt_cert_tile_sphere_miss(cam.ex, cam.ey, cam.ez, Dx, Dy, Dz, h, g.x, g.y, g.z, g.w, S));
+                    keep = !(CULL != 0 && trt_cert_tile_sphere_miss(cam.ex, cam.ey, cam.ez, Dx, Dy, Dz, h, g.x, g.y, g.z, g.w, S));
                 }
                 const unsigned int m = __ballot_sync(0xffffffffu, keep);
                 any_sphere |= m;
@@ -564,14 +566,14 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
             const float bxn = fmaf(cam.bx[2], gn[2], fmaf(cam.bx[1], gn[1], cam.bx[0] * gn[0]));
             const float byn = fmaf(cam.by[2], gn[2], fmaf(cam.by[1], gn[1], cam.by[0] * gn[0]));
             const float scale = (fabsf(Dx) + fabsf(Dy) + fabsf(Dz) + 2.0f * h) * c_scene.ground_normal_l1;
-            const int sgn = c_scene.filter_enabled ? trt_cert_tile_plane_sign(dn, bxn, byn, hx, hy, scale) : 0;
+            const int sgn = CULL != 0 ? trt_cert_tile_plane_sign(dn, bxn, byn, hx, hy, scale) : 0;
             // numerator < 0 with every denominator > 0 (or the mirror image): t < 0 for every primary ray of the tile
             tile_ground_miss = (c_scene.prim_num_sign < 0 && sgn > 0) || (c_scene.prim_num_sign > 0 && sgn < 0);
 
             // ---- patch certificates: no sphere in reach of the primary rays => every hit of this tile's primary rays
             // is a ground hit inside a ball (trt_cert_patch_ball); decide once which spheres its shadow and bounce
             // rays can reach (lane = sphere), instead of classifying every sphere for every ray
-            if (any_sphere == 0 && !tile_ground_miss && num_spheres <= PATCH_MAX_SPHERES && c_scene.prim_num_sign != 0 && c_scene.filter_enabled) {
+            if (any_sphere == 0 && !tile_ground_miss && (CULL == 1 || num_spheres <= PATCH_MAX_SPHERES) && c_scene.prim_num_sign != 0) {
                 trt_cert_ball ball;
                 trt_cert_patch_ball(&cam, Dx, Dy, Dz, hx, hy, c_scene.prim_num_f, gn[0], gn[1], gn[2], S, &ball);
 #ifdef TRT_NO_PATCH
