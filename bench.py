@@ -47,8 +47,9 @@ def workload_config(n_gpus):
                     f"10 samples/pixel, bounce limit 10, skybox {SKYBOX} (synthetic 1024^2 x 6 stand-in: the reference's "
                     f"milky_way assets are not in its checkout), orbit pose t={T_POSE}s",
         "width": WIDTH, "height": HEIGHT, "samples_per_pixel": 10, "bounce_limit": 10, "skybox": SKYBOX,
-        "sharding": (f"cost-weighted contiguous row-bands x{n_gpus}; every rank writes its encoded bytes into rank 0's stream over NVLink "
-                     f"peer memory (70% of a band is pushed while its last 30% renders), NCCL barrier") if n_gpus > 1 else "single GPU",
+        "sharding": (f"cost-weighted contiguous row-bands x{n_gpus} (1/8-resolution cost pre-pass, then feedback from the ranks' measured K1 "
+                     f"times); every rank writes its encoded bytes into rank 0's stream over NVLink peer memory (70% of a band is pushed "
+                     f"while its last 30% renders); one small NCCL all-gather (the K1 times) ends the step") if n_gpus > 1 else "single GPU",
         "l2": "no explicit flush: each step writes 133 MB of cells + 829 MB of stream (> 126 MB L2); inputs (scene 1 KB, "
               "skybox 25 MB) are meant to stay cache resident, the kernel is ALU-bound",
     }
@@ -205,14 +206,11 @@ def main():
     # cost-weighted row bands (sky rows are ~5x cheaper than sphere/ground rows): every rank runs the same
     # deterministic 1/8-resolution pre-pass and derives the same bands; untimed, once per scene
     weights = rd.estimate_row_costs(sc) if world > 1 else None
-    # N > 1: every rank pushes its encoded pieces into rank 0's stream over NVLink peer memory while its next piece renders
-    pipe = pipeline.FramePipeline(rd, width, height, rank, world, row_weights=weights, peer=world > 1, pieces=(0.7, 0.3))
+    # N > 1: every rank pushes its encoded pieces into rank 0's stream over NVLink peer memory while its next piece renders;
+    # the collective that ends a step carries the ranks' K1 times and the next step's bands follow from them (adapt)
+    pipe = pipeline.FramePipeline(rd, width, height, rank, world, row_weights=weights, peer=world > 1, pieces=(0.7, 0.3), adapt=world > 1)
     stream = torch.cuda.current_stream()
-    rows = pipe.row1 - pipe.row0
 
-    # ---- algorithmic flops of this rank's band (untimed counting launch of the same kernel) ------------
-    rd.set_scene(sc)
-    counters, band_flops = rd.count_rows(width, height, pipe.row0, pipe.row1)
     peaks = rd.measure_peaks() if rank == 0 else None
 
     # ---- device-resident steps ------------------------------------------------------------------------
@@ -241,6 +239,12 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_total = t_begin.elapsed_time(t_end)
     k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / max(args.steps, 1)   # all K1 launches of a step (one per piece)
+    k1_launches = len(k1_events)
+    final_bands = list(pipe.bands)
+
+    # ---- algorithmic flops of this rank's band (untimed counting launch of the same kernel) ------------
+    rd.set_scene(sc)
+    counters, band_flops = rd.count_rows(width, height, pipe.row0, pipe.row1)
 
     # N > 1: the assembled stream must be byte-identical to a single-GPU render of the same frame (untimed check)
     stream_ok = None
@@ -257,11 +261,13 @@ def main():
 
     # encoder alone (rank 0's band), for its HBM roofline
     enc_ms = None
+    rows = pipe.row1 - pipe.row0
+    enc_src = pipe.quant.data_ptr() + (pipe.row0 - pipe.base_row) * width * 4
     if rank == 0 and rows > 0:
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ea.record(stream)
         for _ in range(5):
-            rd.encode_rows_quant(pipe.quant.data_ptr(), width, rows, pipe.stream.data_ptr(), abi.HOME_BYTES)
+            rd.encode_rows_quant(enc_src, width, rows, pipe.stream.data_ptr(), abi.HOME_BYTES)
         eb.record(stream)
         torch.cuda.synchronize()
         enc_ms = ea.elapsed_time(eb) / 5
@@ -269,20 +275,23 @@ def main():
     # ---- end-to-end steps through the host-facing call ----------------------------------------------------
     total_bytes = abi.stream_bytes(width, height)
     scene_bytes = C.sizeof(abi.Scene) + C.sizeof(abi.Sphere) * sc.c.num_spheres + C.sizeof(abi.DirectionalLight) + C.sizeof(abi.PointLight)
-    host_out = torch.empty(total_bytes, dtype=torch.uint8).pin_memory() if (rank == 0 and world > 1) else None
+    host_pipe = shared = None
+    if world > 1:
+        # the stream is wanted in host memory: every rank copies its own bands into one shared page-locked buffer over
+        # its own PCIe link (no device-side gather); bands start from the converged ones of the device-resident steps
+        shared = pipeline.SharedHostStream(rd, total_bytes, rank, world)
+        host_pipe = pipeline.FramePipeline(rd, width, height, rank, world, row_weights=pipe.weights, pieces=(0.7, 0.3), adapt=True,
+                                           host_stream=shared.ptr)
 
     def e2e_step():
         if world == 1:
             rd.render_ansi(sc)       # trt_render_ansi: H2D scene, K1, K2, D2H stream into pinned memory, sync
         else:
-            out = pipe.render(sc)    # set_scene (H2D) + K1 + K2 + NCCL gather
-            if rank == 0:
-                host_out.copy_(out, non_blocking=True)
-            torch.cuda.synchronize()
+            host_pipe.render(sc)     # set_scene (H2D) + per piece K1, K2, D2H into the shared host stream + closing collective
 
     if world == 1:
         rd.use_stream(None)          # the plain C-ABI call runs on the library's own stream
-    for _ in range(2):
+    for _ in range(3):
         e2e_step()
     barrier()
     w0 = time.perf_counter()
@@ -290,18 +299,24 @@ def main():
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - w0
+    host_ok = None
+    if world > 1:
+        if rank == 0:
+            import hashlib
+            host_ok = hashlib.sha256(shared.array.tobytes()).hexdigest() == want
+        barrier()
 
     # ---- reduce over ranks ------------------------------------------------------------------------------------
-    stats = torch.tensor([ms_total, k1_ms, e2e_s * 1e3, band_flops], dtype=torch.float64, device="cuda")
+    stats = torch.tensor([ms_total, k1_ms, e2e_s * 1e3, band_flops, k1_launches], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms_total, k1_ms_max, e2e_ms_total = mx[0].item(), mx[1].item(), mx[2].item()
-        frame_flops = sm[3].item()
+        frame_flops, k1_launches_all, k1_ms_mean = sm[3].item(), int(sm[4].item()), sm[1].item() / world
     else:
-        k1_ms_max, e2e_ms_total, frame_flops = k1_ms, e2e_s * 1e3, band_flops
+        k1_ms_max, e2e_ms_total, frame_flops, k1_launches_all, k1_ms_mean = k1_ms, e2e_s * 1e3, band_flops, k1_launches, k1_ms
 
     if rank == 0:
         rays_per_step = 10.0 * width * height
@@ -340,9 +355,14 @@ def main():
                 "traffic": NCU_DRAM_BYTES["k_encode"] if (world == 1 and (width, height) == (WIDTH, HEIGHT)) else None},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(total_bytes),
                     "ms_per_step": e2e_ms_total / args.steps,
-                    "call": "trt_render_ansi(scene,w,h,pinned_out,cap)" if world == 1 else "FramePipeline.render + D2H of the gathered stream"},
-            "gpu_launches": int(args.steps * (1 + 2 * len(pipe.pieces)) * world) if world > 1 else int(args.steps * 3),
+                    "call": "trt_render_ansi(scene,w,h,pinned_out,cap)" if world == 1 else
+                            "FramePipeline(host_stream=shared pinned buffer).render: every rank copies its bands to the host over its own PCIe link"},
+            # K1 + K2 per piece on every rank, plus rank 0's trt_stream_frame_device once per step
+            "gpu_launches": int(2 * k1_launches_all + args.steps),
             "stream_identical_to_single_gpu": stream_ok,
+            "host_stream_identical_to_single_gpu": host_ok,
+            "bands": None if world == 1 else {"rows": final_bands, "k1_ms_max_rank": k1_ms_max, "k1_ms_mean_rank": k1_ms_mean,
+                                              "how": "1/8-resolution cost pre-pass, then feedback from the ranks' measured K1 times of the previous steps"},
             "clocks": clocks,
             "work_counters_rank0": {"trace_calls": counters[9], "sphere_tests": counters[0], "sky_lookups": counters[8],
                                     "bounce_iters": counters[12], "lighting_calls": counters[11]},
@@ -358,6 +378,7 @@ def main():
                           f"single thread as the reference is written, gcc -O3 -ffp-contract=off"}
         print(json.dumps(line))
     if world > 1:
+        shared.close()
         if rank != 0:
             pipe.close()             # importers release rank 0's buffer before rank 0 frees it
         dist.barrier()

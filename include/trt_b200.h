@@ -120,6 +120,12 @@ int trt_ipc_close(void *d_peer_ptr);
 /* after everything enqueued so far on trt_stream(): copy `bytes` from d_src (this GPU) to d_peer_dst (any GPU) */
 int trt_push_to_peer(void *d_peer_dst, const void *d_src, size_t bytes);
 int trt_peer_copies_wait(void);
+/* When the caller wants the stream in HOST memory (the buffer it fwrite()s, TRT.c:1171) the device-side gather is not
+ * needed at all: every rank maps the same host buffer (POSIX shared memory), page-locks its mapping with
+ * trt_host_register, and pushes its own bands there with trt_push_to_peer (the destination may be any address the
+ * device can reach) — N PCIe links carry the device-to-host transfer instead of rank 0's alone. */
+int trt_host_register(void *host_ptr, size_t bytes);
+int trt_host_unregister(void *host_ptr);
 
 /* Write the 6-byte home sequence at d_stream[0..5] and the 3 NUL bytes after the last row of a
  * width x height stream (TRT.c:1102, 1104, 1130). */

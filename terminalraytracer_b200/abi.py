@@ -8,6 +8,7 @@ BOUNCE_LIMIT = 10
 RAYS_PER_PIXEL = 10
 CELL_BYTES = 25
 HOME_BYTES = 6
+HOME = b"\x1b[0;0H"        # reset_str, TRT.c:1102
 TAIL_NULS = 3
 DEMO_SPHERES = 6
 NUM_COUNTERS = 32

@@ -967,6 +967,19 @@ int trt_peer_copies_wait(void)
     return 0;
 }
 
+int trt_host_register(void *host_ptr, size_t bytes)
+{
+    require_init("trt_host_register");
+    CK(cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+
+int trt_host_unregister(void *host_ptr)
+{
+    if (host_ptr) CK(cudaHostUnregister(host_ptr));
+    return 0;
+}
+
 // ---- small helpers for plain-C callers -----------------------------------------------------------------
 
 void *trt_device_alloc(size_t bytes)

@@ -34,6 +34,8 @@ SIGNATURES = {
     "trt_ipc_import": (C.c_void_p, [C.c_void_p]),
     "trt_ipc_close": (C.c_int, [C.c_void_p]),
     "trt_push_to_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "trt_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "trt_host_unregister": (C.c_int, [C.c_void_p]),
     "trt_peer_copies_wait": (C.c_int, []),
     "trt_set_scene": (C.c_int, [C.POINTER(abi.Scene)]),
     "trt_render_rows_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -14,29 +14,85 @@ class _DevicePointer:
         self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
 
 
+class SharedHostStream:
+    """A host buffer for the terminal stream that every rank of the node has mapped and page-locked: POSIX shared memory
+    (a file under /dev/shm, unlinked as soon as everybody has it open) + trt_host_register.  FramePipeline(host_stream=
+    self.ptr) lets each rank copy its own row bands there; rank 0 then holds the complete stream in `self.array`."""
+
+    def __init__(self, renderer, nbytes, rank=0, world_size=1, group=None):
+        import ctypes as C
+        import mmap
+        import os
+        import numpy as np
+        self.r, self.nbytes = renderer, int(nbytes)
+        box = [None]
+        if rank == 0:
+            box[0] = "/dev/shm/trt_b200_stream_%d_%x" % (os.getpid(), id(self) & 0xffffff)
+            fd = os.open(box[0], os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+            os.ftruncate(fd, self.nbytes)
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.broadcast_object_list(box, src=0, group=group)
+            if rank != 0:
+                fd = os.open(box[0], os.O_RDWR)
+        self.map = mmap.mmap(fd, self.nbytes)
+        os.close(fd)
+        if world_size > 1:
+            dist.barrier(group=group)
+        if rank == 0:
+            os.unlink(box[0])                 # the mappings keep the memory alive; nothing is left behind on a crash
+        self.array = np.frombuffer(self.map, dtype=np.uint8)
+        self.ptr = C.addressof(C.c_char.from_buffer(self.map))
+        self.r.L.trt_host_register(self.ptr, self.nbytes)
+
+    def close(self):
+        if self.ptr:
+            self.r.L.trt_host_unregister(self.ptr)
+            self.ptr = None
+            self.array = None     # the mmap itself is released with the object (ctypes keeps an export on it)
+
+
 class FramePipeline:
     """One big frame, row-band sharded across `world_size` ranks (BASELINE configs 1-3).
 
-    Exchange (the only one on the path): with `peer=True` and world_size > 1 every rank writes its encoded bytes
-    straight into rank 0's stream buffer over NVLink peer memory (CUDA IPC handle exchanged once through the process
-    group; copy-engine transfers, trt_push_to_peer), piece by piece while its next piece renders, and a barrier ends
-    the step.  With `peer=False` the bands are gathered with NCCL/gloo send-recv after the render (dist.gather_bands;
-    this is what the CPU tests exercise)."""
+    Exchange (the only one on the path), three forms:
+      * `peer=True`: every rank writes its encoded bytes straight into rank 0's DEVICE stream buffer over NVLink peer
+        memory (CUDA IPC handle exchanged once through the process group; copy-engine transfers, trt_push_to_peer), piece
+        by piece while its next piece renders, and a collective ends the step.
+      * `host_stream=<address>`: the terminal stream is wanted in HOST memory (what the caller fwrite()s).  The address is a
+        page-locked buffer every rank has mapped (shared memory + trt_host_register): each rank copies its own pieces
+        there over its own PCIe link, so the device-to-host transfer is spread over N links instead of funnelled through
+        rank 0's, and no device-side gather is needed at all.
+      * neither: the bands are gathered with NCCL/gloo send-recv after the render (dist.gather_bands; this is what the CPU
+        tests exercise).
+    `adapt=True` (with peer or host_stream): the collective that ends a step carries every rank's measured K1 time, and the
+    bands of the next step follow from it (sharding.reweight): the picture changes slowly from frame to frame, so after a
+    few frames the ranks finish together.  Bands only decide who renders which rows: the stream is byte-identical for any
+    split."""
 
-    def __init__(self, renderer, width, height, rank=0, world_size=1, row_weights=None, group=None, peer=False, pieces=(0.7, 0.3)):
+    def __init__(self, renderer, width, height, rank=0, world_size=1, row_weights=None, group=None, peer=False, pieces=(0.7, 0.3),
+                 adapt=False, host_stream=None):
         self.r = renderer
         self.width, self.height = width, height
         self.rank, self.world_size, self.group = rank, world_size, group
         self.device = torch.device("cuda", renderer.device)
-        self.bands = sharding.row_bands(height, world_size, row_weights)
-        self.row0, self.row1 = self.bands[rank]
-        rows = self.row1 - self.row0
-        self.peer = bool(peer) and world_size > 1
-        self.pieces = sharding.sub_bands(self.bands[rank], pieces if self.peer else 1, row_weights)
+        self.host_stream = int(host_stream) if host_stream else None
+        self.peer = bool(peer) and world_size > 1 and not self.host_stream
+        self.async_pieces = self.peer or bool(self.host_stream)
+        self.adapt = bool(adapt) and world_size > 1 and self.async_pieces
+        self.piece_fractions = pieces if self.async_pieces else 1
+        self.weights = None if row_weights is None else [float(x) for x in row_weights]
+        if self.adapt and self.weights is None:
+            self.weights = [1.0] * height
+        self._set_bands(sharding.row_bands(height, world_size, self.weights))
+        # with adaptive bands any rank may come to own any row: local buffers cover the frame and are indexed by row
+        self.base_row = 0 if self.adapt else self.row0
+        rows = height if self.adapt else self.row1 - self.row0
         self.quant = torch.empty(max(rows * width, 1) * 4, dtype=torch.uint8, device=self.device)
         self.stream_ptr = self.peer_base = None
+        self.k1_pairs = []
         total = abi.stream_bytes(width, height)
-        if rank == 0:
+        if rank == 0 and not self.host_stream:
             if self.peer:
                 # cudaMalloc'ed by the library (an IPC handle needs the base of an allocation), viewed as a torch tensor
                 self.stream_ptr = self.r.L.trt_device_alloc(total + 16)
@@ -47,6 +103,10 @@ class FramePipeline:
         else:
             self.stream = None
             self.band_bytes = torch.empty(max(rows * abi.row_bytes(width), 1), dtype=torch.uint8, device=self.device)
+        if self.host_stream and rank == 0:
+            import ctypes as C
+            C.memmove(self.host_stream, abi.HOME, abi.HOME_BYTES)               # ESC[0;0H, TRT.c:1144
+            C.memset(self.host_stream + total - abi.TAIL_NULS, 0, abi.TAIL_NULS)
         if self.peer:
             import ctypes as C
             import torch.distributed as dist
@@ -61,6 +121,11 @@ class FramePipeline:
                 self.peer_base = self.r.L.trt_ipc_import(handle)
         self.r.use_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _set_bands(self, bands):
+        self.bands = bands
+        self.row0, self.row1 = bands[self.rank]
+        self.pieces = sharding.sub_bands(bands[self.rank], self.piece_fractions, self.weights)
+
     def close(self):
         if self.peer_base:
             self.r.L.trt_ipc_close(self.peer_base)
@@ -71,36 +136,57 @@ class FramePipeline:
             self.stream_ptr = None
 
     def render_local(self, scene, k1_events=None):
-        """K1 + K2 for this rank's band, piece by piece (asynchronous); with peer=True every finished piece is pushed
-        into rank 0's stream.  k1_events: optional list receiving (start, end) torch events around every K1 launch."""
+        """K1 + K2 for this rank's band, piece by piece (asynchronous); with peer=True / host_stream every finished piece
+        is sent on its way while the next one renders.  k1_events: optional list receiving (start, end) torch events
+        around every K1 launch."""
         rb = abi.row_bytes(self.width)
         self.r.set_scene(scene)
-        if self.rank == 0:
+        if self.stream is not None:
             self.r.stream_frame(self.stream.data_ptr(), self.width, self.height)
+        timed = self.adapt or k1_events is not None
+        self.k1_pairs = []
         for (r0, r1) in self.pieces:
-            q = self.quant.data_ptr() + (r0 - self.row0) * self.width * 4
-            if k1_events is not None:
+            q = self.quant.data_ptr() + (r0 - self.base_row) * self.width * 4
+            if timed:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             self.r.render_rows_quant(self.width, self.height, r0, r1, q)
-            if k1_events is not None:
+            if timed:
                 e1.record()
-                k1_events.append((e0, e1))
-            if self.rank == 0:
+                self.k1_pairs.append((e0, e1))
+                if k1_events is not None:
+                    k1_events.append((e0, e1))
+            if self.stream is not None:
                 self.r.encode_rows_quant(q, self.width, r1 - r0, self.stream.data_ptr(), abi.HOME_BYTES + r0 * rb)
             else:
-                off = (r0 - self.row0) * rb
+                off = (r0 - self.base_row) * rb
                 self.r.encode_rows_quant(q, self.width, r1 - r0, self.band_bytes.data_ptr(), off)
-                if self.peer:
-                    self.r.L.trt_push_to_peer(self.peer_base + abi.HOME_BYTES + r0 * rb, self.band_bytes.data_ptr() + off, (r1 - r0) * rb)
+                dst = self.host_stream if self.host_stream else self.peer_base
+                if dst:
+                    self.r.L.trt_push_to_peer(dst + abi.HOME_BYTES + r0 * rb, self.band_bytes.data_ptr() + off, (r1 - r0) * rb)
 
     def gather(self):
-        if self.peer:
+        if self.async_pieces:
             import torch.distributed as dist
-            if self.rank != 0:
-                self.r.L.trt_peer_copies_wait()      # this rank's bytes have landed in rank 0's memory
-            dist.barrier(group=self.group)           # ... and so have everybody else's
-            return self.stream if self.rank == 0 else None
+            if self.stream is None:
+                self.r.L.trt_peer_copies_wait()      # this rank's bytes have landed (rank 0's memory / the host buffer)
+            if not self.adapt:
+                if self.world_size > 1:
+                    dist.barrier(group=self.group)   # ... and so have everybody else's
+                elif self.stream is not None:
+                    torch.cuda.current_stream(self.device).synchronize()
+                return self.stream
+            # the collective that ends the step doubles as the feedback channel: every rank's K1 time of this frame
+            if self.stream is not None:
+                torch.cuda.current_stream(self.device).synchronize()
+            where = self.device if dist.get_backend(self.group) == "nccl" else "cpu"
+            mine = torch.tensor([sum(a.elapsed_time(b) for a, b in self.k1_pairs)], dtype=torch.float32, device=where)
+            times = torch.empty(self.world_size, dtype=torch.float32, device=where)
+            dist.all_gather_into_tensor(times, mine, group=self.group)
+            self.k1_times = times.tolist()
+            self.weights = sharding.reweight(self.weights, self.bands, self.k1_times)
+            self._set_bands(sharding.row_bands(self.height, self.world_size, self.weights))
+            return self.stream
         band = None
         if self.rank != 0:
             n = (self.row1 - self.row0) * abi.row_bytes(self.width)
@@ -108,7 +194,8 @@ class FramePipeline:
         return tdist.gather_bands(self.stream, band, self.width, self.bands, self.rank, self.world_size, self.group)
 
     def render(self, scene, k1_events=None):
-        """Full step: returns the complete byte stream (device tensor) on rank 0, None elsewhere."""
+        """Full step: returns the complete byte stream (device tensor) on rank 0, None elsewhere (and None everywhere with
+        host_stream: the bytes are in the host buffer)."""
         self.render_local(scene, k1_events)
         return self.gather()
 

@@ -1,5 +1,7 @@
 """How the render path is split across GPUs: contiguous row bands of one frame, or
 whole frames of an animation by frame index.  Pure host logic, no CUDA, no torch."""
+import numpy as np
+
 from . import abi
 
 
@@ -22,21 +24,38 @@ def row_bands(height, world_size, weights=None):
         return bands
     if len(weights) != height:
         raise ValueError("need one weight per row")
-    total = float(sum(weights))
+    # running sums in row order (np.cumsum adds sequentially, so every rank gets the same doubles and the same cuts)
+    cs = np.cumsum(np.asarray(weights, dtype=np.float64))
+    total = float(cs[-1]) if height else 0.0
     if total <= 0:
         return row_bands(height, world_size)
-    bands, r, acc = [], 0, 0.0
+    bands, r = [], 0
     for i in range(world_size):
-        target = total * (i + 1) / world_size
-        r1 = r
-        while r1 < height and (acc + weights[r1] <= target or i == world_size - 1):
-            acc += weights[r1]
-            r1 += 1
-        # always leave enough rows for nobody to be forced negative; allow empty bands
-        bands.append((r, r1))
+        if i == world_size - 1:
+            r1 = height
+        else:
+            # the rows whose running sum stays within this band's share of the total cost
+            r1 = max(r, int(np.searchsorted(cs, total * (i + 1) / world_size, side="right")))
+        bands.append((r, r1))   # empty bands are allowed
         r = r1
-    bands[-1] = (bands[-1][0], height)
     return bands
+
+
+def reweight(weights, bands, times):
+    """Feedback for the next frame: scale the per-row cost estimates inside every band so that the band's sum equals the
+    time its rank measured for it (K1 milliseconds).  Bands derived from the result (row_bands) move rows from the slow
+    ranks to the fast ones; with a slowly changing picture — an orbit, or the same frame again — a few frames are enough
+    for the ranks to finish together.  Bands without a usable measurement keep their estimates (scaled like the rest)."""
+    w = np.array(weights, dtype=np.float64)
+    measured = [(r0, r1, float(t)) for (r0, r1), t in zip(bands, times) if r1 > r0 and t > 0 and float(w[r0:r1].sum()) > 0]
+    if not measured:
+        return w
+    # overall scale for the rows nobody measured: time per unit of estimated cost over the measured bands
+    scale = sum(t for _, _, t in measured) / sum(float(w[r0:r1].sum()) for r0, r1, _ in measured)
+    out = w * scale
+    for r0, r1, t in measured:
+        out[r0:r1] = w[r0:r1] * (t / float(w[r0:r1].sum()))
+    return out
 
 
 def sub_bands(band, pieces, weights=None):
@@ -48,21 +67,16 @@ def sub_bands(band, pieces, weights=None):
     if r1 <= r0:
         return []
     n = r1 - r0
-    w = [1.0] * n if weights is None else [float(x) for x in weights[r0:r1]]
+    w = np.ones(n) if weights is None else np.asarray(weights[r0:r1], dtype=np.float64)
     fractions = [1.0 / int(pieces)] * int(pieces) if isinstance(pieces, int) else [float(f) for f in pieces]
-    total, norm = sum(w), sum(fractions)
+    cs = np.cumsum(w)
+    total, norm = float(cs[-1]), sum(fractions)
     if total <= 0 or norm <= 0:
         return [(r0, r1)]
-    out, start, acc, cut = [], 0, 0.0, 0.0
+    out, start, cut = [], 0, 0.0
     for k, f in enumerate(fractions):
         cut += f / norm
-        end = start
-        if k == len(fractions) - 1:
-            end = n
-        else:
-            while end < n and acc + w[end] <= total * cut:
-                acc += w[end]
-                end += 1
+        end = n if k == len(fractions) - 1 else max(start, int(np.searchsorted(cs, total * cut, side="right")))
         if end > start:
             out.append((r0 + start, r0 + end))
             start = end

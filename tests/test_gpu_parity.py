@@ -418,26 +418,38 @@ def test_gpu_orbit_sink_streams_frames_in_order(renderer, orc):
     assert list(got) == [0, 1, 2]
 
 
-def _peer_worker(rank, world, port, w, h, out_path):
+def _peer_worker(rank, world, port, w, h, out_path, mode):
     import torch
     import torch.distributed as dist
     from terminalraytracer_b200 import pipeline, renderer as R
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)   # plumbing only; the bytes travel through CUDA IPC
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # plumbing only; the bytes travel through CUDA IPC / shared memory
     rd = R.Renderer(0)
     try:
         sky = S.synthetic_cubemap("uv_gradient", 64)
         rd.upload_skybox(sky)
         sc = S.SceneData(w, h, sky).set_time(3.7)
         weights = rd.estimate_row_costs(sc)
-        pipe = pipeline.FramePipeline(rd, w, h, rank, world, row_weights=weights, peer=True, pieces=(0.6, 0.4))
-        for _ in range(2):                                          # twice: buffers and events are reused
+        shared = None
+        if mode == "host":
+            shared = pipeline.SharedHostStream(rd, abi.stream_bytes(w, h), rank, world)
+            pipe = pipeline.FramePipeline(rd, w, h, rank, world, row_weights=weights, pieces=(0.6, 0.4), adapt=True, host_stream=shared.ptr)
+        else:
+            pipe = pipeline.FramePipeline(rd, w, h, rank, world, row_weights=weights, peer=True, pieces=(0.6, 0.4), adapt=(mode == "peer_adapt"))
+        seen = set()
+        for _ in range(4):                                          # several frames: buffers and events are reused, bands move
+            seen.add(tuple(pipe.bands))
             stream = pipe.render(sc)
+            assert sum(r1 - r0 for r0, r1 in pipe.bands) == h and pipe.bands[0][0] == 0 and pipe.bands[-1][1] == h
         torch.cuda.synchronize()
         if rank == 0:
-            np.save(out_path, stream.cpu().numpy())
+            np.save(out_path, shared.array.copy() if shared else stream.cpu().numpy())
+            if mode != "peer":
+                assert len(pipe.k1_times) == world and min(pipe.k1_times) > 0
         dist.barrier()
+        if shared:
+            shared.close()
         if rank != 0:
             pipe.close()
         dist.barrier()
@@ -447,9 +459,12 @@ def _peer_worker(rank, world, port, w, h, out_path):
         dist.destroy_process_group()
 
 
-def test_gpu_peer_memory_gather_three_ranks(orc, tmp_path):
-    """the multi-GPU exchange (every rank writes its encoded pieces into rank 0's stream through a CUDA IPC mapping,
-    trt_push_to_peer) with three processes — on one device here, one per GPU in bench.py: same code, same bytes"""
+@pytest.mark.parametrize("mode", ["peer", "peer_adapt", "host"])
+def test_gpu_gather_three_ranks(orc, tmp_path, mode):
+    """the multi-GPU exchange with three processes — on one device here, one per GPU in bench.py: same code, same bytes.
+    peer: every rank writes its encoded pieces into rank 0's stream through a CUDA IPC mapping (trt_push_to_peer);
+    peer_adapt: the same with bands that follow the measured K1 times; host: every rank copies its bands into one shared,
+    page-locked host buffer (SharedHostStream)."""
     import socket
     import torch.multiprocessing as mp
     w, h = 150, 83
@@ -458,10 +473,29 @@ def test_gpu_peer_memory_gather_three_ranks(orc, tmp_path):
     port = sock.getsockname()[1]
     sock.close()
     out = str(tmp_path / "stream.npy")
-    mp.spawn(_peer_worker, args=(3, port, w, h, out), nprocs=3, join=True)
+    mp.spawn(_peer_worker, args=(3, port, w, h, out, mode), nprocs=3, join=True)
     sc = S.SceneData(w, h, S.synthetic_cubemap("uv_gradient", 64)).set_time(3.7)
     want = U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc))
     assert np.array_equal(np.load(out), want)
+
+
+def test_gpu_host_stream_single_rank(renderer, orc):
+    """FramePipeline(host_stream=...) with one rank: the pieces go device -> page-locked host buffer on the copy stream"""
+    from terminalraytracer_b200 import pipeline
+    w, h = 97, 41
+    sky = S.synthetic_cubemap("uv_gradient", 64)
+    renderer.upload_skybox(sky)
+    sc = S.SceneData(w, h, sky).set_time(1.3)
+    shared = pipeline.SharedHostStream(renderer, abi.stream_bytes(w, h))
+    try:
+        pipe = pipeline.FramePipeline(renderer, w, h, host_stream=shared.ptr, pieces=3)
+        for _ in range(2):
+            assert pipe.render(sc) is None
+        want = U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc))
+        assert np.array_equal(shared.array, want)
+    finally:
+        shared.close()
+        renderer.use_stream(None)
 
 
 # ---- full-size configs: size-independent properties + sampled rows against the oracle -----------------------

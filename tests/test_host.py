@@ -188,3 +188,53 @@ def test_sub_bands_partition_a_band_exactly():
     w = [1.0] * 50 + [9.0] * 50                     # the second half of the rows costs 9x more
     (a0, a1), (b0, b1) = sharding.sub_bands((0, 100), (0.5, 0.5), w)
     assert a0 == 0 and a1 == b0 and b1 == 100 and 70 <= a1 <= 80
+
+
+def test_reweight_feedback_balances_bands_within_a_few_frames():
+    """adaptive bands (FramePipeline adapt=True): a poor first estimate, then the ranks' measured times.  The true cost
+    profile is never seen row by row — only one total per band and frame — and the bands still converge."""
+    import numpy as np
+    rng = np.random.default_rng(7)
+    h, world = 4320, 8
+    rows = np.arange(h)
+    true = 1.0 + 4.0 * np.exp(-((rows - 2600) / 500.0) ** 2) + 2.0 * (rows > 3000)      # cheap sky on top, spheres, ground
+    weights = np.ones(h)                                                                 # knows nothing
+    imbalance = []
+    for frame in range(6):
+        bands = sharding.row_bands(h, world, weights)
+        assert bands[0][0] == 0 and bands[-1][1] == h and all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+        times = [float(true[r0:r1].sum()) * (1.0 + 0.01 * rng.standard_normal()) for r0, r1 in bands]   # 1 % timing noise
+        imbalance.append(max(times) / (sum(times) / world))
+        weights = sharding.reweight(weights, bands, times)
+    assert imbalance[0] > 1.5
+    assert imbalance[-1] < 1.05, imbalance
+
+
+def test_reweight_keeps_unmeasured_bands_and_handles_empty_ones():
+    import numpy as np
+    w = [1.0] * 10
+    out = sharding.reweight(w, [(0, 5), (5, 5), (5, 10)], [2.0, 0.0, 6.0])
+    assert np.allclose(out[:5].sum(), 2.0) and np.allclose(out[5:].sum(), 6.0)
+    out = sharding.reweight(w, [(0, 5), (5, 10)], [0.0, 0.0])          # nothing measured: unchanged
+    assert np.allclose(out, w)
+    out = sharding.reweight(w, [(0, 4), (4, 10)], [8.0, 0.0])          # rank 1 has no measurement: scaled like the rest
+    assert np.allclose(out[:4], 2.0) and np.allclose(out[4:], 2.0)
+
+
+def test_row_bands_numpy_cuts_match_the_sequential_definition():
+    import numpy as np
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        h, world = int(rng.integers(1, 300)), int(rng.integers(1, 9))
+        w = rng.random(h) * (rng.random(h) > 0.2)
+        want, r, acc, total = [], 0, 0.0, float(np.cumsum(w)[-1])
+        if total <= 0:
+            continue
+        for i in range(world):
+            r1 = r
+            while r1 < h and (acc + w[r1] <= total * (i + 1) / world or i == world - 1):
+                acc += w[r1]
+                r1 += 1
+            want.append((r, r1))
+            r = r1
+        assert sharding.row_bands(h, world, w) == want
