@@ -90,7 +90,7 @@ class FramePipeline:
         rows = height if self.adapt else self.row1 - self.row0
         self.quant = torch.empty(max(rows * width, 1) * 4, dtype=torch.uint8, device=self.device)
         self.stream_ptr = self.peer_base = None
-        self.k1_pairs = []
+        self.k1_span, self.k1_launches = None, 0
         total = abi.stream_bytes(width, height)
         if rank == 0 and not self.host_stream:
             if self.peer:
@@ -137,25 +137,26 @@ class FramePipeline:
 
     def render_local(self, scene, k1_events=None):
         """K1 + K2 for this rank's band, piece by piece (asynchronous); with peer=True / host_stream every finished piece
-        is sent on its way while the next one renders.  k1_events: optional list receiving (start, end) torch events
-        around every K1 launch."""
+        is sent on its way while the next one renders.  k1_events: optional list receiving one (start, end) pair of torch
+        events per call: start of the first K1 launch, end of the last."""
         rb = abi.row_bytes(self.width)
         self.r.set_scene(scene)
         if self.stream is not None:
             self.r.stream_frame(self.stream.data_ptr(), self.width, self.height)
+        # (Pieces on two alternating streams — the next piece's K1 filling the SMs that the tail of the previous one leaves
+        # idle — were measured: the tails are short, ~0.04 ms, and the persistent K1 of the next piece then keeps the
+        # previous piece's K2 and with it its transfer off the SMs until it ends.  One stream it is.)
         timed = self.adapt or k1_events is not None
-        self.k1_pairs = []
-        for (r0, r1) in self.pieces:
+        first = last = None
+        for i, (r0, r1) in enumerate(self.pieces):
             q = self.quant.data_ptr() + (r0 - self.base_row) * self.width * 4
-            if timed:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
+            if timed and first is None:
+                first = torch.cuda.Event(enable_timing=True)
+                first.record()
             self.r.render_rows_quant(self.width, self.height, r0, r1, q)
-            if timed:
-                e1.record()
-                self.k1_pairs.append((e0, e1))
-                if k1_events is not None:
-                    k1_events.append((e0, e1))
+            if timed and i == len(self.pieces) - 1:
+                last = torch.cuda.Event(enable_timing=True)
+                last.record()
             if self.stream is not None:
                 self.r.encode_rows_quant(q, self.width, r1 - r0, self.stream.data_ptr(), abi.HOME_BYTES + r0 * rb)
             else:
@@ -164,6 +165,11 @@ class FramePipeline:
                 dst = self.host_stream if self.host_stream else self.peer_base
                 if dst:
                     self.r.L.trt_push_to_peer(dst + abi.HOME_BYTES + r0 * rb, self.band_bytes.data_ptr() + off, (r1 - r0) * rb)
+        # K1 time of this rank and frame: from the start of the first piece to the end of the last one (includes the small K2s between)
+        self.k1_span = (first, last) if (first is not None and last is not None) else None
+        if k1_events is not None and self.k1_span:
+            k1_events.append(self.k1_span)
+        self.k1_launches += len(self.pieces)
 
     def gather(self):
         if self.async_pieces:
@@ -180,7 +186,7 @@ class FramePipeline:
             if self.stream is not None:
                 torch.cuda.current_stream(self.device).synchronize()
             where = self.device if dist.get_backend(self.group) == "nccl" else "cpu"
-            mine = torch.tensor([sum(a.elapsed_time(b) for a, b in self.k1_pairs)], dtype=torch.float32, device=where)
+            mine = torch.tensor([self.k1_span[0].elapsed_time(self.k1_span[1]) if self.k1_span else 0.0], dtype=torch.float32, device=where)
             times = torch.empty(self.world_size, dtype=torch.float32, device=where)
             dist.all_gather_into_tensor(times, mine, group=self.group)
             self.k1_times = times.tolist()
