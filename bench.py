@@ -35,9 +35,9 @@ sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT, SKYBOX, T_POSE = 7680, 4320, "milky_way", 3.7
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this workload on one GPU
-# (profiles/r01c_k1_k2_ncu_summary.txt): K1 19.6 MB + 118.3 MB (the 133 MB of quantised cells; scene, skybox and the sample
+# (profiles/r01f_k1_k2_ncu_summary.txt): K1 19.6 MB + 118.3 MB (the 133 MB of quantised cells; scene, skybox and the sample
 # scratch stay in L2), K2 132.8 MB + 770.8 MB at capture time (the rest of the 829 MB stream was still in L2)
-NCU_DRAM_BYTES = {"k_render": 19.616e6 + 118.257e6, "k_encode": 132.752e6 + 770.813e6}
+NCU_DRAM_BYTES = {"k_render": 16.610e6 + 106.326e6, "k_encode": 132.726e6 + 771.709e6}
 CPU_SAMPLE_W, CPU_SAMPLE_H = 480, 270   # same 16:9 framing, 1/256 of the pixels
 
 
@@ -347,7 +347,7 @@ def main():
             "roofline": {
                 "bound": "alu-fp32", "achieved": achieved, "peak": peak32, "unit": "TFLOP/s", "frac": achieved / peak32,
                 "traffic": NCU_DRAM_BYTES["k_render"] if (world == 1 and (width, height) == (WIDTH, HEIGHT)) else None,
-                "traffic_unit": "bytes of DRAM traffic per launch (ncu, profiles/r01c_k1_k2_ncu_summary.txt)",
+                "traffic_unit": "bytes of DRAM traffic per launch (ncu, profiles/r01f_k1_k2_ncu_summary.txt)",
                 "kernel": "k_render (K1)", "kernel_ms": k1_ms_max,
                 "algorithmic_flops_per_launch": frame_flops / world, "flops_per_primary_ray": frame_flops / rays_per_step,
                 "peak_source": "FFMA loop measured in this run by libtrt_b200 (trt_measure_fp32_tflops); MEASURED_PEAKS.json "
