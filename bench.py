@@ -48,8 +48,8 @@ def workload_config(n_gpus):
                     f"milky_way assets are not in its checkout), orbit pose t={T_POSE}s",
         "width": WIDTH, "height": HEIGHT, "samples_per_pixel": 10, "bounce_limit": 10, "skybox": SKYBOX,
         "sharding": (f"cost-weighted contiguous row-bands x{n_gpus} (1/8-resolution cost pre-pass, then feedback from the ranks' measured K1 "
-                     f"times); every rank writes its encoded bytes into rank 0's stream over NVLink peer memory (70% of a band is pushed "
-                     f"while its last 30% renders); one small NCCL all-gather (the K1 times) ends the step") if n_gpus > 1 else "single GPU",
+                     f"times); every rank's encoded bytes go into rank 0's stream over NVLink peer memory (see 'gather'); one small NCCL "
+                     f"all-gather (the K1 times) ends the step") if n_gpus > 1 else "single GPU",
         "l2": "no explicit flush: each step writes 133 MB of cells + 829 MB of stream (> 126 MB L2); inputs (scene 1 KB, "
               "skybox 25 MB) are meant to stay cache resident, the kernel is ALU-bound",
     }
@@ -172,6 +172,10 @@ def main():
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused", type=int, default=int(os.environ.get("TRT_BENCH_FUSED", "-1")),
+                    help="N > 1, device-resident gather: 1 = K1 stores the encoded tiles straight into rank 0's stream over NVLink (no K2, "
+                         "no copies), 0 = K1, K2 and copy-engine pushes piece by piece, -1 = by GPU count (measured: pieces win at 2 GPUs, "
+                         "14.8 vs 15.7 ms, the fused kernel at 8, 4.21 vs 4.38 ms)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -211,9 +215,11 @@ def main():
     # cost-weighted row bands (sky rows are ~5x cheaper than sphere/ground rows): every rank runs the same
     # deterministic 1/8-resolution pre-pass and derives the same bands; untimed, once per scene
     weights = rd.estimate_row_costs(sc) if world > 1 else None
-    # N > 1: every rank pushes its encoded pieces into rank 0's stream over NVLink peer memory while its next piece renders;
+    fused = (world >= 8) if args.fused < 0 else bool(args.fused)
+    # N > 1: every rank pushes its encoded pieces into rank 0's stream over NVLink peer memory while its next piece renders
+    # (or, fused: K1 itself stores every finished tile's bytes there);
     # the collective that ends a step carries the ranks' K1 times and the next step's bands follow from them (adapt)
-    pipe = pipeline.FramePipeline(rd, width, height, rank, world, row_weights=weights, peer=world > 1, pieces=(0.7, 0.3), adapt=world > 1)
+    pipe = pipeline.FramePipeline(rd, width, height, rank, world, row_weights=weights, peer=world > 1, pieces=(0.7, 0.3), adapt=world > 1, fused=fused)
     stream = torch.cuda.current_stream()
 
     peaks = rd.measure_peaks() if rank == 0 else None
@@ -288,7 +294,7 @@ def main():
         shared = pipeline.SharedHostStream(rd, total_bytes, rank, world)
         # (PCIe is ~15x slower than NVLink: more, geometrically shrinking pieces keep the exposed last copy short)
         host_pipe = pipeline.FramePipeline(rd, width, height, rank, world, row_weights=pipe.weights, pieces=(0.4, 0.3, 0.2, 0.1), adapt=True,
-                                           host_stream=shared.ptr)
+                                           host_stream=shared.ptr)     # (fused zero-copy stores over PCIe were measured slower: 11.5 vs 10.6 ms at 8 GPUs)
 
     def e2e_step():
         if world == 1:
@@ -364,8 +370,10 @@ def main():
                     "ms_per_step": e2e_ms_total / args.steps,
                     "call": "trt_render_ansi(scene,w,h,pinned_out,cap)" if world == 1 else
                             "FramePipeline(host_stream=shared pinned buffer).render: every rank copies its bands to the host over its own PCIe link"},
-            # K1 + K2 per piece on every rank, plus rank 0's trt_stream_frame_device once per step
-            "gpu_launches": int(2 * k1_launches_all + args.steps),
+            # K1 + K2 per piece on every rank (fused: K1 alone), plus rank 0's trt_stream_frame_device once per step
+            "gpu_launches": int((1 if (world > 1 and fused) else 2) * k1_launches_all + args.steps),
+            "gather": None if world == 1 else ("fused: K1 stores encoded tiles into rank 0's stream (NVLink peer memory)" if fused else
+                                               "pieces: K1, K2, copy-engine push per piece (NVLink peer memory)"),
             "stream_identical_to_single_gpu": stream_ok,
             "host_stream_identical_to_single_gpu": host_ok,
             "bands": None if world == 1 else {"rows": final_bands, "k1_ms_max_rank": k1_ms_max, "k1_ms_mean_rank": k1_ms_mean,

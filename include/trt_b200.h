@@ -107,6 +107,12 @@ int trt_encode_rows_device(const double *d_pixels, int width, int rows, char *d_
  * (4 bytes instead of 24) and the encoder reads those; the bytes produced are identical. */
 int trt_render_rows_quant_device(int width, int height, int row0, int row1, unsigned char *d_quant);
 int trt_encode_rows_quant_device(const unsigned char *d_quant, int width, int rows, char *d_bytes, size_t byte_offset);
+/* K1 with the encoder and the transfer fused in: renders rows [row0,row1) and stores every finished tile's cells as
+ * terminal bytes at their place in the stream that starts at `stream` (the rows' bytes only: home sequence and trailing
+ * NULs are trt_stream_frame_device's).  `stream` may be memory of this GPU, of a peer (trt_ipc_import: the bytes cross
+ * NVLink as the tiles finish, no separate copy) or page-locked host memory (trt_host_alloc_pinned / trt_host_register:
+ * zero-copy stores over PCIe).  Same bytes as buffered_draw_screen (TRT.c:1142-1172) produces for these rows. */
+int trt_render_rows_ansi_device(int width, int height, int row0, int row1, char *stream);
 
 /* ---- multi-GPU gather over NVLink peer memory (one process per GPU) ------------------------------------------------
  * The only exchange step of the path: every rank's encoded row band is written straight into rank 0's stream buffer.

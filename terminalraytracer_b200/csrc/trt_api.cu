@@ -426,6 +426,7 @@ RenderParams make_params(int width, int height, int row0, int row1, double *d_pi
     p.pixel_h_f = height > 0 ? (float)(g.scene.screen_height / height) : 0.f;
     p.pixels = d_pixels;
     p.quant = d_quant;
+    p.ansi = nullptr;
     p.sphere_geom = (const double4 *)g.sphere_geom.p;
     p.sphere_cull = (const float4 *)g.sphere_cull.p;
     p.sphere_prim = (const double4 *)g.sphere_prim.p;
@@ -604,6 +605,15 @@ int trt_render_rows_quant_device(int width, int height, int row0, int row1, unsi
 {
     require_init("trt_render_rows_quant_device");
     RenderParams p = make_params(width, height, row0, row1, nullptr, (uchar4 *)d_quant, false);
+    launch_render(p, false, cull_mode(), one_plus_one(), g.num_sms, g.stream);
+    return 0;
+}
+
+int trt_render_rows_ansi_device(int width, int height, int row0, int row1, char *stream)
+{
+    require_init("trt_render_rows_ansi_device");
+    RenderParams p = make_params(width, height, row0, row1, nullptr, nullptr, false);
+    p.ansi = (unsigned char *)stream;
     launch_render(p, false, cull_mode(), one_plus_one(), g.num_sms, g.stream);
     return 0;
 }

@@ -71,6 +71,7 @@ enum QueryMode : int {
 // consumed separately because a tile's first-generation hits share tile-level (patch) certificates.
 constexpr int PATCH_MAX_SPHERES = 32;                     // patch certificates: one mask word per query
 constexpr int PATCH_QUERIES = 2 * TRT_MAX_LIGHTS + 1;     // every directional light, every point light, the bounce
+constexpr int ANSI_STAGE_STRIDE = 208;                      // fused encode: 8 cells x 25 bytes + '\n', rounded up to 16
 struct WarpShared {
     // ring A
     double a_dx[QCAP], a_dy[QCAP], a_dz[QCAP];   // unit direction of the primary ray
@@ -87,6 +88,7 @@ struct WarpShared {
     int index[QCAP];
     unsigned int tmask[TMASK_WORDS];       // spheres the tile certificate could not rule out for primary rays
     unsigned int pmask[PATCH_QUERIES + 1]; // patch certificates: spheres each query of a first-generation hit can reach
+    unsigned int ansi_stage[TILE_H * ANSI_STAGE_STRIDE / 4];   // fused encode: one staging row of cells per tile row
 };
 constexpr size_t SMEM_TABLE_BYTES = 256 * sizeof(double);
 constexpr size_t SMEM_BYTES = SMEM_TABLE_BYTES + WARPS_PER_CTA * sizeof(WarpShared);
@@ -467,6 +469,51 @@ __device__ __forceinline__ d3 push_back(const d3 &o, const d3 &hit)
     return hit + back;
 }
 
+// ---- fused encode (RenderParams::ansi): a finished tile's cells as terminal bytes, stored where they belong -----------
+// The destination may be another GPU's memory (NVLink peer mapping) or page-locked host memory: every store instruction
+// should carry whole words to consecutive addresses.  Each warp keeps one staging row per tile row in shared memory,
+// pre-filled once with the constant part of the cells (pixel_str, TRT.c:1103) and the newline; a finished pixel only drops its
+// nine digits in (byte_to_digits, TRT.c:1134-1139), and the warp copies the rows out, 128 consecutive bytes per store
+// instruction, the byte shift between the word-aligned staging row and the destination done with a funnel shift.
+__constant__ unsigned char c_cell_template[TRT_CELL_BYTES + 3] = {0x1b, '[', '4', '8', ';', '2', ';', '0', '0', '0', ';', '0', '0', '0', ';',
+                                                                  '0', '0', '0', 'm', ' ', ' ', 0x1b, '[', '0', 'm', 0, 0, 0};
+
+__device__ __forceinline__ void stage_fill(unsigned char *stage, int lane)
+{
+    for (int i = lane; i < TILE_H * ANSI_STAGE_STRIDE; i += 32) {
+        const int pos = i % ANSI_STAGE_STRIDE;
+        stage[i] = pos < TILE_W * TRT_CELL_BYTES ? c_cell_template[pos % TRT_CELL_BYTES] : (unsigned char)(pos == TILE_W * TRT_CELL_BYTES ? '\n' : 0);
+    }
+}
+
+__device__ __forceinline__ void stage_digits(unsigned char *cell, unsigned int r, unsigned int g, unsigned int b)
+{
+    const unsigned int v[3] = {r, g, b};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const unsigned int h = v[c] / 100u, rest = v[c] - 100u * h, t = rest / 10u;
+        cell[7 + 4 * c] = (unsigned char)('0' + h);
+        cell[8 + 4 * c] = (unsigned char)('0' + t);
+        cell[9 + 4 * c] = (unsigned char)('0' + rest - 10u * t);
+    }
+}
+
+// n bytes from the word-aligned staging row to dst (any alignment)
+__device__ __forceinline__ void copy_row_bytes(unsigned char *dst, const unsigned char *stage, int n, int lane)
+{
+    const unsigned int s = (unsigned int)(reinterpret_cast<unsigned long long>(dst) & 3ull);
+    unsigned int *const dst_words = reinterpret_cast<unsigned int *>(dst - s);
+    const unsigned int *const src = reinterpret_cast<const unsigned int *>(stage);
+    // destination word j = staging bytes [4j - s, 4j - s + 4): the upper s bytes of word j-1 and the lower 4-s of word j.
+    // Whole words first ...
+    const int j0 = s ? 1 : 0, j1 = (n + (int)s) >> 2;
+    for (int j = j0 + lane; j < j1; j += 32) dst_words[j] = __funnelshift_rc(j > 0 ? src[j - 1] : 0u, src[j], 8u * (4u - s));
+    // ... then the at most three bytes before the first and after the last of them
+    const int head = s ? min(4 - (int)s, n) : 0, tail = j1 > j0 ? (n + (int)s) & 3 : (j1 >= j0 ? n - head : 0);
+    if (lane < head) dst[lane] = stage[lane];
+    if (lane < tail) dst[n - tail + lane] = stage[n - tail + lane];
+}
+
 // Q_CLOSEST query set-up for a ray with a double unit direction; S0 = |o|_1 + max centre |.|_1 (inf: unusable)
 __device__ __forceinline__ void setup_closest_query(Query &qy, const d3 &o, const d3 &d, float S0)
 {
@@ -501,6 +548,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     WarpShared &W = reinterpret_cast<WarpShared *>(smem_raw + SMEM_TABLE_BYTES)[warp];
+    if (P.ansi) stage_fill(reinterpret_cast<unsigned char *>(W.ansi_stage), lane);
     // finished samples of the current tile, [channel][k * 32 + pixel lane]: written once, read once at the end of
     // the tile by the pixel's lane -> parked in an L2-resident per-warp slice of global memory, not in shared memory
     double *const res = P.sample_scratch + (size_t)(blockIdx.x * WARPS_PER_CTA + warp) * (size_t)(3 * TILE_SAMPLES);
@@ -948,8 +996,8 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
         // ---- per pixel: add the samples in order, average, store (TRT.c:1063-1066) ---------------------------
         __threadfence_block();    // the samples were written by other lanes of this warp
         __syncwarp();
+        d3 average = mk3(0.0, 0.0, 0.0);
         if (valid) {
-            d3 average = mk3(0.0, 0.0, 0.0);
 #pragma unroll
             for (int k = 0; k < TRT_RAYS_PER_PIXEL; k++)
                 average = average + mk3(__ldcg(&res[0 * TILE_SAMPLES + k * 32 + lane]), __ldcg(&res[1 * TILE_SAMPLES + k * 32 + lane]),
@@ -970,6 +1018,28 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                 q.z = (unsigned char)x86_int(average.z * 255);
                 q.w = 0;
                 P.quant[pix] = q;
+            }
+        }
+        if (P.ansi) {
+            unsigned char *const stage = reinterpret_cast<unsigned char *>(W.ansi_stage);
+            static_assert(TILE_W * TRT_CELL_BYTES + 1 <= ANSI_STAGE_STRIDE - 4, "a tile row, its newline and the word read past it");
+            const int cols = min(TILE_W, P.width - tx * TILE_W);
+            const bool row_end = tx == tiles_x - 1, narrow = row_end && cols < TILE_W;
+            if (valid) {
+                // the quantisation of buffered_draw_screen, TRT.c:1157-1163: truncation toward zero
+                unsigned char *const cell = stage + (lane >> 3) * ANSI_STAGE_STRIDE + (lane & (TILE_W - 1)) * TRT_CELL_BYTES;
+                stage_digits(cell, (unsigned char)x86_int(average.x * 255), (unsigned char)x86_int(average.y * 255), (unsigned char)x86_int(average.z * 255));
+                if (narrow && (lane & (TILE_W - 1)) == cols - 1) cell[TRT_CELL_BYTES] = '\n';   // the row ends inside the tile (TRT.c:1125)
+            }
+            __syncwarp();
+            const size_t row_bytes = (size_t)TRT_CELL_BYTES * (size_t)P.width + 1;
+            const int n = cols * TRT_CELL_BYTES + (row_end ? 1 : 0);
+            for (int r = 0; r < TILE_H && ty * TILE_H + r < band_rows; r++)
+                copy_row_bytes(P.ansi + TRT_HOME_BYTES + (size_t)(P.row0 + ty * TILE_H + r) * row_bytes + (size_t)(tx * TILE_W) * TRT_CELL_BYTES,
+                               stage + r * ANSI_STAGE_STRIDE, n, lane);
+            if (narrow) {
+                __syncwarp();
+                if (lane < TILE_H) stage[lane * ANSI_STAGE_STRIDE + cols * TRT_CELL_BYTES] = 0x1b;   // back to the template
             }
         }
         __syncwarp();   // the sample slice and tmask are rewritten by the next tile

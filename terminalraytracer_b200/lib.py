@@ -42,6 +42,7 @@ SIGNATURES = {
     "trt_encode_rows_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "trt_render_rows_quant_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "trt_encode_rows_quant_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "trt_render_rows_ansi_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "trt_stream_frame_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "trt_estimate_row_costs": (C.c_int, [C.POINTER(abi.Scene), C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "trt_count_rows_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_longlong)]),

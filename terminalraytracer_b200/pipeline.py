@@ -65,13 +65,17 @@ class FramePipeline:
         rank 0's, and no device-side gather is needed at all.
       * neither: the bands are gathered with NCCL/gloo send-recv after the render (dist.gather_bands; this is what the CPU
         tests exercise).
+    `fused=True` (with peer or host_stream): no separate encode kernel and no copies at all — K1 encodes every finished tile
+    and stores its bytes directly at their place in the destination stream (trt_render_rows_ansi_device), rank 0's memory
+    over NVLink or the shared host buffer over PCIe: one kernel launch per rank and frame, the transfer rides along tile by
+    tile.
     `adapt=True` (with peer or host_stream): the collective that ends a step carries every rank's measured K1 time, and the
     bands of the next step follow from it (sharding.reweight): the picture changes slowly from frame to frame, so after a
     few frames the ranks finish together.  Bands only decide who renders which rows: the stream is byte-identical for any
     split."""
 
     def __init__(self, renderer, width, height, rank=0, world_size=1, row_weights=None, group=None, peer=False, pieces=(0.7, 0.3),
-                 adapt=False, host_stream=None):
+                 adapt=False, host_stream=None, fused=False):
         self.r = renderer
         self.width, self.height = width, height
         self.rank, self.world_size, self.group = rank, world_size, group
@@ -80,7 +84,8 @@ class FramePipeline:
         self.peer = bool(peer) and world_size > 1 and not self.host_stream
         self.async_pieces = self.peer or bool(self.host_stream)
         self.adapt = bool(adapt) and world_size > 1 and self.async_pieces
-        self.piece_fractions = pieces if self.async_pieces else 1
+        self.fused = bool(fused) and self.async_pieces
+        self.piece_fractions = pieces if (self.async_pieces and not self.fused) else 1
         self.weights = None if row_weights is None else [float(x) for x in row_weights]
         if self.adapt and self.weights is None:
             self.weights = [1.0] * height
@@ -88,6 +93,8 @@ class FramePipeline:
         # with adaptive bands any rank may come to own any row: local buffers cover the frame and are indexed by row
         self.base_row = 0 if self.adapt else self.row0
         rows = height if self.adapt else self.row1 - self.row0
+        if self.fused:
+            rows = 0                              # K1 stores the encoded bytes at their destination: no intermediate buffers
         self.quant = torch.empty(max(rows * width, 1) * 4, dtype=torch.uint8, device=self.device)
         self.stream_ptr = self.peer_base = None
         self.k1_span, self.k1_launches = None, 0
@@ -153,10 +160,16 @@ class FramePipeline:
             if timed and first is None:
                 first = torch.cuda.Event(enable_timing=True)
                 first.record()
-            self.r.render_rows_quant(self.width, self.height, r0, r1, q)
+            if self.fused:
+                dst = self.host_stream or (self.stream.data_ptr() if self.stream is not None else self.peer_base)
+                self.r.render_rows_ansi(self.width, self.height, r0, r1, dst)
+            else:
+                self.r.render_rows_quant(self.width, self.height, r0, r1, q)
             if timed and i == len(self.pieces) - 1:
                 last = torch.cuda.Event(enable_timing=True)
                 last.record()
+            if self.fused:
+                continue
             if self.stream is not None:
                 self.r.encode_rows_quant(q, self.width, r1 - r0, self.stream.data_ptr(), abi.HOME_BYTES + r0 * rb)
             else:
@@ -174,7 +187,9 @@ class FramePipeline:
     def gather(self):
         if self.async_pieces:
             import torch.distributed as dist
-            if self.stream is None:
+            if self.fused:
+                torch.cuda.current_stream(self.device).synchronize()   # K1 has ended: its stores have been performed
+            elif self.stream is None:
                 self.r.L.trt_peer_copies_wait()      # this rank's bytes have landed (rank 0's memory / the host buffer)
             if not self.adapt:
                 if self.world_size > 1:

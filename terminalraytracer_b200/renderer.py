@@ -91,6 +91,11 @@ class Renderer:
     def render_rows_quant(self, width, height, row0, row1, d_quant_ptr):
         self.L.trt_render_rows_quant_device(width, height, row0, row1, d_quant_ptr)
 
+    def render_rows_ansi(self, width, height, row0, row1, stream_ptr):
+        """K1 with the encoder fused in: the rows' terminal bytes are stored at their place in the stream at stream_ptr
+        (device, peer or page-locked host memory)."""
+        self.L.trt_render_rows_ansi_device(width, height, row0, row1, C.c_void_p(int(stream_ptr)))
+
     def encode_rows(self, d_pixels_ptr, width, rows, d_bytes_ptr, byte_offset):
         self.L.trt_encode_rows_device(d_pixels_ptr, width, rows, d_bytes_ptr, byte_offset)
 

@@ -432,11 +432,14 @@ def _peer_worker(rank, world, port, w, h, out_path, mode):
         sc = S.SceneData(w, h, sky).set_time(3.7)
         weights = rd.estimate_row_costs(sc)
         shared = None
-        if mode == "host":
+        fused = mode.endswith("fused")
+        if mode.startswith("host"):
             shared = pipeline.SharedHostStream(rd, abi.stream_bytes(w, h), rank, world)
-            pipe = pipeline.FramePipeline(rd, w, h, rank, world, row_weights=weights, pieces=(0.6, 0.4), adapt=True, host_stream=shared.ptr)
+            pipe = pipeline.FramePipeline(rd, w, h, rank, world, row_weights=weights, pieces=(0.6, 0.4), adapt=True, host_stream=shared.ptr,
+                                          fused=fused)
         else:
-            pipe = pipeline.FramePipeline(rd, w, h, rank, world, row_weights=weights, peer=True, pieces=(0.6, 0.4), adapt=(mode == "peer_adapt"))
+            pipe = pipeline.FramePipeline(rd, w, h, rank, world, row_weights=weights, peer=True, pieces=(0.6, 0.4), adapt=(mode != "peer"),
+                                          fused=fused)
         seen = set()
         for _ in range(4):                                          # several frames: buffers and events are reused, bands move
             seen.add(tuple(pipe.bands))
@@ -459,12 +462,13 @@ def _peer_worker(rank, world, port, w, h, out_path, mode):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["peer", "peer_adapt", "host"])
+@pytest.mark.parametrize("mode", ["peer", "peer_adapt", "host", "peer_fused", "host_fused"])
 def test_gpu_gather_three_ranks(orc, tmp_path, mode):
     """the multi-GPU exchange with three processes — on one device here, one per GPU in bench.py: same code, same bytes.
     peer: every rank writes its encoded pieces into rank 0's stream through a CUDA IPC mapping (trt_push_to_peer);
     peer_adapt: the same with bands that follow the measured K1 times; host: every rank copies its bands into one shared,
-    page-locked host buffer (SharedHostStream)."""
+    page-locked host buffer (SharedHostStream); *_fused: K1 itself stores the encoded tiles at the destination
+    (trt_render_rows_ansi_device), no encode kernel, no copies."""
     import socket
     import torch.multiprocessing as mp
     w, h = 150, 83
@@ -477,6 +481,42 @@ def test_gpu_gather_three_ranks(orc, tmp_path, mode):
     sc = S.SceneData(w, h, S.synthetic_cubemap("uv_gradient", 64)).set_time(3.7)
     want = U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc))
     assert np.array_equal(np.load(out), want)
+
+
+@pytest.mark.parametrize("size", [(97, 41), (64, 32), (7, 3), (150, 83), (8, 4), (1, 1), (33, 5)], ids=lambda s: f"{s[0]}x{s[1]}")
+def test_gpu_fused_encode_writes_the_reference_bytes(renderer, orc, size):
+    """trt_render_rows_ansi_device: K1 with the encoder fused in, band by band, at every byte alignment of the stream base,
+    into device memory and into page-locked host memory"""
+    import torch
+    from terminalraytracer_b200 import pipeline
+    w, h = size
+    sky = S.synthetic_cubemap("uv_gradient", 64)
+    renderer.upload_skybox(sky)
+    sc = S.SceneData(w, h, sky).set_time(2.1)
+    want = U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc))
+    total = abi.stream_bytes(w, h)
+    renderer.use_stream(torch.cuda.current_stream().cuda_stream)
+    shared = pipeline.SharedHostStream(renderer, total + 8)
+    try:
+        renderer.set_scene(sc)
+        cuts = sorted(set([0, h // 3, (2 * h) // 3 + 1 if h > 2 else h, h]))
+        for shift in range(4):
+            buf = torch.full((total + 8,), 0xEE, dtype=torch.uint8, device="cuda")
+            shared.array[:] = 0xEE
+            for base, is_host in ((buf.data_ptr() + shift, False), (shared.ptr + shift, True)):
+                for r0, r1 in zip(cuts, cuts[1:]):
+                    renderer.render_rows_ansi(w, h, r0, min(r1, h), base)
+            renderer.stream_frame(buf.data_ptr() + shift, w, h)
+            torch.cuda.synchronize()
+            got = buf.cpu().numpy()
+            assert np.array_equal(got[shift:shift + total], want), shift
+            assert (got[:shift] == 0xEE).all() and (got[shift + total:] == 0xEE).all()          # nothing outside the stream
+            host = np.array(shared.array)
+            assert np.array_equal(host[shift + 6:shift + total - 3], want[6:-3]), shift
+            assert (host[:shift + 6] == 0xEE).all() and (host[shift + total - 3:] == 0xEE).all()
+    finally:
+        shared.close()
+        renderer.use_stream(None)
 
 
 def test_gpu_host_stream_single_rank(renderer, orc):
