@@ -57,7 +57,20 @@ def main():
         rd.set_scene(sc)
         ctr, _ = rd.count_rows(sc.width, sc.height, 0, sc.height)
         same = np.array_equal(got, want)
-        stream_ok = np.array_equal(np.array(rd.render_ansi(sc)), U.oracle_stream(orc, want))
+        want_stream = U.oracle_stream(orc, want)
+        stream_ok = np.array_equal(np.array(rd.render_ansi(sc)), want_stream)
+        # the fused kernel (K1 encodes and stores its tiles), in two bands, at a random byte alignment of the stream
+        shift = int(rng.integers(0, 4))
+        d_stream = rd.L.trt_device_alloc(want_stream.size + 8)
+        cut = int(rng.integers(0, sc.height + 1))
+        rd.render_rows_ansi(sc.width, sc.height, 0, cut, d_stream + shift)
+        rd.render_rows_ansi(sc.width, sc.height, cut, sc.height, d_stream + shift)
+        rd.stream_frame(d_stream + shift, sc.width, sc.height)
+        fused = np.empty(want_stream.size, dtype=np.uint8)
+        rd.L.trt_copy_to_host(fused.ctypes.data_as(C.c_void_p), C.c_void_p(d_stream + shift), want_stream.size)
+        rd.synchronize()
+        rd.L.trt_device_free(d_stream)
+        stream_ok = stream_ok and np.array_equal(fused, want_stream)
         if not (same and stream_ok and ctr[28] == 0):
             bad += 1
         print("scene %3d: %3dx%-3d spheres %3d lights %d+%d  pixels %s  stream %s  audit disagreements %d" % (
