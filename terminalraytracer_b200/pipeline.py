@@ -98,6 +98,7 @@ class FramePipeline:
         self.quant = torch.empty(max(rows * width, 1) * 4, dtype=torch.uint8, device=self.device)
         self.stream_ptr = self.peer_base = None
         self.k1_span, self.k1_launches = None, 0
+        self.rebalance_above = 1.005          # adapt: move the cuts when the slowest rank is this far above the mean
         total = abi.stream_bytes(width, height)
         if rank == 0 and not self.host_stream:
             if self.peer:
@@ -205,8 +206,11 @@ class FramePipeline:
             times = torch.empty(self.world_size, dtype=torch.float32, device=where)
             dist.all_gather_into_tensor(times, mine, group=self.group)
             self.k1_times = times.tolist()
-            self.weights = sharding.reweight(self.weights, self.bands, self.k1_times)
-            self._set_bands(sharding.row_bands(self.height, self.world_size, self.weights))
+            # every rank sees the same numbers and takes the same decision; bands that are already level are left alone
+            busy = [t for t in self.k1_times if t > 0]
+            if busy and max(busy) * len(busy) > self.rebalance_above * sum(busy):
+                self.weights = sharding.reweight(self.weights, self.bands, self.k1_times)
+                self._set_bands(sharding.row_bands(self.height, self.world_size, self.weights))
             return self.stream
         band = None
         if self.rank != 0:
