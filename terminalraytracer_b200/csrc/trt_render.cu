@@ -480,6 +480,7 @@ __constant__ unsigned char c_cell_template[TRT_CELL_BYTES + 3] = {0x1b, '[', '4'
 
 __device__ __forceinline__ void stage_fill(unsigned char *stage, int lane)
 {
+#pragma unroll 1
     for (int i = lane; i < TILE_H * ANSI_STAGE_STRIDE; i += 32) {
         const int pos = i % ANSI_STAGE_STRIDE;
         stage[i] = pos < TILE_W * TRT_CELL_BYTES ? c_cell_template[pos % TRT_CELL_BYTES] : (unsigned char)(pos == TILE_W * TRT_CELL_BYTES ? '\n' : 0);
@@ -498,20 +499,32 @@ __device__ __forceinline__ void stage_digits(unsigned char *cell, unsigned int r
     }
 }
 
-// n bytes from the word-aligned staging row to dst (any alignment)
-__device__ __forceinline__ void copy_row_bytes(unsigned char *dst, const unsigned char *stage, int n, int lane)
+// `rows` staging rows of n bytes each to dst0, dst0 + row_bytes, ... (any alignment).  One compact loop (the code runs once
+// per tile and must stay small): 64 word slots per row, two trips of the warp per row.
+__device__ __forceinline__ void copy_tile_rows(unsigned char *dst0, size_t row_bytes, const unsigned char *stage, int n, int rows, int lane)
 {
-    const unsigned int s = (unsigned int)(reinterpret_cast<unsigned long long>(dst) & 3ull);
-    unsigned int *const dst_words = reinterpret_cast<unsigned int *>(dst - s);
-    const unsigned int *const src = reinterpret_cast<const unsigned int *>(stage);
-    // destination word j = staging bytes [4j - s, 4j - s + 4): the upper s bytes of word j-1 and the lower 4-s of word j.
-    // Whole words first ...
-    const int j0 = s ? 1 : 0, j1 = (n + (int)s) >> 2;
-    for (int j = j0 + lane; j < j1; j += 32) dst_words[j] = __funnelshift_rc(j > 0 ? src[j - 1] : 0u, src[j], 8u * (4u - s));
-    // ... then the at most three bytes before the first and after the last of them
-    const int head = s ? min(4 - (int)s, n) : 0, tail = j1 > j0 ? (n + (int)s) & 3 : (j1 >= j0 ? n - head : 0);
-    if (lane < head) dst[lane] = stage[lane];
-    if (lane < tail) dst[n - tail + lane] = stage[n - tail + lane];
+#pragma unroll 1
+    for (int idx = lane; idx < rows * 64; idx += 32) {
+        const int r = idx >> 6, j = idx & 63;
+        unsigned char *const dst = dst0 + (size_t)r * row_bytes;
+        const unsigned int s = (unsigned int)(reinterpret_cast<unsigned long long>(dst) & 3ull);
+        // destination word j (of the word-aligned address below dst) = staging bytes [4j - s, 4j - s + 4):
+        // the upper s bytes of staging word j-1 and the lower 4-s of word j
+        const int first = 4 * j - (int)s;
+        if (first < n && j < ANSI_STAGE_STRIDE / 4) {
+            const unsigned int *const src = reinterpret_cast<const unsigned int *>(stage + r * ANSI_STAGE_STRIDE);
+            const unsigned int v = __funnelshift_rc(j > 0 ? src[j - 1] : 0u, src[j], 8u * (4u - s));
+            unsigned char *const out = dst + first;
+            if (first >= 0 && first + 4 <= n) {
+                *reinterpret_cast<unsigned int *>(out) = v;
+            } else {
+                // the at most three bytes before the first whole word and after the last
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    if (first + b >= 0 && first + b < n) out[b] = (unsigned char)(v >> (8 * b));
+            }
+        }
+    }
 }
 
 // Q_CLOSEST query set-up for a ray with a double unit direction; S0 = |o|_1 + max centre |.|_1 (inf: unusable)
@@ -1034,9 +1047,8 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
             __syncwarp();
             const size_t row_bytes = (size_t)TRT_CELL_BYTES * (size_t)P.width + 1;
             const int n = cols * TRT_CELL_BYTES + (row_end ? 1 : 0);
-            for (int r = 0; r < TILE_H && ty * TILE_H + r < band_rows; r++)
-                copy_row_bytes(P.ansi + TRT_HOME_BYTES + (size_t)(P.row0 + ty * TILE_H + r) * row_bytes + (size_t)(tx * TILE_W) * TRT_CELL_BYTES,
-                               stage + r * ANSI_STAGE_STRIDE, n, lane);
+            copy_tile_rows(P.ansi + TRT_HOME_BYTES + (size_t)(P.row0 + ty * TILE_H) * row_bytes + (size_t)(tx * TILE_W) * TRT_CELL_BYTES, row_bytes,
+                           stage, n, min(TILE_H, band_rows - ty * TILE_H), lane);
             if (narrow) {
                 __syncwarp();
                 if (lane < TILE_H) stage[lane * ANSI_STAGE_STRIDE + cols * TRT_CELL_BYTES] = 0x1b;   // back to the template
