@@ -300,7 +300,7 @@ long long cert_check_rows(const trt_Scene *scene, int W, int H, int row0, int ro
         for (int tx = 0; tx < W; tx += TILE_W) {
             /* tile certificates, as the kernel evaluates them once per tile */
             float Dx, Dy, Dz, hx, hy;
-            trt_cert_tile_cone(&cc, tx, ty, TILE_W, TILE_H, W, H, &Dx, &Dy, &Dz, &hx, &hy);
+            trt_cert_tile_cone(&cc, cc.pw, cc.ph, tx, ty, TILE_W, TILE_H, &Dx, &Dy, &Dz, &hx, &hy);
             for (int i = 0; i < n; i++)
                 tile_miss[i] = (unsigned char)trt_cert_tile_sphere_miss(cc.ex, cc.ey, cc.ez, Dx, Dy, Dz, fmaf(hx, cc.nbx, hy * cc.nby), c.cull[4 * i], c.cull[4 * i + 1],
                                                                         c.cull[4 * i + 2], c.cull[4 * i + 3], S_eye);

@@ -236,7 +236,7 @@ typedef struct {
     float bx[3], by[3], bz[3];    /* camera basis                                                   */
     float nbx, nby;               /* |bx|_2, |by|_2 rounded up                                      */
     float sw, sh, dist;           /* screen width, height, distance                                 */
-    float pw, ph;                 /* sw / W, sh / H for the W x H screen being rendered (rounded to nearest) */
+    float pw, ph;                 /* sw / W, sh / H for the W x H screen being rendered (rounded to nearest): passed to trt_cert_tile_cone */
     float off_x, off_y;           /* largest sub-pixel offset in x and y, in pixels (TRT.c:992-993) */
 } trt_cert_camera;
 
@@ -245,12 +245,9 @@ typedef struct {
  * construction of TRT.c:987-1005 places them (top-left pixel corner + offset in [0, off] pixels; screen_y negated
  * before the offset is added).  Every sample direction of the tile is Dc + ex*bx + ey*by, |ex| <= hx, |ey| <= hy;
  * the sphere certificate takes h = hx*|bx| + hy*|by|. */
-TRT_HD void trt_cert_tile_cone(const trt_cert_camera *c, int col0, int row0, int tw, int th, int W, int H,
+TRT_HD void trt_cert_tile_cone(const trt_cert_camera *c, float pw, float ph, int col0, int row0, int tw, int th,
                                float *Dx, float *Dy, float *Dz, float *hx, float *hy)
 {
-    const float pw = c->pw, ph = c->ph;
-    (void)W;
-    (void)H;
     const float half_w = 0.5f * ((float)(tw - 1) + c->off_x), half_h = 0.5f * ((float)(th - 1) + c->off_y);
     const float scx = fmaf((float)col0 + half_w, pw, -0.5f * c->sw);
     const float syc = fmaf(-((float)(row0 + th - 1) - half_h), ph, 0.5f * c->sh);

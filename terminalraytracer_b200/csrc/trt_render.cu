@@ -603,11 +603,10 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
         bool tile_ground_miss = false;
         bool patch = false;       // patch certificates available for this tile's first-generation hits
         if (tile_certs) {
-            trt_cert_camera cam = c_scene.cam_f;
-            cam.pw = P.pixel_w_f;
-            cam.ph = P.pixel_h_f;
+            // (read in place: the fields become constant-bank operands; a local copy would be twenty loads per tile)
+            const trt_cert_camera &cam = c_scene.cam_f;
             float Dx, Dy, Dz, hx, hy;
-            trt_cert_tile_cone(&cam, tx * TILE_W, P.row0 + ty * TILE_H, TILE_W, TILE_H, P.width, P.height, &Dx, &Dy, &Dz, &hx, &hy);
+            trt_cert_tile_cone(&cam, P.pixel_w_f, P.pixel_h_f, tx * TILE_W, P.row0 + ty * TILE_H, TILE_W, TILE_H, &Dx, &Dy, &Dz, &hx, &hy);
             const float h = fmaf(hx, cam.nbx, hy * cam.nby);
             const float S = c_scene.eye_l1 + c_scene.filter_centre_l1;
             unsigned int any_sphere = 0;
