@@ -287,20 +287,27 @@ def main():
     # ---- end-to-end steps through the host-facing call ----------------------------------------------------
     total_bytes = abi.stream_bytes(width, height)
     scene_bytes = C.sizeof(abi.Scene) + C.sizeof(abi.Sphere) * sc.c.num_spheres + C.sizeof(abi.DirectionalLight) + C.sizeof(abi.PointLight)
-    host_pipe = shared = None
-    if world > 1:
+    host_pipe = shared = host_out = None
+    if world > 1 and pipeline.SharedHostStream.available(total_bytes, rank, world):
         # the stream is wanted in host memory: every rank copies its own bands into one shared page-locked buffer over
         # its own PCIe link (no device-side gather); bands start from the converged ones of the device-resident steps
         shared = pipeline.SharedHostStream(rd, total_bytes, rank, world)
         # (PCIe is ~15x slower than NVLink: more, geometrically shrinking pieces keep the exposed last copy short)
         host_pipe = pipeline.FramePipeline(rd, width, height, rank, world, row_weights=pipe.weights, pieces=(0.4, 0.3, 0.2, 0.1), adapt=True,
                                            host_stream=shared.ptr)     # (fused zero-copy stores over PCIe were measured slower: 11.5 vs 10.6 ms at 8 GPUs)
+    elif world > 1 and rank == 0:
+        host_out = torch.empty(total_bytes, dtype=torch.uint8).pin_memory()   # no room in /dev/shm: rank 0 copies the gathered stream out
 
     def e2e_step():
         if world == 1:
             rd.render_ansi(sc)       # trt_render_ansi: H2D scene, K1, K2, D2H stream into pinned memory, sync
-        else:
+        elif host_pipe is not None:
             host_pipe.render(sc)     # set_scene (H2D) + per piece K1, K2, D2H into the shared host stream + closing collective
+        else:
+            out = pipe.render(sc)    # device-side gather, then one D2H on rank 0
+            if rank == 0:
+                host_out.copy_(out, non_blocking=True)
+            torch.cuda.synchronize()
 
     if world == 1:
         rd.use_stream(None)          # the plain C-ABI call runs on the library's own stream
@@ -316,7 +323,8 @@ def main():
     if world > 1:
         if rank == 0:
             import hashlib
-            host_ok = hashlib.sha256(shared.array.tobytes()).hexdigest() == want
+            host_bytes = shared.array.tobytes() if shared is not None else host_out.numpy().tobytes()
+            host_ok = hashlib.sha256(host_bytes).hexdigest() == want
         barrier()
 
     # ---- reduce over ranks ------------------------------------------------------------------------------------
@@ -369,7 +377,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(total_bytes),
                     "ms_per_step": e2e_ms_total / args.steps,
                     "call": "trt_render_ansi(scene,w,h,pinned_out,cap)" if world == 1 else
-                            "FramePipeline(host_stream=shared pinned buffer).render: every rank copies its bands to the host over its own PCIe link"},
+                            ("FramePipeline(host_stream=shared pinned buffer).render: every rank copies its bands to the host over its own PCIe link"
+                             if shared is not None else "FramePipeline.render + D2H of the gathered stream on rank 0 (no room in /dev/shm)")},
             # K1 + K2 per piece on every rank (fused: K1 alone), plus rank 0's trt_stream_frame_device once per step
             "gpu_launches": int((1 if (world > 1 and fused) else 2) * k1_launches_all + args.steps),
             "gather": None if world == 1 else ("fused: K1 stores encoded tiles into rank 0's stream (NVLink peer memory)" if fused else
@@ -393,7 +402,8 @@ def main():
                           f"single thread as the reference is written, gcc -O3 -ffp-contract=off"}
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
-        shared.close()
+        if shared is not None:
+            shared.close()
         if rank != 0:
             pipe.close()             # importers release rank 0's buffer before rank 0 frees it
         dist.barrier()

@@ -19,6 +19,22 @@ class SharedHostStream:
     (a file under /dev/shm, unlinked as soon as everybody has it open) + trt_host_register.  FramePipeline(host_stream=
     self.ptr) lets each rank copy its own row bands there; rank 0 then holds the complete stream in `self.array`."""
 
+    @staticmethod
+    def available(nbytes, rank=0, world_size=1, group=None):
+        """True on every rank when /dev/shm can hold the buffer (rank 0 looks, everybody hears)."""
+        import os
+        box = [None]
+        if rank == 0:
+            try:
+                st = os.statvfs("/dev/shm")
+                box[0] = bool(st.f_bavail * st.f_frsize >= int(nbytes) + (64 << 20))
+            except OSError:
+                box[0] = False
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.broadcast_object_list(box, src=0, group=group)
+        return bool(box[0])
+
     def __init__(self, renderer, nbytes, rank=0, world_size=1, group=None):
         import ctypes as C
         import mmap

@@ -238,3 +238,10 @@ def test_row_bands_numpy_cuts_match_the_sequential_definition():
             want.append((r, r1))
             r = r1
         assert sharding.row_bands(h, world, w) == want
+
+
+def test_shared_host_stream_availability_probe():
+    """bench.py falls back to the rank-0 copy when /dev/shm cannot hold the stream"""
+    from terminalraytracer_b200 import pipeline
+    assert pipeline.SharedHostStream.available(1 << 16) in (True, False)
+    assert pipeline.SharedHostStream.available(1 << 62) is False
