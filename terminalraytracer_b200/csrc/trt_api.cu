@@ -664,9 +664,12 @@ int trt_estimate_row_costs(const trt_Scene *scene, int width, int height, double
     d_cost.reserve(sizeof(unsigned int) * (size_t)sh);
     d_quant.reserve(sizeof(uchar4) * (size_t)sw * (size_t)sh);
     CK(cudaMemsetAsync(d_cost.p, 0, sizeof(unsigned int) * (size_t)sh, g.stream));
-    RenderParams p = make_params(sw, sh, 0, sh, nullptr, (uchar4 *)d_quant.p, false);
+    // the counting flavour of K1 carries the per-row cost accounting (the production flavour has no branch for it)
+    g.counters.reserve(sizeof(unsigned long long) * TRT_NUM_COUNTERS);
+    CK(cudaMemsetAsync(g.counters.p, 0, sizeof(unsigned long long) * TRT_NUM_COUNTERS, g.stream));
+    RenderParams p = make_params(sw, sh, 0, sh, nullptr, (uchar4 *)d_quant.p, true);
     p.row_cost = (unsigned int *)d_cost.p;
-    launch_render(p, false, cull_mode(), one_plus_one(), g.num_sms, g.stream);
+    launch_render(p, true, cull_mode(), one_plus_one(), g.num_sms, g.stream);
     std::vector<unsigned int> cost((size_t)sh);
     CK(cudaMemcpyAsync(cost.data(), d_cost.p, sizeof(unsigned int) * (size_t)sh, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));

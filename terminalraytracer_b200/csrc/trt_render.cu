@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                     const int pix = (int)(meta & 31u), k = (int)((meta >> 5) & 15u);
                     int bounces = (int)((meta >> 9) & 15u);
                     const int obj = (int)((meta >> 13) & 3u);
-                    if (P.row_cost) atomicAdd(&P.row_cost[ty * TILE_H + (pix >> 3)], 25u);
+                    if (COUNT && P.row_cost) atomicAdd(&P.row_cost[ty * TILE_H + (pix >> 3)], 25u);   // (counting flavour: the cost pre-pass)
                     tally.add(CTR_LIGHTING_CALLS);
 
                     // the surface point (TRT.c:663-665 / 690-692), pushed back by EPSILON (871-874), and its normal (878)
@@ -1015,7 +1015,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                 average = average + mk3(__ldcg(&res[0 * TILE_SAMPLES + k * 32 + lane]), __ldcg(&res[1 * TILE_SAMPLES + k * 32 + lane]),
                                         __ldcg(&res[2 * TILE_SAMPLES + k * 32 + lane]));
             average = average * (1.0 / TRT_RAYS_PER_PIXEL);
-            if (P.row_cost) atomicAdd(&P.row_cost[brow], 50u);
+            if (COUNT && P.row_cost) atomicAdd(&P.row_cost[brow], 50u);
             const size_t pix = (size_t)brow * (size_t)P.width + (size_t)col;
             if (P.pixels) {
                 P.pixels[pix * 3 + 0] = average.x;
