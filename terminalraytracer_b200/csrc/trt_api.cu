@@ -243,6 +243,11 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
         s.dir[i].plane_denom = dot3_ref(s.dir[i].L, s.ground_normal);      // TRT.c:681 for this light's shadow rays
         s.dir[i].plane_possible = fabs(s.dir[i].plane_denom) > 0.00001 ? 1 : 0;
         for (int k = 0; k < 3; k++) s.dir[i].Lf[k] = (float)s.dir[i].L[k];
+        {
+            const float *f = s.dir[i].Lf;
+            const float dd = fmaf(f[2], f[2], fmaf(f[1], f[1], f[0] * f[0]));     // the float expression the certificates' bound assumes
+            s.dir[i].lf_unit = (dd > 0.99999f && dd < 1.00001f) ? 1 : 0;
+        }
     }
     double light_l1 = 0.0;
     for (int i = 0; i < s.num_point; i++) {
@@ -277,6 +282,7 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
         s.cam_f.off_y = float_round_up(my);
     }
     s.num_spheres = scene->num_spheres;
+    s.sphere_mask = scene->num_spheres >= 32 ? 0xffffffffu : ((1u << scene->num_spheres) - 1u);
     s.filter_in_const = s.num_spheres <= TRT_MAX_CONST_SPHERES ? 1 : 0;
     s.sky_dim = g.sky_dim;
     s.sky_face_stride = g.sky_face_stride;

@@ -393,7 +393,8 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const Que
         }
         // pass 1 (float, warp-uniform record addresses): classify the candidate spheres of this chunk — all of them,
         // or, for the first-generation hits of a patch tile, the few the patch certificate left (use_patch, n <= 32)
-        const unsigned int valid = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+        // (small scenes: the mask of existing spheres is a per-scene constant, host-evaluated)
+        const unsigned int valid = CONST_RECORDS ? c_scene.sphere_mask : (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u));
         const unsigned int candidates = use_patch ? (patch_mask & valid) : (valid & reachable);
         unsigned int survivors = 0;
         // two spheres per trip: the arithmetic of trt_cert_sphere2 (same operations, same rounding) on float pairs
@@ -428,7 +429,7 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const Que
         survivors &= own;
         if (shadow && usable && blocked) survivors = 0;
         // many-sphere scenes: once every lane's light is proven blocked the remaining chunks cannot change anything
-        if (shadow && n > 32 && __all_sync(__activemask(), usable && blocked)) break;
+        if (!CONST_RECORDS && shadow && n > 32 && __all_sync(__activemask(), usable && blocked)) break;
         if (exact_tests) *exact_tests += (unsigned int)__popc(survivors);
         // pass 2 (double, exact): each lane walks its own survivors in index order
         if (TRT_UNLIKELY(survivors != 0)) {
@@ -841,9 +842,8 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                             qy.mode = Q_DIR;
                             qy.d = mk3(Ld.L[0], Ld.L[1], Ld.L[2]);                  // unit(-direction), TRT.c:903-904
                             qy.rf.dx = Ld.Lf[0]; qy.rf.dy = Ld.Lf[1]; qy.rf.dz = Ld.Lf[2];
-                            const float dd = fmaf(qy.rf.dz, qy.rf.dz, fmaf(qy.rf.dy, qy.rf.dy, qy.rf.dx * qy.rf.dx));
                             qy.rf.slack_t = (32.0f * TRT_CERT_U) * S0;
-                            qy.rf.usable = (S0 < 1e15f) && (dd > 0.99999f) && (dd < 1.00001f);
+                            qy.rf.usable = (S0 < 1e15f) && Ld.lf_unit;     // |Lf| = 1 within 1e-5: checked once on the host
                             qy.plane_denom = Ld.plane_denom;
                         } else if (q < num_dir + num_point) {
                             const DevLightPoint &Lp = c_scene.point[q - num_dir];
