@@ -123,6 +123,14 @@ static void check_bounce(ctx_t *c, const trt_Ray *ray)
     const int gmiss = trt_cert_plane_miss(&r, c->gp[0], c->gp[1], c->gp[2], c->gn[0], c->gn[1], c->gn[2]);
     if (gmiss) c->st[ST_BOUNCE_GROUND_CULLED]++;
     if (gmiss && ghit) c->bad++;
+    {
+        /* the form the kernel's bounce queries use: the reference's own numerator (TRT.c:684-685), float denominator */
+        const double tx = s->ground.point.x - ray->origin.x, ty = s->ground.point.y - ray->origin.y, tz = s->ground.point.z - ray->origin.z;
+        const double num = tx * s->ground.normal.x + ty * s->ground.normal.y + tz * s->ground.normal.z;
+        const int gmiss_num = trt_cert_plane_miss_num(&r, num, c->gn[0], c->gn[1], c->gn[2]);
+        if (gmiss_num && ghit) c->bad++;
+        if (gmiss && !gmiss_num) c->bad++;          /* it must not be weaker than the all-float form */
+    }
 }
 
 /* closest hit among the SURVIVORS of the certificates (spheres in index order, strict <, then the ground), as

@@ -175,6 +175,18 @@ TRT_HD int trt_cert_plane_miss(const trt_cert_ray *r, float px, float py, float 
     return finite && ((num < -e_num && den > e_den) || (num > e_num && den < -e_den));
 }
 
+/* The same when the caller holds the numerator the reference itself computes, (p - o) . n in double with the reference's
+ * operations (TRT.c:684-685): its sign is exact, only the denominator's has to be certified.  A zero numerator gives t = 0,
+ * which is not > 1e-5: a miss as well. */
+TRT_HD int trt_cert_plane_miss_num(const trt_cert_ray *r, double num, float nx, float ny, float nz)
+{
+    const float den = fmaf(r->dz, nz, fmaf(r->dy, ny, r->dx * nx));
+    const float den_scale = fmaf(fabsf(r->dz), fabsf(nz), fmaf(fabsf(r->dy), fabsf(ny), fabsf(r->dx) * fabsf(nx)));
+    const float e_den = (16.0f * TRT_CERT_U) * den_scale;
+    const int finite = r->usable && (den_scale < 1e30f);
+    return finite && ((num < 0.0 && den > e_den) || (num > 0.0 && den < -e_den) || num == 0.0);
+}
+
 /*
  * Tile-level certificate for PRIMARY rays.  All sample rays of a pixel tile leave the eye with directions
  * D = Dc + e, |e| <= h (Dc: direction through the tile centre, un-normalised; h: half extent of the tile on the

@@ -90,7 +90,11 @@ struct WarpShared {
     unsigned int pmask[PATCH_QUERIES + 1]; // patch certificates: spheres each query of a first-generation hit can reach
     unsigned int ansi_stage[TILE_H * ANSI_STAGE_STRIDE / 4];   // fused encode: one staging row of cells per tile row
 };
-constexpr size_t SMEM_TABLE_BYTES = 256 * sizeof(double);
+// k/255 table, then (small scenes) the certificate records of the single chunk: 17 pairs x 32 B.  From shared memory a pair
+// is two 16-byte loads; from __constant__ memory with a run-time index it is four 8-byte ones.
+constexpr size_t SMEM_PAIRS_OFFSET = 256 * sizeof(double);
+constexpr int SMEM_PAIRS = TRT_CLUSTER_MIN_SPHERES / 2 + 1;
+constexpr size_t SMEM_TABLE_BYTES = SMEM_PAIRS_OFFSET + ((SMEM_PAIRS * sizeof(CullPair) + 127) & ~(size_t)127);
 constexpr size_t SMEM_BYTES = SMEM_TABLE_BYTES + WARPS_PER_CTA * sizeof(WarpShared);
 
 // (cx,cy,cz,r*r) of sphere i through the read-only path
@@ -333,7 +337,7 @@ struct Query {
 // CONST_RECORDS: small scene (at most TRT_CLUSTER_MIN_SPHERES spheres): records in __constant__, reference order, no
 // clusters.  Otherwise the scene is k-d-sorted with bounding balls and its records are read from global memory.
 template <bool CONST_RECORDS>
-__device__ __forceinline__ bool query_certified(const RenderParams &P, const Query &qy, const d3 &o, double num_g, bool use_patch,
+__device__ __forceinline__ bool query_certified(const RenderParams &P, const float4 *s_pairs, const Query &qy, const d3 &o, double num_g, bool use_patch,
                                                 unsigned int patch_mask, int &obj, int &index, double &t_hit, unsigned int *exact_tests)
 {
     const Tally<false> no_tally{nullptr};
@@ -401,7 +405,14 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const Que
 #pragma unroll 1
         for (unsigned int m = (candidates | (candidates >> 1)) & 0x55555555u; m; m &= m - 1) {
             const int j = __ffs(m) - 1;             // even: spheres base + j and base + j + 1
-            const CullPair g = CONST_RECORDS ? c_cull_pairs[(base + j) >> 1] : ldg_pair(P.cull_pairs, (base + j) >> 1);
+            CullPair g;
+            if (CONST_RECORDS) {
+                const float4 lo = s_pairs[j], hi = s_pairs[j + 1];      // pair j / 2 = float4 j and j + 1 (j is even)
+                g.cx = make_float2(lo.x, lo.y); g.cy = make_float2(lo.z, lo.w);
+                g.cz = make_float2(hi.x, hi.y); g.r = make_float2(hi.z, hi.w);
+            } else {
+                g = ldg_pair(P.cull_pairs, (base + j) >> 1);
+            }
             const float2 ocx = __fadd2_rn(g.cx, rp.nox), ocy = __fadd2_rn(g.cy, rp.noy), ocz = __fadd2_rn(g.cz, rp.noz);
             const float2 tc = __ffma2_rn(ocz, rp.dz, __ffma2_rn(ocy, rp.dy, __fmul2_rn(ocx, rp.dx)));
             const float2 ntc = __fmul2_rn(tc, neg1);
@@ -445,8 +456,8 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const Que
     }
     blocked = blocked && usable && shadow;
     if (qy.mode == Q_CLOSEST) {
-        if (!(usable && trt_cert_plane_miss(&qy.rf, c_scene.ground_point_f[0], c_scene.ground_point_f[1], c_scene.ground_point_f[2],
-                                            c_scene.ground_normal_f[0], c_scene.ground_normal_f[1], c_scene.ground_normal_f[2])))
+        // (num_g is the reference's own numerator for this origin: only the denominator's sign is left to the float certificate)
+        if (!(usable && trt_cert_plane_miss_num(&qy.rf, num_g, c_scene.ground_normal_f[0], c_scene.ground_normal_f[1], c_scene.ground_normal_f[2])))
             plane_exact_num<false>(num_g, o, d, closest, obj, t_hit, no_tally);
     } else if (qy.mode == Q_DIR) {
         // any hit blocks.  The ground (TRT.c:677-695): numerator and denominator are the reference's own doubles
@@ -556,6 +567,9 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_byte_to_unit = reinterpret_cast<double *>(smem_raw);   // k/255.0 (TRT.c:866), evaluated on the host in double
     for (int k = threadIdx.x; k < 256; k += CTA_THREADS) s_byte_to_unit[k] = P.byte_to_unit[k];
+    float4 *const s_pairs = reinterpret_cast<float4 *>(smem_raw + SMEM_PAIRS_OFFSET);
+    if (CULL == 1 && threadIdx.x < 2 * SMEM_PAIRS && threadIdx.x < 2 * (c_scene.num_spheres / 2 + 1))
+        s_pairs[threadIdx.x] = __ldg(reinterpret_cast<const float4 *>(P.cull_pairs) + threadIdx.x);
     __syncthreads();
 
     const Tally<COUNT> tally{P.counters};
@@ -896,7 +910,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                                 int obj3, index3;
                                 double t3;
                                 unsigned int exact = 0;
-                                const bool blocked3 = query_certified<CULL == 1>(P, qy, at, num_g, use_patch, use_patch ? W.pmask[q] : 0u, obj3, index3, t3,
+                                const bool blocked3 = query_certified<CULL == 1>(P, s_pairs, qy, at, num_g, use_patch, use_patch ? W.pmask[q] : 0u, obj3, index3, t3,
                                                                                  COUNT ? &exact : nullptr);
                                 if (COUNT) {
                                     // the audit: both paths must lead to the same decision / the same hit
@@ -1077,8 +1091,8 @@ __global__ void k_probe_trace(const RenderParams P, const double *__restrict__ r
     if (c_scene.filter_enabled) {
         Query qy;
         setup_closest_query(qy, o, d, fabsf((float)o.x) + fabsf((float)o.y) + fabsf((float)o.z) + c_scene.filter_centre_l1);
-        if (!c_scene.clustered) query_certified<true>(P, qy, o, plane_numerator(o), false, 0u, obj, index, t_hit, nullptr);
-        else query_certified<false>(P, qy, o, plane_numerator(o), false, 0u, obj, index, t_hit, nullptr);
+        if (!c_scene.clustered) query_certified<true>(P, reinterpret_cast<const float4 *>(P.cull_pairs), qy, o, plane_numerator(o), false, 0u, obj, index, t_hit, nullptr);
+        else query_certified<false>(P, nullptr, qy, o, plane_numerator(o), false, 0u, obj, index, t_hit, nullptr);
     } else {
         query_reference<false>(P, o, d, obj, index, t_hit, tally);
     }
