@@ -37,7 +37,7 @@ WIDTH, HEIGHT, SKYBOX, T_POSE = 7680, 4320, "milky_way", 3.7
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this workload on one GPU
 # (profiles/r01f_k1_k2_ncu_summary.txt): K1 19.6 MB + 118.3 MB (the 133 MB of quantised cells; scene, skybox and the sample
 # scratch stay in L2), K2 132.8 MB + 770.8 MB at capture time (the rest of the 829 MB stream was still in L2)
-NCU_DRAM_BYTES = {"k_render": 15.560e6 + 104.926e6, "k_encode": 132.727e6 + 772.355e6}
+NCU_DRAM_BYTES = {"k_render": 15.381e6 + 107.915e6, "k_encode": 132.727e6 + 770.604e6}
 CPU_SAMPLE_W, CPU_SAMPLE_H = 480, 270   # same 16:9 framing, 1/256 of the pixels
 
 
