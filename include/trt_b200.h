@@ -33,7 +33,6 @@ extern "C" {
 
 #define TRT_DEMO_SPHERES 6
 #define TRT_MAX_LIGHTS 16        /* per kind; the demo scene uses 1 + 1 (TRT.c:1278-1287) */
-#define TRT_MAX_CONST_SPHERES 1024 /* geometry kept in __constant__; larger scenes fall back to global memory */
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
 /* Bind this process to CUDA device `device` (one process per GPU; under torchrun pass LOCAL_RANK).

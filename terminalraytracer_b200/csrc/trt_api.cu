@@ -283,7 +283,6 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
     }
     s.num_spheres = scene->num_spheres;
     s.sphere_mask = scene->num_spheres >= 32 ? 0xffffffffu : ((1u << scene->num_spheres) - 1u);
-    s.filter_in_const = s.num_spheres <= TRT_MAX_CONST_SPHERES ? 1 : 0;
     s.sky_dim = g.sky_dim;
     s.sky_face_stride = g.sky_face_stride;
     trt_subpixel_offsets(s.sub_dx, s.sub_dy);
@@ -394,8 +393,7 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
     }
     g.cull_pairs.reserve(sizeof(CullPair) * pairs.size());
     CK(cudaMemcpyAsync(g.cull_pairs.p, staged(pairs.data(), sizeof(CullPair) * pairs.size()), sizeof(CullPair) * pairs.size(), cudaMemcpyHostToDevice, g.stream));
-    upload_scene_constants(*(const DevScene *)staged(&s, sizeof s), (const CullPair *)staged(pairs.data(), sizeof(CullPair) * pairs.size()),
-                           s.clustered ? 0 : (int)pairs.size(), g.stream);   // k-d-sorted scenes read the global copy
+    upload_scene_constants(*(const DevScene *)staged(&s, sizeof s), g.stream);
     // every source above is pageable host memory: the copies were staged before the calls returned, so the vectors may
     // die now; the wait only keeps the historical "scene is resident when this returns" behaviour for callers that time
     if (wait) CK(cudaStreamSynchronize(g.stream));
@@ -726,8 +724,7 @@ int trt_probe_skybox(const double *dirs, int n, int *out)
         memset(&g.scene, 0, sizeof g.scene);
         g.scene.sky_dim = g.sky_dim;
         g.scene.sky_face_stride = g.sky_face_stride;
-        g.scene.filter_in_const = 1;
-        upload_scene_constants(g.scene, nullptr, 0, g.stream);
+        upload_scene_constants(g.scene, g.stream);
         g.sphere_geom.reserve(sizeof(double4));
         g.sphere_cull.reserve(sizeof(float4));
         g.sphere_prim.reserve(sizeof(double4));
@@ -741,7 +738,7 @@ int trt_probe_skybox(const double *dirs, int n, int *out)
     } else {
         g.scene.sky_dim = g.sky_dim;
         g.scene.sky_face_stride = g.sky_face_stride;
-        upload_scene_constants(g.scene, nullptr, 0, g.stream);
+        upload_scene_constants(g.scene, g.stream);
     }
     Buffer d_in, d_out;
     d_in.reserve(sizeof(double) * 3 * (size_t)n);

@@ -6,7 +6,7 @@
 namespace trt {
 
 // trt_render.cu (owns the __constant__ scene)
-void upload_scene_constants(const DevScene &scene, const CullPair *pairs, int count, cudaStream_t stream);
+void upload_scene_constants(const DevScene &scene, cudaStream_t stream);
 // one_plus_one: the scene has exactly one directional and one point light (specialised kernel flavour)
 void launch_render(const RenderParams &p, bool count, int cull, bool one_plus_one, int num_sms, cudaStream_t stream);
 int render_ctas_per_sm();

@@ -40,9 +40,9 @@
 namespace trt {
 
 __constant__ DevScene c_scene;
-// Certificate records, two spheres per record so that the classification runs on the packed FP32 pipe
-// (FFMA2/FADD2/FMUL2 of sm_100: one issue slot, two spheres): .x = sphere 2p, .y = sphere 2p+1 (a pad sphere has r = 0)
-__constant__ CullPair c_cull_pairs[TRT_MAX_CONST_SPHERES / 2 + 1];
+// (The certificate records — two spheres per record so that the classification runs on the packed FP32 pipe, FFMA2/FADD2/FMUL2
+// of sm_100: one issue slot, two spheres; .x = sphere 2p, .y = sphere 2p+1, a pad sphere has r = 0 — live in global memory,
+// RenderParams::cull_pairs; small scenes copy theirs into shared memory at kernel start.)
 
 constexpr int TILE_W = 8;
 constexpr int TILE_H = 4;
@@ -1216,11 +1216,9 @@ static void die(cudaError_t e, const char *file, int line)
 }
 #define CK(x) die((x), __FILE__, __LINE__)
 
-void upload_scene_constants(const DevScene &scene, const CullPair *pairs, int count, cudaStream_t stream)
+void upload_scene_constants(const DevScene &scene, cudaStream_t stream)
 {
     CK(cudaMemcpyToSymbolAsync(c_scene, &scene, sizeof(DevScene), 0, cudaMemcpyHostToDevice, stream));
-    if (pairs && count > 0 && count <= TRT_MAX_CONST_SPHERES / 2 + 1)
-        CK(cudaMemcpyToSymbolAsync(c_cull_pairs, pairs, sizeof(CullPair) * (size_t)count, 0, cudaMemcpyHostToDevice, stream));
 }
 
 template <bool COUNT, int CULL>

@@ -102,7 +102,7 @@ def test_gpu_stress_scene_constant_memory_path(renderer, orc):
 
 
 def test_gpu_stress_scene_global_memory_path(renderer, orc):
-    """more spheres than TRT_MAX_CONST_SPHERES -> geometry read through the read-only global path"""
+    """well above the single-chunk and 1024-sphere sizes: k-d-sorted clusters, records read through the read-only global path"""
     sc = S.SceneData(40, 24, S.synthetic_cubemap("uv_gradient", 64), kind="stress", num_spheres=1100).set_time(3.7)
     assert np.array_equal(gpu_frame(renderer, sc), U.cpu_render(orc, "orc_project_scene", sc))
 
