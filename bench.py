@@ -6,12 +6,17 @@ at 7680x4320, reference bounce depth, milky_way skybox, row-band sharded over 1/
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One step = one frame through the hot path: K1 (render band, persistent FP64 kernel) -> K2 (ANSI
-encode) -> gather of the byte bands on rank 0.  Prints ONE JSON line on rank 0.
+encode) -> gather of the byte bands on rank 0 over NVLink peer memory (piece by piece behind the next
+piece's K1, or — 8 GPUs — by K1 itself, which then encodes and stores its tiles straight into rank 0's
+stream); the bands follow the ranks' measured K1 times.  Prints ONE JSON line on rank 0 (stdout carries
+nothing else).
 
   value      Mrays/s = 10*W*H*K / seconds (primary samples; TRT.c:58 RAYS_PER_PIXEL = 10), scene and
              skybox resident in HBM, device-timed (CUDA events), max over ranks.
   e2e        same metric through the C-ABI call a host program makes (trt_render_ansi at N=1: scene
-             upload H2D, K1, K2, D2H of the byte stream into pinned host memory — all inside the timing).
+             upload H2D, K1, K2, D2H of the byte stream into pinned host memory — all inside the timing;
+             at N>1 every rank copies its own bands into one shared page-locked host stream over its own
+             PCIe link, pipeline.FramePipeline(host_stream=...)).
   roofline   K1 against the FP32 CUDA-core peak (the path has no dense contraction and ~400 flop/byte,
              SURVEY.md §8d): achieved = algorithmic flops of the frame (work counters x the as-written
              per-event flop costs, counted by the kernel itself in a separate untimed launch and
@@ -35,8 +40,8 @@ sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT, SKYBOX, T_POSE = 7680, 4320, "milky_way", 3.7
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this workload on one GPU
-# (profiles/r01f_k1_k2_ncu_summary.txt): K1 19.6 MB + 118.3 MB (the 133 MB of quantised cells; scene, skybox and the sample
-# scratch stay in L2), K2 132.8 MB + 770.8 MB at capture time (the rest of the 829 MB stream was still in L2)
+# (profiles/r01f_k1_k2_ncu_summary.txt): K1 15.4 MB + 107.9 MB (the 133 MB of quantised cells, partly still in L2 at the end;
+# scene, skybox and the sample scratch stay in L2), K2 132.7 MB + 770.6 MB (the rest of the 829 MB stream was still in L2)
 NCU_DRAM_BYTES = {"k_render": 15.381e6 + 107.915e6, "k_encode": 132.727e6 + 770.604e6}
 CPU_SAMPLE_W, CPU_SAMPLE_H = 480, 270   # same 16:9 framing, 1/256 of the pixels
 
