@@ -245,3 +245,29 @@ def test_shared_host_stream_availability_probe():
     from terminalraytracer_b200 import pipeline
     assert pipeline.SharedHostStream.available(1 << 16) in (True, False)
     assert pipeline.SharedHostStream.available(1 << 62) is False
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """the JSON line bench.py printed on the B200 (profiles/r01f_bench_n1.json) carries every key of the bench contract"""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "profiles", "r01f_bench_n1.json")) as f:
+        line = json.loads(f.read())
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["metric"] == "Mrays/s" and line["unit"] == "Mrays/s" and line["higher_is_better"] is True
+    assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["gpu_launches"] == 3 * line["steps"]
+    assert "workload" in line["config"] and "model" not in line["config"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in line["roofline"], key
+    assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-9
+    for key in ("value", "unit", "cores", "kind", "sample"):
+        assert key in line["cpu_baseline"], key
+    for key in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert key in line["e2e"], key
+    assert line["e2e"]["d2h_bytes_per_step"] == abi.stream_bytes(7680, 4320)
+    assert line["e2e"]["value"] < line["value"]                       # host copies inside the timed region
+    assert line["clocks"]["reasons"] == [] or "sw_power_cap" in line["clocks"]["reasons"]
+    # value = primary rays per second over the timed steps
+    assert abs(line["value"] - 10.0 * 7680 * 4320 / (line["ms_per_step"] * 1e-3) / 1e6) < 1e-6 * line["value"]
