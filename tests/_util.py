@@ -167,3 +167,93 @@ def random_encoder_pixels():
     px = hash_uniform((280, 480, 3), 77, -0.2, 1.3)
     px[0, :16, 0] = np.arange(16) / 255.0
     return px
+
+
+# ---- checkers fanned over the host's cores (full-size configs) ------------------------------------------
+
+def load_reference_rows():
+    """oracle/_ref/libtrt_ref_rows.so: the reference TU with the row loop of TRT.c:973 bounded by a thread-local
+    [row0,row1) (oracle/Makefile); None when the reference build did not travel."""
+    if not os.path.exists(REF_ROWS_SO):
+        return None
+    lib = C.CDLL(REF_ROWS_SO)
+    lib.ref_project_rows.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Screen), C.c_int, C.c_int]
+    return lib
+
+
+def checker_rows_parallel(scene, rows, orc=None, threads=None):
+    """FP64 pixels of the given rows (any iterable of row indices) of scene.width x scene.height as the REFERENCE's
+    project_scene computes them (row-range build), or as the oracle port does when the reference build is absent;
+    the rows are spread over the host cores (ctypes releases the GIL; the row bounds are thread-local).
+    Returns (array (len(rows), W, 3), kind)."""
+    from concurrent.futures import ThreadPoolExecutor
+    rows = [int(r) for r in rows]
+    w, h = scene.width, scene.height
+    ref = load_reference_rows()
+    kind = "reference" if ref is not None else "port"
+    if ref is None and orc is None:
+        orc = load_oracle()
+    threads = threads or max(1, (os.cpu_count() or 1))
+    out = np.zeros((len(rows), w, 3), dtype=np.float64)
+    # contiguous runs of rows -> one call each, cut so that every thread gets several jobs (rows differ ~5x in cost)
+    runs, start = [], 0
+    for i in range(1, len(rows) + 1):
+        if i == len(rows) or rows[i] != rows[i - 1] + 1:
+            runs.append((start, i))
+            start = i
+    jobs = []
+    max_run = max(1, len(rows) // (threads * 8))
+    for a, b in runs:
+        for s in range(a, b, max_run):
+            jobs.append((s, min(b, s + max_run)))
+
+    def work(job):
+        a, b = job
+        r0, r1 = rows[a], rows[b - 1] + 1
+        # a Screen whose row r0 lands at out[a]: the checkers index pixels[row * width + col]
+        base = out[a:].ctypes.data - r0 * w * 24
+        scr = abi.Screen(C.cast(C.c_void_p(base), C.POINTER(abi.Vector)), w, h)
+        if ref is not None:
+            ref.ref_project_rows(C.byref(scene.c), C.byref(scr), r0, r1)
+        else:
+            orc.orc_render_rows(C.byref(scene.c), C.byref(scr), r0, r1, None)
+
+    with ThreadPoolExecutor(threads) as pool:
+        list(pool.map(work, jobs))
+    return out, kind
+
+
+def mismatch_report(got_px, want_px, got_stream_rows, want_stream_rows, row_ids, limit=200):
+    """mismatches as (row, col, channel, ref, got) for the FP64 pixels and the identical-cell fraction of
+    the terminal stream (rows of 25-byte cells + '\\n').  got/want_px: (R, W, 3); *_stream_rows: (R, 25W+1) uint8."""
+    bad = np.argwhere(got_px != want_px)
+    listed = [(int(row_ids[r]), int(c), int(ch), float(want_px[r, c, ch]), float(got_px[r, c, ch])) for r, c, ch in bad[:limit]]
+    R, W = got_px.shape[0], got_px.shape[1]
+    gc = got_stream_rows[:, :-1].reshape(R, W, abi.CELL_BYTES)
+    wc = want_stream_rows[:, :-1].reshape(R, W, abi.CELL_BYTES)
+    same_cells = int((gc == wc).all(axis=2).sum())
+    newline_ok = bool((got_stream_rows[:, -1] == want_stream_rows[:, -1]).all())
+    return {"rows_checked": int(R), "pixels_checked": int(R * W), "pixel_channel_mismatches": int(len(bad)),
+            "max_abs_diff": float(np.abs(got_px - want_px).max()) if got_px.size else 0.0,
+            "mismatches_row_col_channel_ref_got": listed,
+            "cells_checked": int(R * W), "cells_identical": same_cells, "cells_identical_pct": 100.0 * same_cells / max(R * W, 1),
+            "row_terminators_identical": newline_ok}
+
+
+def write_report(name, report):
+    """per-config parity reports: gpurun_out/ on the GPU box (merged back by gpurun), copied to profiles/ by hand"""
+    import json
+    d = os.environ.get("TRT_REPORT_DIR", os.path.join(ROOT, "gpurun_out"))
+    try:
+        os.makedirs(d, exist_ok=True)
+        path = os.path.join(d, "r02_parity_configs.json")
+        try:
+            with open(path) as f:
+                allr = json.load(f)
+        except (OSError, ValueError):
+            allr = {}
+        allr[name] = report
+        with open(path, "w") as f:
+            json.dump(allr, f, indent=1)
+    except OSError:
+        pass
