@@ -32,6 +32,10 @@ extern "C" {
 #endif
 
 #define TRT_DEMO_SPHERES 6
+/* LIMIT (differs from the reference, which takes any count): at most TRT_MAX_LIGHTS directional and TRT_MAX_LIGHTS point
+ * lights per scene — they live in the kernel's constant block.  A scene with more makes every entry point that takes a
+ * scene print "unsupported scene" to stderr and exit(1), in the reference's die-on-error style.  INTEGRATION.md repeats this
+ * next to the swap instructions. */
 #define TRT_MAX_LIGHTS 16        /* per kind; the demo scene uses 1 + 1 (TRT.c:1278-1287) */
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
@@ -75,7 +79,12 @@ size_t trt_draw_screen(const trt_Screen *screen, char *out);
 void trt_buffered_draw_screen(const trt_Screen *screen);
 
 /* fused path: render w x h and encode on the device, copy only the byte stream back.
- * `out` needs TRT_STREAM_BYTES(w,h) bytes; returns the byte count (0 if cap is too small). */
+ * `out` needs TRT_STREAM_BYTES(w,h) bytes; returns the byte count (0 if cap is too small).
+ * PRECONDITION of every path that carries QUANTISED cells between the kernels (this call, trt_render_orbit*, the *_quant_ and
+ * *_ansi_ device calls): pixels in [0,1], which every scene with finite lights, materials in [0,1] and a loaded skybox gives
+ * (TRT.c:960 clamps the lit colour, 1061 normalises by the weight sum).  A NaN/Inf light or material makes (int)(c*255) leave
+ * 0..255; the reference feeds that int to byte_to_digits (TRT.c:1134-1139) and so does trt_project_scene +
+ * trt_draw_screen, whereas the quantised paths keep its low byte: different digits for such pixels only. */
 size_t trt_render_ansi(const trt_Scene *scene, int width, int height, char *out, size_t cap);
 
 /* Streaming sink for camera animations — the reference's frame loop (TRT.c:1317-1367) with both hot calls on the GPU.
@@ -89,6 +98,17 @@ size_t trt_render_ansi(const trt_Scene *scene, int width, int height, char *out,
 typedef int (*trt_frame_sink)(const char *bytes, size_t n_bytes, int frame, void *user);
 int trt_render_orbit(const trt_Scene *scene, int width, int height, const double *times, int n_frames, int first, int stride,
                      trt_frame_sink sink, void *user);
+
+/* The same loop with caller-owned destinations — the cross-process form of the streaming sink: `acquire(frame, n_bytes, user)`
+ * returns the PAGE-LOCKED address (trt_host_alloc_pinned / trt_host_register) the frame's bytes are copied to straight from
+ * the device; it is called after the frame's kernels have been enqueued and may block until a destination is free (NULL stops
+ * the loop).  `sink` (may be NULL) is called with that address once the bytes have landed.  With the destinations in a
+ * shared-memory ring that every rank of a node has registered (pipeline.OrderedFrameRing), rank r renders frames r, r+N, ...
+ * into the ring while one consumer writes the frames out strictly in order — frame-index sharding of the reference's loop
+ * (TRT.c:1317-1367) with ONE ordered output, no gather at the end. */
+typedef char *(*trt_frame_acquire)(int frame, size_t n_bytes, void *user);
+int trt_render_orbit_to(const trt_Scene *scene, int width, int height, const double *times, int n_frames, int first, int stride,
+                        trt_frame_acquire acquire, trt_frame_sink sink, void *user);
 
 /* ---- device-resident pieces (row bands; used by the multi-GPU plumbing and by bench.py) ------- */
 /* Upload scene (spheres, ground, lights, camera) for subsequent *_device calls. */

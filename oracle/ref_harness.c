@@ -58,6 +58,45 @@ void ref_orbit_camera(Camera *camera, double t)
     transform_frame(&camera->frame, &tf0);
 }
 
+/* ---- the demo scene of main(): literals of TRT.c:1256-1288, camera by the reference's own init_camera
+ * (TRT.c:299-305) with the screen width of line 303 re-evaluated for a W x H screen.  The literals live inside
+ * main() and cannot be called; this restates them so that the reference arm of bench.py builds its input without
+ * loading the product library. `spheres` must hold 6 entries. */
+void ref_demo_scene(Scene *scene, Sphere *spheres, DirectionalLight *dl, PointLight *pl, int width, int height)
+{
+    static const double centre[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {-1, 0, 0}, {0, -1, 0}, {0, 0, -1}};
+    static const double colour[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 1, 1}, {1, 0, 1}, {1, 1, 0}};
+    Skybox keep = scene->skybox;
+    memset(scene, 0, sizeof *scene);
+    scene->skybox = keep;
+    for (int i = 0; i < 6; i++)
+    {
+        Sphere s = {.center = {.x = centre[i][0], .y = centre[i][1], .z = centre[i][2]},
+                    .material = {.color = {.x = colour[i][0], .y = colour[i][1], .z = colour[i][2]}, .reflectivity = i == 0 ? 1.0 : 0.8, .specularity = 100.0},
+                    .radius = 0.5};
+        spheres[i] = s;
+    }
+    Plane ground = {
+        .normal = {.x = 0.0, .y = 1.0, .z = 0.0},
+        .point = {.x = 0.0, .y = -2.0, .z = 0.0},
+        .even_material = {.color = GROUND_EVEN_COLOR, .reflectivity = 0.2, .specularity = 100.0},
+        .odd_material = {.color = GROUND_ODD_COLOR, .reflectivity = 0.2, .specularity = 100.0},
+    };
+    DirectionalLight d = {.direction = {.x = -1.0, .y = -1.0, .z = -1.0}, .color = {.x = 1.0, .y = 1.0, .z = 1.0}};
+    PointLight p = {.position = {.x = 0.0, .y = 0.0, .z = 0.0}, .color = {.x = 1.0, .y = 1.0, .z = 1.0}, .intensity = 10.0};
+    *dl = d;
+    *pl = p;
+    scene->spheres = spheres;
+    scene->num_spheres = 6;
+    scene->ground = ground;
+    scene->directional_lights = dl;
+    scene->num_directional_lights = 1;
+    scene->point_lights = pl;
+    scene->num_point_lights = 1;
+    init_camera(&scene->camera);
+    scene->camera.screen_width = 5 * (double)width / (double)height; /* TRT.c:303 for a W x H screen */
+}
+
 /* ---- sub-pixel offsets exactly as TRT.c:992-993 evaluates them ------------------- */
 void ref_subpixel_offsets(double *dx, double *dy)
 {

@@ -79,7 +79,7 @@ struct Context {
     Buffer sky;
     int sky_dim = -1, sky_face_stride = 0;
     // work
-    Buffer tile_counter, counters, byte_to_unit, scratch;
+    Buffer tile_counter, counters, byte_to_unit, scratch, tile_info;
     Buffer pixels, quant, bytes;
     PinnedBuffer stage;
     // pinned staging for scene uploads: copies from pageable memory make the runtime wait for the stream first, which
@@ -378,8 +378,11 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
     g.sphere_prim.reserve(sizeof(double4) * prim.size());
     CK(cudaMemcpyAsync(g.sphere_prim.p, staged(prim.data(), sizeof(double4) * prim.size()), sizeof(double4) * prim.size(), cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(g.sphere_cull.p, staged(cull.data(), sizeof(float4) * cull.size()), sizeof(float4) * cull.size(), cudaMemcpyHostToDevice, g.stream));
-    // The vectors above die at the end of this function, so these copies must complete before it
-    // returns: plain (staged) cudaMemcpyAsync from pageable memory is synchronous w.r.t. the host buffer.
+    // Every source goes through staged(): a memcpy into the page-locked arena g.arena[g.arena_which], so the vectors may die
+    // when this function returns and the copies are truly asynchronous.  Invariant: an arena may be rewritten only after the
+    // stream work of the upload that last used it has completed — wait == true synchronises below (arena 0);
+    // trt_render_orbit (wait == false) alternates the two arenas and waits for the copied[] event of two frames back
+    // before it uploads again.
     CK(cudaMemcpyAsync(g.sphere_geom.p, staged(geom.data(), sizeof(double4) * geom.size()), sizeof(double4) * geom.size(), cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(g.sphere_mat.p, staged(mats.data(), sizeof(DevMaterial) * mats.size()), sizeof(DevMaterial) * mats.size(), cudaMemcpyHostToDevice, g.stream));
     // the same records two by two for the packed classification; the odd one out is paired with a sphere of radius 0
@@ -394,13 +397,12 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
     g.cull_pairs.reserve(sizeof(CullPair) * pairs.size());
     CK(cudaMemcpyAsync(g.cull_pairs.p, staged(pairs.data(), sizeof(CullPair) * pairs.size()), sizeof(CullPair) * pairs.size(), cudaMemcpyHostToDevice, g.stream));
     upload_scene_constants(*(const DevScene *)staged(&s, sizeof s), g.stream);
-    // every source above is pageable host memory: the copies were staged before the calls returned, so the vectors may
-    // die now; the wait only keeps the historical "scene is resident when this returns" behaviour for callers that time
+    // wait: the caller's arena (0) is reused by the next call, and callers that time expect a resident scene on return
     if (wait) CK(cudaStreamSynchronize(g.stream));
     g.have_scene = true;
 }
 
-// 0: all FP64; 1: small scene, certificate records in __constant__; 2: k-d-sorted scene with cluster balls, records in global memory
+// 0: all FP64; 1: small scene (one chunk), certificate records copied to shared memory at kernel start; 2: k-d-sorted scene with cluster balls, records in global memory
 int cull_mode() { return !g.cull ? 0 : (g.scene.clustered ? 2 : 1); }
 
 bool one_plus_one() { return g.scene.num_dir == 1 && g.scene.num_point == 1; }
@@ -442,6 +444,9 @@ RenderParams make_params(int width, int height, int row0, int row1, double *d_pi
     p.sphere_mat = (const DevMaterial *)g.sphere_mat.p;
     p.byte_to_unit = (const double *)g.byte_to_unit.p;
     p.sky = (const uchar4 *)g.sky.p;
+    // sized for the whole frame, so that bands of any height (adaptive bands, row chunks) never reallocate
+    g.tile_info.reserve(render_tile_info_bytes(width, height > row1 - row0 ? height : row1 - row0));
+    p.tile_info = (const uint4 *)g.tile_info.p;
     p.tile_counter = (unsigned int *)g.tile_counter.p;
     g.scratch.reserve(render_scratch_bytes(g.num_sms));
     p.sample_scratch = (double *)g.scratch.p;
@@ -509,6 +514,7 @@ void trt_shutdown(void)
     g.sky.release();
     g.tile_counter.release();
     g.scratch.release();
+    g.tile_info.release();
     g.byte_to_unit.release();
     g.counters.release();
     g.pixels.release();
@@ -584,8 +590,12 @@ int trt_upload_skybox(const trt_Skybox *skybox)
     g.sky_dim = dim;
     g.sky_face_stride = (int)stride;
     if (g.have_scene) {
+        // the band API (trt_render_rows_*) renders with the constants of the last trt_set_scene: they carry the skybox
+        // geometry, so a skybox uploaded after the scene has to refresh them (set_scene -> upload_skybox -> render is legal)
         g.scene.sky_dim = dim;
         g.scene.sky_face_stride = (int)stride;
+        upload_scene_constants(g.scene, g.stream);
+        CK(cudaStreamSynchronize(g.stream));
     }
     return 0;
 }
@@ -874,37 +884,37 @@ size_t trt_render_ansi(const trt_Scene *scene, int width, int height, char *out,
     return total;
 }
 
-int trt_render_orbit(const trt_Scene *scene, int width, int height, const double *times, int n_frames, int first, int stride,
-                     trt_frame_sink sink, void *user)
+// The frame loop behind trt_render_orbit / trt_render_orbit_to.  `acquire` names the page-locked destination of a frame's
+// bytes (it may block until one is free: called after the frame's kernels have been enqueued, so the GPU works meanwhile);
+// `sink` is called once the bytes have landed.  Two device buffers: the copy of frame k runs while frame k+1 renders.
+static int orbit_loop(const trt_Scene *scene, int width, int height, const double *times, int n_frames, int first, int stride,
+                      trt_frame_acquire acquire, trt_frame_sink sink, void *user)
 {
-    require_init("trt_render_orbit");
-    if (width <= 0 || height <= 0 || n_frames <= 0 || stride <= 0 || first < 0 || !sink) return 0;
     const size_t total = TRT_STREAM_BYTES(width, height);
     g.quant.reserve(sizeof(uchar4) * (size_t)width * (size_t)height);
     Buffer d_bytes[2];
-    PinnedBuffer h_bytes[2];
     cudaEvent_t encoded[2], copied[2];
     for (int b = 0; b < 2; b++) {
         d_bytes[b].reserve(total + 16);
-        h_bytes[b].reserve(total);
         CK(cudaEventCreateWithFlags(&encoded[b], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
     }
     trt_Scene posed = *scene;
     int launched = 0, delivered = 0, pending_frame[2] = {-1, -1};
+    char *pending_dst[2] = {nullptr, nullptr};
     bool stop = false;
     auto deliver = [&](int b) {
-        // frame pending_frame[b] is on its way to h_bytes[b]: wait for the copy, hand it to the sink
+        // frame pending_frame[b] is on its way to pending_dst[b]: wait for the copy, hand it to the sink
         CK(cudaEventSynchronize(copied[b]));
         if (!stop) {
-            if (sink((const char *)h_bytes[b].p, total, pending_frame[b], user) != 0) stop = true;
+            if (sink && sink(pending_dst[b], total, pending_frame[b], user) != 0) stop = true;
             delivered++;
         }
         pending_frame[b] = -1;
     };
     for (int k = first; k < n_frames && !stop; k += stride) {
         const int b = launched & 1;
-        if (pending_frame[b] >= 0) deliver(b);          // frame k-2*stride: its buffers are reused now
+        if (pending_frame[b] >= 0) deliver(b);          // frame k-2*stride: its device buffer and upload arena are reused now
         if (stop) break;
         posed.camera = scene->camera;
         trt_orbit_camera(&posed.camera, times[k]);
@@ -914,11 +924,16 @@ int trt_render_orbit(const trt_Scene *scene, int width, int height, const double
         launch_stream_frame((char *)d_bytes[b].p, width, height, g.stream);
         launch_encode_quant((const uchar4 *)g.quant.p, width, height, (char *)d_bytes[b].p, TRT_HOME_BYTES, g.stream);
         CK(cudaEventRecord(encoded[b], g.stream));
+        char *dst = acquire(k, total, user);            // may block: the kernels above are already running
+        if (!dst) {
+            stop = true;
+            break;
+        }
         CK(cudaStreamWaitEvent(g.copy_stream, encoded[b], 0));
-        CK(cudaMemcpyAsync(h_bytes[b].p, d_bytes[b].p, total, cudaMemcpyDeviceToHost, g.copy_stream));
+        CK(cudaMemcpyAsync(dst, d_bytes[b].p, total, cudaMemcpyDeviceToHost, g.copy_stream));
         CK(cudaEventRecord(copied[b], g.copy_stream));
-        // d_bytes[b] / h_bytes[b] are written again two frames from now, after deliver(b) has waited for this copy
         pending_frame[b] = k;
+        pending_dst[b] = dst;
         launched++;
         // while this frame renders, deliver the previous one
         if (pending_frame[b ^ 1] >= 0) deliver(b ^ 1);
@@ -928,13 +943,54 @@ int trt_render_orbit(const trt_Scene *scene, int width, int height, const double
         if (pending_frame[b] >= 0) deliver(b);
     }
     CK(cudaStreamSynchronize(g.stream));
+    CK(cudaStreamSynchronize(g.copy_stream));
     for (int b = 0; b < 2; b++) {
         d_bytes[b].release();
-        h_bytes[b].release();
         cudaEventDestroy(encoded[b]);
         cudaEventDestroy(copied[b]);
     }
     return delivered;
+}
+
+namespace {
+struct OwnBuffers {
+    PinnedBuffer h[2];
+    int next = 0;
+    trt_frame_sink sink = nullptr;
+    void *user = nullptr;
+};
+char *own_acquire(int, size_t, void *u)
+{
+    OwnBuffers *o = (OwnBuffers *)u;
+    return (char *)o->h[(o->next++) & 1].p;     // frame k-2's buffer: orbit_loop delivered that frame before asking again
+}
+int own_sink(const char *bytes, size_t n, int frame, void *u)
+{
+    OwnBuffers *o = (OwnBuffers *)u;
+    return o->sink(bytes, n, frame, o->user);
+}
+} // namespace
+
+int trt_render_orbit(const trt_Scene *scene, int width, int height, const double *times, int n_frames, int first, int stride,
+                     trt_frame_sink sink, void *user)
+{
+    require_init("trt_render_orbit");
+    if (width <= 0 || height <= 0 || n_frames <= 0 || stride <= 0 || first < 0 || !sink) return 0;
+    OwnBuffers own;
+    own.sink = sink;
+    own.user = user;
+    for (int b = 0; b < 2; b++) own.h[b].reserve(TRT_STREAM_BYTES(width, height));
+    const int delivered = orbit_loop(scene, width, height, times, n_frames, first, stride, own_acquire, own_sink, &own);
+    for (int b = 0; b < 2; b++) own.h[b].release();
+    return delivered;
+}
+
+int trt_render_orbit_to(const trt_Scene *scene, int width, int height, const double *times, int n_frames, int first, int stride,
+                        trt_frame_acquire acquire, trt_frame_sink sink, void *user)
+{
+    require_init("trt_render_orbit_to");
+    if (width <= 0 || height <= 0 || n_frames <= 0 || stride <= 0 || first < 0 || !acquire) return 0;
+    return orbit_loop(scene, width, height, times, n_frames, first, stride, acquire, sink, user);
 }
 
 // ---- gather over NVLink peer memory ------------------------------------------------------------------------

@@ -11,6 +11,7 @@ void upload_scene_constants(const DevScene &scene, cudaStream_t stream);
 void launch_render(const RenderParams &p, bool count, int cull, bool one_plus_one, int num_sms, cudaStream_t stream);
 int render_ctas_per_sm();
 size_t render_scratch_bytes(int num_sms);   // RenderParams::sample_scratch must be at least this big
+size_t render_tile_info_bytes(int width, int rows);   // RenderParams::tile_info for a launch of `rows` rows (k_tile_certs)
 unsigned long long run_selftest_division(unsigned long long seed, int ctas, int iters, unsigned long long *d_scratch, cudaStream_t stream);
 void launch_probe_trace(const RenderParams &p, const double *d_rays, int n, double *d_out, cudaStream_t stream);
 void launch_probe_sky(const RenderParams &p, const double *d_dirs, int n, int *d_out, cudaStream_t stream);

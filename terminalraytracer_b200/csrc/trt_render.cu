@@ -44,6 +44,13 @@ __constant__ DevScene c_scene;
 // of sm_100: one issue slot, two spheres; .x = sphere 2p, .y = sphere 2p+1, a pad sphere has r = 0 — live in global memory,
 // RenderParams::cull_pairs; small scenes copy theirs into shared memory at kernel start.)
 
+#ifndef TRT_SUM_UNROLL
+#define TRT_SUM_UNROLL 10       // per-pixel sum of the ten samples at the end of a tile: unroll factor (code size vs loop overhead)
+#endif
+#ifndef TRT_TILE_PREPASS
+#define TRT_TILE_PREPASS 1      // 0: every flavour takes its tile certificates inside k_render (A/B runs)
+#endif
+constexpr int SUM_UNROLL = TRT_SUM_UNROLL;
 constexpr int TILE_W = 8;
 constexpr int TILE_H = 4;
 #ifndef TRT_WARPS_PER_CTA
@@ -334,8 +341,9 @@ struct Query {
     int mode;
 };
 
-// CONST_RECORDS: small scene (at most TRT_CLUSTER_MIN_SPHERES spheres): records in __constant__, reference order, no
-// clusters.  Otherwise the scene is k-d-sorted with bounding balls and its records are read from global memory.
+// CONST_RECORDS: small scene (at most TRT_CLUSTER_MIN_SPHERES spheres): records in shared memory (s_pairs, copied at kernel
+// start), reference order, no clusters.  Otherwise the scene is k-d-sorted with bounding balls and its records are read
+// from global memory.
 template <bool CONST_RECORDS>
 __device__ __forceinline__ bool query_certified(const RenderParams &P, const float4 *s_pairs, const Query &qy, const d3 &o, double num_g, bool use_patch,
                                                 unsigned int patch_mask, int &obj, int &index, double &t_hit, unsigned int *exact_tests)
@@ -596,6 +604,8 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
     // certificates on (CULL != 0: the host only picks these flavours when the scene's magnitudes are inside the range the error
     // bounds hold for, DevScene::filter_enabled) or off (inf: every certificate ray unusable) is a compile-time property here
     const float S_max = CULL != 0 ? c_scene.filter_centre_l1 : INFINITY;
+    // small scenes with exactly 1 + 1 lights (the reference's own shape): tile and patch certificates come from the prepass
+    constexpr bool PREPASS = TRT_TILE_PREPASS && CULL == 1 && LIGHTS == 1;
 
     for (;;) {
         unsigned int tile = 0;
@@ -617,7 +627,19 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
         // ---- tile certificates (float): which spheres can any primary ray of this tile hit at all? the ground?
         bool tile_ground_miss = false;
         bool patch = false;       // patch certificates available for this tile's first-generation hits
-        if (tile_certs) {
+        if (PREPASS) {
+            // the tile's certificates were taken by k_tile_certs (same functions, same inputs, one thread per tile): the
+            // per-tile code of this kernel is a 32-byte load instead of 8 KB of instructions that would evict the hot loop
+            const uint4 m = __ldg(P.tile_info + 2 * (size_t)tile), f = __ldg(P.tile_info + 2 * (size_t)tile + 1);
+            if (lane == 0) {
+                W.tmask[0] = m.x;
+                W.pmask[0] = m.y;
+                W.pmask[1] = m.z;
+                W.pmask[2] = m.w;
+            }
+            tile_ground_miss = (f.x & 1u) != 0u;
+            patch = (f.x & 2u) != 0u;
+        } else if (tile_certs) {
             // (read in place: the fields become constant-bank operands; a local copy would be twenty loads per tile)
             const trt_cert_camera &cam = c_scene.cam_f;
             float Dx, Dy, Dz, hx, hy;
@@ -1024,7 +1046,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
         __syncwarp();
         d3 average = mk3(0.0, 0.0, 0.0);
         if (valid) {
-#pragma unroll
+#pragma unroll SUM_UNROLL
             for (int k = 0; k < TRT_RAYS_PER_PIXEL; k++)
                 average = average + mk3(__ldcg(&res[0 * TILE_SAMPLES + k * 32 + lane]), __ldcg(&res[1 * TILE_SAMPLES + k * 32 + lane]),
                                         __ldcg(&res[2 * TILE_SAMPLES + k * 32 + lane]));
@@ -1069,6 +1091,68 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
         }
         __syncwarp();   // the sample slice and tmask are rewritten by the next tile
     }
+}
+
+// ---- tile certificates as a prepass (small scenes, 1 + 1 lights) --------------------------------------------------
+// K1 is bound by instruction supply: the code it executes regularly is larger than the SM's instruction cache, and the 8 KB of
+// per-tile certificate code evicted the hot loop once per tile and warp (ncu: gcc__cache_requests_type_instruction at 83 % of
+// its peak rate).  This kernel takes the same certificates — same trt_cert.h functions on the same inputs — with one THREAD
+// per tile instead of one warp per tile (lane = sphere), ahead of k_render, and leaves 32 bytes per tile:
+//   word 0: spheres the tile's primary rays can reach   words 1-3: patch masks (directional light, point light, bounce)
+//   word 4: bit 0 ground certainly missed by the tile's primary rays, bit 1 patch certificates valid
+__global__ void __launch_bounds__(128) k_tile_certs(const RenderParams P, uint4 *__restrict__ out)
+{
+    const int band_rows = P.row1 - P.row0;
+    const int tiles_x = (P.width + TILE_W - 1) / TILE_W;
+    const int tiles_y = (band_rows + TILE_H - 1) / TILE_H;
+    const unsigned int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= (unsigned int)(tiles_x * tiles_y)) return;
+    const int ty = (int)(tile / (unsigned)tiles_x), tx = (int)(tile % (unsigned)tiles_x);
+    const int num_spheres = c_scene.num_spheres;          // <= 32 here
+    const trt_cert_camera &cam = c_scene.cam_f;
+    float Dx, Dy, Dz, hx, hy;
+    trt_cert_tile_cone(&cam, P.pixel_w_f, P.pixel_h_f, tx * TILE_W, P.row0 + ty * TILE_H, TILE_W, TILE_H, &Dx, &Dy, &Dz, &hx, &hy);
+    const float h = fmaf(hx, cam.nbx, hy * cam.nby);
+    const float S = c_scene.eye_l1 + c_scene.filter_centre_l1;
+    unsigned int tmask = 0u;
+    for (int i = 0; i < num_spheres; i++) {
+        const float4 g = __ldg(&P.sphere_cull[i]);
+        if (!trt_cert_tile_sphere_miss(cam.ex, cam.ey, cam.ez, Dx, Dy, Dz, h, g.x, g.y, g.z, g.w, S)) tmask |= 1u << i;
+    }
+    const float *gn = c_scene.ground_normal_f;
+    const float dn = fmaf(Dz, gn[2], fmaf(Dy, gn[1], Dx * gn[0]));
+    const float bxn = fmaf(cam.bx[2], gn[2], fmaf(cam.bx[1], gn[1], cam.bx[0] * gn[0]));
+    const float byn = fmaf(cam.by[2], gn[2], fmaf(cam.by[1], gn[1], cam.by[0] * gn[0]));
+    const float scale = (fabsf(Dx) + fabsf(Dy) + fabsf(Dz) + 2.0f * h) * c_scene.ground_normal_l1;
+    const int sgn = trt_cert_tile_plane_sign(dn, bxn, byn, hx, hy, scale);
+    const bool tile_ground_miss = (c_scene.prim_num_sign < 0 && sgn > 0) || (c_scene.prim_num_sign > 0 && sgn < 0);
+    bool patch = false;
+    unsigned int pm_dir = 0u, pm_point = 0u, pm_bounce = 0u;
+    if (tmask == 0u && !tile_ground_miss && c_scene.prim_num_sign != 0) {
+        trt_cert_ball ball;
+        trt_cert_patch_ball(&cam, Dx, Dy, Dz, hx, hy, c_scene.prim_num_f, gn[0], gn[1], gn[2], S, &ball);
+#ifndef TRT_NO_PATCH
+        patch = ball.ok != 0;
+#endif
+        if (patch) {
+            const float S_ball = fabsf(ball.cx) + fabsf(ball.cy) + fabsf(ball.cz) + ball.r + c_scene.filter_centre_l1;
+            const float *Lf = c_scene.dir[0].Lf;
+            const DevLightPoint &Lp = c_scene.point[0];
+            // reflection of the tile's central direction about the plane (unit normal in float)
+            const float *un = c_scene.ground_unit_normal_f;
+            const float dnn = 2.0f * fmaf(Dz, un[2], fmaf(Dy, un[1], Dx * un[0]));
+            const float Rx = fmaf(-dnn, un[0], Dx), Ry = fmaf(-dnn, un[1], Dy), Rz = fmaf(-dnn, un[2], Dz);
+            const float hb = h * 1.0001f + (32.0f * TRT_CERT_U) * (fabsf(Dx) + fabsf(Dy) + fabsf(Dz));
+            for (int i = 0; i < num_spheres; i++) {
+                const float4 g = __ldg(&P.sphere_cull[i]);
+                if (trt_cert_patch_dir_candidate(&ball, Lf[0], Lf[1], Lf[2], g.x, g.y, g.z, g.w, S_ball)) pm_dir |= 1u << i;
+                if (trt_cert_patch_point_candidate(&ball, Lp.pos_f[0], Lp.pos_f[1], Lp.pos_f[2], g.x, g.y, g.z, g.w, S_ball + Lp.pos_l1)) pm_point |= 1u << i;
+                if (trt_cert_patch_bounce_candidate(&ball, Rx, Ry, Rz, hb, g.x, g.y, g.z, g.w, S_ball)) pm_bounce |= 1u << i;
+            }
+        }
+    }
+    out[2 * (size_t)tile] = make_uint4(tmask, pm_dir, pm_point, pm_bounce);
+    out[2 * (size_t)tile + 1] = make_uint4((tile_ground_miss ? 1u : 0u) | (patch ? 2u : 0u), 0u, 0u, 0u);
 }
 
 // ---- unit-level probe: trace_ray (TRT.c:793-889) for an array of rays, all out-params ---------------
@@ -1242,6 +1326,12 @@ int render_ctas_per_sm()
     return cached;
 }
 
+size_t render_tile_info_bytes(int width, int rows)
+{
+    const size_t tiles = (size_t)((width + TILE_W - 1) / TILE_W) * (size_t)((rows + TILE_H - 1) / TILE_H);
+    return (tiles ? tiles : 1) * 2 * sizeof(uint4);
+}
+
 size_t render_scratch_bytes(int num_sms)
 {
     // one slice of finished samples (3 channels x 320 samples) per warp of the persistent grid
@@ -1259,6 +1349,13 @@ void launch_render(const RenderParams &p, bool count, int cull, bool one_plus_on
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     dim3 g((unsigned)grid), b(CTA_THREADS);
+    if (TRT_TILE_PREPASS && cull == 1 && one_plus_one) {
+        if (!p.tile_info) {
+            fprintf(stderr, "libtrt_b200: launch_render without a tile_info buffer\n");
+            exit(1);
+        }
+        k_tile_certs<<<(unsigned)((tiles + 127) / 128), 128, 0, stream>>>(p, const_cast<uint4 *>(p.tile_info));
+    }
     // 12 flavours: counting or not, certificates off / small scene / clustered scene, generic lights or exactly 1 + 1
 #define TRT_LAUNCH(COUNT, CULL) \
     do { \

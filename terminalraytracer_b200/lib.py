@@ -15,6 +15,9 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("TRT_B200_LIB", "libtrt_b200.so"))
 # trt_frame_sink (include/trt_b200.h)
 FRAME_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
 
+# trt_frame_acquire (include/trt_b200.h)
+FRAME_ACQUIRE = C.CFUNCTYPE(C.c_void_p, C.c_int, C.c_size_t, C.c_void_p)
+
 # name -> (restype, argtypes); mirrors include/trt_b200.h one to one
 SIGNATURES = {
     "trt_init": (C.c_int, [C.c_int]),
@@ -30,6 +33,7 @@ SIGNATURES = {
     "trt_buffered_draw_screen": (None, [C.POINTER(abi.Screen)]),
     "trt_render_ansi": (C.c_size_t, [C.POINTER(abi.Scene), C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "trt_render_orbit": (C.c_int, [C.POINTER(abi.Scene), C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "trt_render_orbit_to": (C.c_int, [C.POINTER(abi.Scene), C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "trt_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "trt_ipc_import": (C.c_void_p, [C.c_void_p]),
     "trt_ipc_close": (C.c_int, [C.c_void_p]),

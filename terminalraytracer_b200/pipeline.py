@@ -241,22 +241,156 @@ class FramePipeline:
         return self.gather()
 
 
-class OrbitPipeline:
-    """Animation, frame-sharded: frame k is rendered by rank k mod N (BASELINE config 4)."""
+class OrderedFrameRing:
+    """The ordered sink of a frame-sharded animation: a ring of `slots` frame buffers in POSIX shared memory that every rank
+    of the node maps (and page-locks, when a renderer is given, so that the device-to-host copies land in it directly), a
+    ready flag per frame and the count of frames consumed.  Rank r produces frames r, r+N, ... (acquire -> the frame's bytes
+    arrive -> publish); ONE consumer takes the frames strictly in order while later ones are still rendering.  Frame k lives
+    in slot k mod slots; a producer may run at most `slots` frames ahead of the consumer.  Host logic only (mmap + numpy):
+    the CPU tests drive it with plain processes."""
 
-    def __init__(self, renderer, width, height, rank=0, world_size=1, group=None):
-        self.frame = FramePipeline(renderer, width, height, 0, 1)  # every rank renders whole frames
+    HEADER = 4096
+
+    def __init__(self, frame_bytes, n_frames, slots, rank=0, world_size=1, group=None, renderer=None):
+        import ctypes as C
+        import mmap
+        import os
+        import numpy as np
+        self.frame_bytes, self.n_frames, self.slots = int(frame_bytes), int(n_frames), int(slots)
+        self.rank, self.world_size, self.r = rank, world_size, renderer
+        self.slot_stride = (self.frame_bytes + 4095) & ~4095
+        self.flags_bytes = (4 * self.n_frames + 4095) & ~4095
+        self.nbytes = self.HEADER + self.flags_bytes + self.slots * self.slot_stride
+        box = [None]
+        if rank == 0:
+            box[0] = "/dev/shm/trt_b200_ring_%d_%x" % (os.getpid(), id(self) & 0xffffff)
+            fd = os.open(box[0], os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+            os.ftruncate(fd, self.nbytes)          # zero-filled: nothing ready, nothing consumed
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.broadcast_object_list(box, src=0, group=group)
+            if rank != 0:
+                fd = os.open(box[0], os.O_RDWR)
+        self.map = mmap.mmap(fd, self.nbytes)
+        os.close(fd)
+        if world_size > 1:
+            dist.barrier(group=group)
+        if rank == 0:
+            os.unlink(box[0])
+        self.base = C.addressof(C.c_char.from_buffer(self.map))
+        self.header = np.frombuffer(self.map, dtype=np.int64, count=2, offset=0)          # [consumed, stop]
+        self.ready = np.frombuffer(self.map, dtype=np.int32, count=self.n_frames, offset=self.HEADER)
+        self.slots_base = self.base + self.HEADER + self.flags_bytes
+        self.registered = False
+        if renderer is not None:
+            renderer.L.trt_host_register(self.slots_base, self.slots * self.slot_stride)
+            self.registered = True
+
+    # ---- producers -------------------------------------------------------------------------------------------------
+    def slot_address(self, frame):
+        return self.slots_base + (frame % self.slots) * self.slot_stride
+
+    def acquire(self, frame, poll_s=20e-6):
+        """address of frame's slot once the consumer has freed it (frame - slots consumed); None after stop()"""
+        import time
+        while frame >= int(self.header[0]) + self.slots:
+            if self.header[1]:
+                return None
+            time.sleep(poll_s)
+        return None if self.header[1] else self.slot_address(frame)
+
+    def publish(self, frame):
+        self.ready[frame] = 1
+
+    def stop(self):
+        self.header[1] = 1
+
+    # ---- the one consumer ------------------------------------------------------------------------------------------
+    def consume(self, write, poll_s=20e-6, timeout_s=600.0):
+        """frames 0..n_frames-1 in order: write(frame_index, memoryview of its bytes) as soon as frame k is ready; returns the
+        number of frames written (fewer than n_frames after stop() or when write returns a true value)"""
+        import time
+        view = memoryview(self.map)
+        off0 = self.HEADER + self.flags_bytes
+        deadline = time.monotonic() + timeout_s
+        k = 0
+        try:
+            while k < self.n_frames:
+                while not self.ready[k]:
+                    if self.header[1] or time.monotonic() > deadline:
+                        return k
+                    time.sleep(poll_s)
+                off = off0 + (k % self.slots) * self.slot_stride
+                halt = write(k, view[off:off + self.frame_bytes])
+                k += 1
+                self.header[0] = k
+                if halt:
+                    self.stop()
+                    break
+        finally:
+            view.release()
+        return k
+
+    def close(self):
+        if self.registered:
+            self.r.L.trt_host_unregister(self.slots_base)
+            self.registered = False
+        self.header = self.ready = None
+
+
+class OrbitPipeline:
+    """Animation, frame-sharded with streamed, ordered output (BASELINE config 4; the reference's frame loop
+    TRT.c:1317-1367 with one fwrite per frame, TRT.c:1171): frame k is rendered by rank k mod N through
+    trt_render_orbit_to, its bytes go from the device straight into a shared page-locked ring (OrderedFrameRing) over the
+    rank's own PCIe link, and rank 0 writes the frames out strictly in order while later ones render.  Nothing is gathered
+    at the end and no rank ever holds more than `slots_per_rank` finished frames."""
+
+    def __init__(self, renderer, width, height, rank=0, world_size=1, group=None, slots_per_rank=3):
         self.r = renderer
         self.width, self.height = width, height
         self.rank, self.world_size, self.group = rank, world_size, group
-        self.device = self.frame.device
+        self.slots_per_rank = slots_per_rank
+        self.frame_bytes = abi.stream_bytes(width, height)
 
-    def render(self, scene, times):
-        ids = sharding.frames_for_rank(len(times), self.rank, self.world_size)
-        mine = []
-        for k in ids:
-            scene.set_time(times[k])
-            self.frame.render_local(scene)
-            mine.append(self.frame.stream.clone())
-        return tdist.gather_frames(mine, ids, len(times), abi.stream_bytes(self.width, self.height), self.rank,
-                                   self.world_size, self.device, self.group)
+    def stream(self, scene, times, write=None):
+        """Render this rank's frames of the camera path `times` (scene: un-posed camera, as SceneData builds it); rank 0 also
+        consumes: write(frame_index, memoryview) for k = 0, 1, 2, ... in order (default: discard).  Returns the number of
+        frames this rank rendered and — on rank 0 — the number written out."""
+        import ctypes as C
+        import threading
+        from . import lib as _lib
+        n = len(times)
+        ring = OrderedFrameRing(self.frame_bytes, n, self.slots_per_rank * self.world_size, self.rank, self.world_size, self.group, self.r)
+        written = [0]
+        consumer = None
+        if self.rank == 0:
+            sink = write if write is not None else (lambda k, view: False)
+            consumer = threading.Thread(target=lambda: written.__setitem__(0, ring.consume(sink)), daemon=True)
+            consumer.start()
+        arr = (C.c_double * n)(*[float(t) for t in times])
+
+        def _acquire(frame, nbytes, _user):
+            return ring.acquire(frame)          # None -> NULL: the loop stops
+
+        def _landed(ptr, nbytes, frame, _user):
+            ring.publish(frame)
+            return 0
+
+        acq, snk = _lib.FRAME_ACQUIRE(_acquire), _lib.FRAME_SINK(_landed)
+        self.r.use_stream(None)                 # the orbit loop runs on the library's own streams
+        done = self.r.L.trt_render_orbit_to(C.byref(scene.c), self.width, self.height, arr, n, self.rank, self.world_size,
+                                            C.cast(acq, C.c_void_p), C.cast(snk, C.c_void_p), None)
+        if consumer is not None:
+            consumer.join()
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)      # nobody unmaps the ring while the consumer may still read it
+        ring.close()
+        return done, written[0]
+
+    def collect(self, scene, times):
+        """small animations (tests): the ordered frames as a list of uint8 arrays on rank 0, None elsewhere"""
+        import numpy as np
+        frames = []
+        self.stream(scene, times, (lambda k, view: frames.append(np.frombuffer(view, dtype=np.uint8).copy()) and False))
+        return frames if self.rank == 0 else None

@@ -106,3 +106,74 @@ def test_frame_sharded_gather_world2(tmp_path):
         sc.set_time(t)
         want = U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc))
         assert np.array_equal(got[k], want), k
+
+
+# ---- the ordered sink of the frame-sharded animation (pipeline.OrderedFrameRing): host logic, no GPU ----------------
+
+def _ring_worker(rank, world, port, nframes, slots, out_path):
+    import time
+    from terminalraytracer_b200 import pipeline
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        orc = U.load_oracle()
+        w, h = 16, 9
+        nbytes = abi.stream_bytes(w, h)
+        ring = pipeline.OrderedFrameRing(nbytes, nframes, slots, rank, world)
+        order, frames = [], []
+        consumer = None
+        if rank == 0:
+            import threading
+
+            def write(k, view):
+                order.append(k)
+                frames.append(np.frombuffer(view, dtype=np.uint8).copy())
+                time.sleep(0.002)                   # a slow terminal: producers must wait for free slots
+                return False
+
+            consumer = threading.Thread(target=lambda: ring.consume(write))
+            consumer.start()
+        sc = S.SceneData(w, h, S.synthetic_cubemap("colors", 16))
+        times = sharding.orbit_times(nframes)
+        for k in sharding.frames_for_rank(nframes, rank, world):
+            if rank == world - 1:
+                time.sleep(0.004)                   # the last rank is late: the consumer must wait for ITS frames, in order
+            addr = ring.acquire(k)
+            assert addr == ring.slot_address(k)
+            sc.set_time(times[k])
+            data = U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc))
+            C.memmove(addr, data.ctypes.data, nbytes)
+            ring.publish(k)
+        if consumer is not None:
+            consumer.join()
+            assert order == list(range(nframes))
+            np.save(out_path, np.stack(frames))
+        dist.barrier()
+        ring.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ordered_frame_ring_world3_fewer_slots_than_frames(tmp_path):
+    out = str(tmp_path / "ring.npy")
+    nframes, world = 11, 3
+    mp.spawn(_ring_worker, args=(world, _free_port(), nframes, 3, out), nprocs=world, join=True)   # 3 slots: one per rank
+    orc = U.load_oracle()
+    sc = S.SceneData(16, 9, S.synthetic_cubemap("colors", 16))
+    got = np.load(out)
+    assert got.shape[0] == nframes
+    for k, t in enumerate(sharding.orbit_times(nframes)):
+        sc.set_time(t)
+        assert np.array_equal(got[k], U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc))), k
+
+
+def test_ordered_frame_ring_stop_releases_producers():
+    from terminalraytracer_b200 import pipeline
+    ring = pipeline.OrderedFrameRing(64, 8, 2)
+    assert ring.acquire(0) == ring.slot_address(0) and ring.acquire(1) == ring.slot_address(1)
+    ring.publish(0)
+    seen = []
+    assert ring.consume(lambda k, v: seen.append(k) or True) == 1      # the writer asks to stop after frame 0
+    assert seen == [0] and ring.acquire(2) is None                       # producers are released with "stop"
+    ring.close()

@@ -380,11 +380,11 @@ def test_gpu_pipeline_single_rank(renderer, orc):
         orbit = pipeline.OrbitPipeline(renderer, 64, 36)
         sc2 = S.SceneData(64, 36, sc.skybox)
         times = sharding.orbit_times(4)
-        frames = orbit.render(sc2, times)
+        frames = orbit.collect(sc2, times)          # trt_render_orbit_to into the ordered shared ring, one rank
         torch.cuda.synchronize()
         for k, t in enumerate(times):
             sc2.set_time(t)
-            assert np.array_equal(frames[k].cpu().numpy(), U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc2)))
+            assert np.array_equal(frames[k], U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc2)))
     finally:
         renderer.use_stream(None)
 
@@ -416,6 +416,49 @@ def test_gpu_orbit_sink_streams_frames_in_order(renderer, orc):
     got.clear()
     assert renderer.render_orbit(S.SceneData(w, h, sky), times, lambda f, v: got.setdefault(f, True) and f >= 2) == 3
     assert list(got) == [0, 1, 2]
+
+
+def _orbit_worker(rank, world, port, w, h, nframes, out_path):
+    import torch.distributed as dist
+    from terminalraytracer_b200 import pipeline, renderer as R
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rd = R.Renderer(0)
+    try:
+        sky = S.synthetic_cubemap("uv_gradient", 64)
+        rd.upload_skybox(sky)
+        orbit = pipeline.OrbitPipeline(rd, w, h, rank, world, slots_per_rank=2)
+        order = []
+        with open(out_path, "wb") if rank == 0 else open(os.devnull, "wb") as f:
+            done, written = orbit.stream(S.SceneData(w, h, sky), sharding.orbit_times(nframes),
+                                         (lambda k, view: order.append(k) or f.write(view) != len(view)))
+        assert done == len(sharding.frames_for_rank(nframes, rank, world))
+        if rank == 0:
+            assert written == nframes and order == list(range(nframes))
+    finally:
+        rd.close()
+        dist.destroy_process_group()
+
+
+def test_gpu_orbit_three_ranks_stream_in_order(orc, tmp_path):
+    """BASELINE config 4's sharding with three processes (one device here, one per GPU in bench.py): frame k on rank k mod 3
+    through trt_render_orbit_to, the bytes copied from the device straight into the shared page-locked ring, rank 0 writing
+    the frames to ONE file strictly in order while later frames render; the file equals the oracle's streams back to back"""
+    import socket
+    import torch.multiprocessing as mp
+    w, h, nframes = 96, 54, 10
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    out = str(tmp_path / "orbit.bin")
+    mp.spawn(_orbit_worker, args=(3, port, w, h, nframes, out), nprocs=3, join=True)
+    got = np.fromfile(out, dtype=np.uint8).reshape(nframes, abi.stream_bytes(w, h))
+    sky = S.synthetic_cubemap("uv_gradient", 64)
+    for k, t in enumerate(sharding.orbit_times(nframes)):
+        sc = S.SceneData(w, h, sky).set_time(t)
+        assert np.array_equal(got[k], U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc))), k
 
 
 def _peer_worker(rank, world, port, w, h, out_path, mode):
