@@ -38,25 +38,44 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WIDTH, HEIGHT, SKYBOX, T_POSE = 7680, 4320, "milky_way", 3.7
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this workload on one GPU
-# (profiles/r01f_k1_k2_ncu_summary.txt): K1 15.4 MB + 107.9 MB (the 133 MB of quantised cells, partly still in L2 at the end;
-# scene, skybox and the sample scratch stay in L2), K2 132.7 MB + 770.6 MB (the rest of the 829 MB stream was still in L2)
-NCU_DRAM_BYTES = {"k_render": 15.381e6 + 107.915e6, "k_encode": 132.727e6 + 770.604e6}
-CPU_SAMPLE_W, CPU_SAMPLE_H = 480, 270   # same 16:9 framing, 1/256 of the pixels
+# BASELINE.json `configs`: [2] is the headline (default); the others are selected with --config and are measured with the
+# same harness (profiles/r02_config*.json); [0] is the reference's own CPU case and has no GPU line.
+CONFIGS = {
+    "demo8k": {"label": "BASELINE config 2", "kind": "demo", "width": 7680, "height": 4320, "skybox": "milky_way", "t": 3.7,
+               "cpu_rows": list(range(128, 4320, 256))},
+    "demo4k": {"label": "BASELINE config 1", "kind": "demo", "width": 3840, "height": 2160, "skybox": "uv_checker", "t": 3.7,
+               "cpu_rows": list(range(64, 2160, 128))},
+    "stress": {"label": "BASELINE config 3", "kind": "stress", "spheres": 1024, "width": 3840, "height": 2160, "skybox": "uv_checker", "t": 3.7,
+               "cpu_rows": [270, 810, 1350, 1890]},
+    "orbit": {"label": "BASELINE config 4", "kind": "demo", "width": 1920, "height": 1080, "skybox": "milky_way", "frames": 360,
+              "cpu_frames": [0, 120, 240], "cpu_rows": list(range(32, 1080, 64))},
+}
+TRAFFIC_STAMP = os.path.join(ROOT, "profiles", "k1_k2_traffic_stamp.json")
 
 
-def workload_config(n_gpus):
+def workload_config(cfg, n_gpus):
+    w, h = cfg["width"], cfg["height"]
+    if cfg["kind"] == "stress":
+        what = f"synthetic stress scene: {cfg['spheres']} random spheres with mixed materials (splitmix64 seed 0x5EED1024, SURVEY 8d) + checker ground + 1 directional + 1 point light"
+    else:
+        what = "default demo scene (6 spheres + checker ground + 1 directional + 1 point light)"
+    sky = cfg["skybox"] + (" (synthetic 1024^2 x 6 stand-in: the reference's milky_way assets are not in its checkout)" if cfg["skybox"] == "milky_way" else " (the reference's own asset)")
+    if "frames" in cfg:
+        pose = f"{cfg['frames']}-frame camera orbit, t_k = k*20/{cfg['frames']} s (one yaw turn at the reference's 0.05 rev/s)"
+        shard = (f"frame k on rank k mod {n_gpus}; every rank copies its frames from the device into one shared page-locked ring over its own "
+                 f"PCIe link, rank 0 writes them out strictly in order (no gather, no data-path collective)") if n_gpus > 1 else "single GPU"
+    else:
+        pose = f"orbit pose t={cfg['t']}s"
+        shard = (f"cost-weighted contiguous row-bands x{n_gpus} (1/8-resolution cost pre-pass, then feedback from the ranks' measured K1 "
+                 f"times); every rank's encoded bytes go into rank 0's stream over NVLink peer memory (see 'gather'); one small NCCL "
+                 f"all-gather (the K1 times) ends the step") if n_gpus > 1 else "single GPU"
     return {
-        "workload": f"default demo scene (6 spheres + checker ground + 1 directional + 1 point light), {WIDTH}x{HEIGHT} cells, "
-                    f"10 samples/pixel, bounce limit 10, skybox {SKYBOX} (synthetic 1024^2 x 6 stand-in: the reference's "
-                    f"milky_way assets are not in its checkout), orbit pose t={T_POSE}s",
-        "width": WIDTH, "height": HEIGHT, "samples_per_pixel": 10, "bounce_limit": 10, "skybox": SKYBOX,
-        "sharding": (f"cost-weighted contiguous row-bands x{n_gpus} (1/8-resolution cost pre-pass, then feedback from the ranks' measured K1 "
-                     f"times); every rank's encoded bytes go into rank 0's stream over NVLink peer memory (see 'gather'); one small NCCL "
-                     f"all-gather (the K1 times) ends the step") if n_gpus > 1 else "single GPU",
-        "l2": "no explicit flush: each step writes 133 MB of cells + 829 MB of stream (> 126 MB L2); inputs (scene 1 KB, "
-              "skybox 25 MB) are meant to stay cache resident, the kernel is ALU-bound",
+        "workload": f"{cfg['label']}: {what}, {w}x{h} cells, 10 samples/pixel, bounce limit 10, skybox {sky}, {pose}",
+        "width": w, "height": h, "samples_per_pixel": 10, "bounce_limit": 10, "skybox": cfg["skybox"],
+        "sharding": shard,
+        "l2": f"no explicit flush: each step writes {4 * w * h / 1e6:.0f} MB of cells + {(25 * w + 1) * h / 1e6:.0f} MB of stream"
+              + (" (> 126 MB L2)" if 29 * w * h > 126e6 else " per frame, a different camera pose every frame") +
+              "; inputs (scene 1 KB, skybox 25 MB) are meant to stay cache resident, the kernel is bound by instruction issue, not memory",
     }
 
 
@@ -119,51 +138,176 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------
 # CPU reference timing (the only place bench.py executes anything under oracle/)
 
-def time_reference_cpu(width, height, repeats):
-    """project_scene of the unmodified reference (oracle/_ref) — or of the oracle port when the reference
-    build is absent — on ONE host thread (the reference is single-threaded as written)."""
-    import numpy as np
-    from terminalraytracer_b200 import abi, scene as S
-    from tests import _util as U
-    if U.have_reference_build():
-        lib, fn, kind = U.load_reference(), "project_scene", "reference"
-    else:
-        lib, fn, kind = U.load_oracle(), "orc_project_scene", "port"
-    sky = S.get_skybox(SKYBOX)
-    sc = S.SceneData(width, height, sky).set_time(T_POSE)
-    px = np.zeros((height, width, 3))
-    scr = abi.Screen(px.ctypes.data_as(C.POINTER(abi.Vector)), width, height)
-    times = []
-    for _ in range(repeats):
+def _stress_spheres(n):
+    """the stress scene's spheres as trt_stress_scene (csrc/trt_host.c) generates them — restated here so that the reference
+    arm builds its input without mapping the product library (tests/test_host.py checks the two agree bit for bit)"""
+    from terminalraytracer_b200 import abi
+    mask = (1 << 64) - 1
+    state = [0x5EED1024]
+
+    def unit():
+        state[0] = (state[0] + 0x9E3779B97F4A7C15) & mask
+        z = state[0]
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & mask
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & mask
+        z ^= z >> 31
+        return float(z >> 11) * (1.0 / 9007199254740992.0)
+
+    def rng(lo, hi):
+        return lo + unit() * (hi - lo)
+
+    reflect = (0.0, 0.2, 0.8, 1.0)
+    out = (abi.Sphere * n)()
+    made = 0
+    while made < n:
+        cx, cy, cz = rng(-8.0, 8.0), rng(-1.5, 6.0), rng(-8.0, 8.0)
+        radius = rng(0.1, 0.5)
+        r, g, b = rng(0.0, 1.0), rng(0.0, 1.0), rng(0.0, 1.0)
+        d = (cx * cx + cy * cy + cz * cz) ** 0.5
+        if 1.99 - radius - 0.05 < d < 1.99 + radius + 0.05:
+            continue
+        out[made] = abi.Sphere(abi.Vector(cx, cy, cz), abi.Material(abi.Vector(r, g, b), reflect[made & 3], 100.0), radius)
+        made += 1
+    return out
+
+
+class ReferenceCPU:
+    """The reference's own project_scene on ONE host thread (it is single-threaded as written), on rows sampled from the REAL
+    frame of the configured workload: oracle/_ref/libtrt_ref_rows.so is the unmodified TU with the row loop of TRT.c:973
+    bounded (oracle/Makefile); the scene comes from the reference's init_camera, the literals of its main() and its camera
+    recipe (oracle/ref_harness.c: ref_demo_scene, ref_orbit_camera).  The product library is never loaded here.  Falls back to
+    the oracle port (kind "port") when the reference build did not travel to the box."""
+
+    def __init__(self, cfg):
+        from terminalraytracer_b200 import abi, scene as S
+        self.cfg, self.abi = cfg, abi
+        root = os.path.join(ROOT, "oracle")
+        ref_rows, ref_so = os.path.join(root, "_ref", "libtrt_ref_rows.so"), os.path.join(root, "_ref", "libtrt_ref.so")
+        if os.path.exists(ref_rows):
+            self.lib, self.kind = C.CDLL(ref_rows), "reference"
+            self.render = self.lib.ref_project_rows
+            self.render.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Screen), C.c_int, C.c_int]
+        else:
+            port = os.path.join(root, "_build", "libtrt_oracle.so")
+            if not os.path.exists(port):
+                subprocess.check_call(["make", "-s", "-C", root, "oracle"])
+            self.lib, self.kind = C.CDLL(port), "port"
+            self.lib.orc_render_rows.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Screen), C.c_int, C.c_int, C.c_void_p]
+            self.render = lambda sc, scr, r0, r1: self.lib.orc_render_rows(sc, scr, r0, r1, None)
+        w, h = cfg["width"], cfg["height"]
+        self.sky = S.get_skybox(cfg["skybox"])              # numpy + ctypes only
+        self.scene = abi.Scene()
+        self.scene.skybox = self.sky.c
+        self.dl, self.pl = abi.DirectionalLight(), abi.PointLight()
+        self.spheres = (abi.Sphere * 6)()
+        builder = C.CDLL(ref_so) if os.path.exists(ref_so) else None
+        if builder is not None:
+            builder.ref_demo_scene.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Sphere), C.POINTER(abi.DirectionalLight),
+                                               C.POINTER(abi.PointLight), C.c_int, C.c_int]
+            builder.ref_orbit_camera.argtypes = [C.POINTER(abi.Camera), C.c_double]
+            builder.ref_demo_scene(C.byref(self.scene), self.spheres, C.byref(self.dl), C.byref(self.pl), w, h)
+            self.pose = lambda t: builder.ref_orbit_camera(C.byref(self.scene.camera), float(t))
+            self.scene_by = "the reference's init_camera / main() literals / camera recipe (oracle/_ref/libtrt_ref.so)"
+        else:
+            # no reference build on this box: the product's host C helpers (bit-identical, tests/test_host.py) build the scene
+            sd = S.SceneData(w, h, self.sky)
+            self.keep = sd
+            self.scene, self.spheres = sd.c, sd.spheres
+            self.pose = lambda t: sd.set_time(t)
+            self.scene_by = "libtrt_b200's host C helpers (no reference build on this box)"
+        if cfg["kind"] == "stress":
+            self.spheres = _stress_spheres(cfg["spheres"])
+            self.scene.spheres = C.cast(self.spheres, C.POINTER(abi.Sphere))
+            self.scene.num_spheres = cfg["spheres"]
+        self.rows = [r for r in cfg["cpu_rows"] if r < h]
+        self.frames = [sharding_time(cfg, k) for k in cfg.get("cpu_frames", [None])]
+        import numpy as np
+        self.px = np.zeros((len(self.rows), w, 3))
+
+    def rays_per_pass(self):
+        return 10.0 * self.cfg["width"] * len(self.rows) * len(self.frames)
+
+    def one_pass(self):
+        """every sampled row of every sampled pose once; returns seconds"""
+        w, h = self.cfg["width"], self.cfg["height"]
         t0 = time.perf_counter()
-        getattr(lib, fn)(C.byref(sc.c), C.byref(scr))
-        times.append(time.perf_counter() - t0)
-    return kind, times
+        for t in self.frames:
+            self.pose(t)
+            for i, r in enumerate(self.rows):
+                base = self.px[i:].ctypes.data - r * w * 24     # a Screen whose row r lands at px[i]
+                scr = self.abi.Screen(C.cast(C.c_void_p(base), C.POINTER(self.abi.Vector)), w, h)
+                self.render(C.byref(self.scene), C.byref(scr), r, r + 1)
+        return time.perf_counter() - t0
+
+    def sample_text(self, passes):
+        cfg = self.cfg
+        where = (f"{len(self.rows)} rows (every {self.rows[1] - self.rows[0]}th, first {self.rows[0]}) of the real "
+                 f"{cfg['width']}x{cfg['height']} frame" if len(self.rows) > 1 else f"row {self.rows[0]}")
+        if "frames" in cfg:
+            where += f" at frames {cfg['cpu_frames']} of the {cfg['frames']}-frame orbit"
+        return (f"{passes} timed passes over {where} = {self.rays_per_pass() / 1e6:.3f} M primary rays per pass; project_scene of the "
+                f"{'unmodified reference TU (row loop bounded, oracle/Makefile)' if self.kind == 'reference' else 'oracle port'}, "
+                f"gcc -O3 -ffp-contract=off, 1 thread as the reference is written; scene built by {self.scene_by}")
 
 
-def run_reference_arm(args):
+def sharding_time(cfg, k):
+    return cfg["t"] if k is None else k * (20.0 / cfg["frames"])
+
+
+def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    kind, times = time_reference_cpu(CPU_SAMPLE_W, CPU_SAMPLE_H, args.warmup + args.steps)
-    timed = times[args.warmup:]
-    total = sum(timed)
-    rays = 10.0 * CPU_SAMPLE_W * CPU_SAMPLE_H * len(timed)
-    value = rays / total / 1e6
-    sample = (f"{len(timed)} frames of the same scene, pose and skybox at {CPU_SAMPLE_W}x{CPU_SAMPLE_H} "
-              f"(1/256 of the pixels of the {WIDTH}x{HEIGHT} workload; cost per ray is resolution independent), "
-              f"1 thread as written, {'unmodified reference TU' if kind == 'reference' else 'oracle port'} built -O3 -ffp-contract=off")
+    cpu = ReferenceCPU(cfg)
+    times = [cpu.one_pass() for _ in range(args.warmup + args.steps)][args.warmup:]
+    total = sum(times)
+    value = cpu.rays_per_pass() * len(times) / total / 1e6
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": 1, "kind": kind, "sample": sample,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(cfg, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": 1, "kind": cpu.kind, "sample": cpu.sample_text(len(times)),
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if "frames" in cfg:
+        line["frames_per_s"] = value * 1e6 / (10.0 * cfg["width"] * cfg["height"])
     print(json.dumps(line))
     return 0
+
+
+def cpu_baseline_leg(cfg, budget_s=20.0):
+    """cpu_baseline of the product arm: the same sampler, about budget_s seconds of single-thread CPU work"""
+    cpu = ReferenceCPU(cfg)
+    first = cpu.one_pass()                       # warm-up pass, also sizes the loop
+    passes = max(2, min(12, int(budget_s / max(first, 1e-3))))
+    times = [cpu.one_pass() for _ in range(passes)]
+    mean, best = sum(times) / len(times), min(times)
+    out = {"value": cpu.rays_per_pass() / mean / 1e6, "unit": "Mrays/s", "cores": 1, "kind": cpu.kind,
+           "best_value": cpu.rays_per_pass() / best / 1e6, "host_cores_available": os.cpu_count(), "sample": cpu.sample_text(passes)}
+    if "frames" in cfg:
+        out["frames_per_s"] = out["value"] * 1e6 / (10.0 * cfg["width"] * cfg["height"])
+    return out
+
+
+def traffic_stamp():
+    """DRAM bytes per launch of K1 / K2 from the last `ncu --set full` capture of the bench workload, stamped with the hash of the
+    kernel sources it was taken at (scripts/stamp_traffic.py); `current` says whether the kernels are still those."""
+    import hashlib
+    try:
+        with open(TRAFFIC_STAMP) as f:
+            st = json.load(f)
+    except (OSError, ValueError):
+        return None
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "terminalraytracer_b200", "csrc")
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(csrc, name), "rb") as f:
+                h.update(f.read())
+    st["current"] = st.get("kernel_sources_sha256") == h.hexdigest()
+    return st
 
 
 # --------------------------------------------------------------------------------------------------------
