@@ -166,7 +166,7 @@ def _stress_spheres(n):
         d = (cx * cx + cy * cy + cz * cz) ** 0.5
         if 1.99 - radius - 0.05 < d < 1.99 + radius + 0.05:
             continue
-        out[made] = abi.Sphere(abi.Vector(cx, cy, cz), abi.Material(abi.Vector(r, g, b), reflect[made & 3], 100.0), radius)
+        out[made] = abi.Sphere(abi.Vector(cx, cy, cz), radius, abi.Material(abi.Vector(r, g, b), reflect[made & 3], 100.0))
         made += 1
     return out
 
@@ -291,6 +291,19 @@ def cpu_baseline_leg(cfg, budget_s=20.0):
     return out
 
 
+def host_pieces(world):
+    """Piece schedule of the host-stream path (e2e, N > 1): a rank's band leaves for the host piece by piece, each copy behind
+    the next piece's K1.  Per rank K1 takes T = K1_frame / N and its copy C = bytes / (N * link rate); the step ends at
+    max(T + last copy, first piece's K1 + C) — so the first piece must be SMALL (the copy engine starts early) when C is close to
+    or above T (few GPUs: the copy is the floor), and the last piece small in any case.  Measured rates on this box class:
+    K1 ~23.7 ms per frame, ~50 GB/s per link, ~80 GB/s aggregate host ingest (scripts/pcie_bw.py)."""
+    k1, link, ingest, total = 23.7e-3 / world, 50e9, 80e9, 829.4e6
+    copy = total / min(world * link, ingest)
+    if copy >= 0.8 * k1:
+        return (0.06, 0.14, 0.22, 0.26, 0.2, 0.12)      # copy-bound: start copying after ~6 % of K1, keep the engine fed
+    return (0.3, 0.3, 0.25, 0.15)                        # K1-bound: fewer launches, small exposed tail
+
+
 def traffic_stamp():
     """DRAM bytes per launch of K1 / K2 from the last `ncu --set full` capture of the bench workload, stamped with the hash of the
     kernel sources it was taken at (scripts/stamp_traffic.py); `current` says whether the kernels are still those."""
@@ -311,23 +324,205 @@ def traffic_stamp():
 
 
 # --------------------------------------------------------------------------------------------------------
+# BASELINE config 4: the camera orbit, frame-sharded, streamed in order
+
+def run_orbit(args, cfg):
+    """--config orbit.  A step is one frame of the orbit; --steps K renders frames 0..K-1 of the 360-frame path (default: all 360),
+    frame k on rank k mod N ("scaling": strong — the animation is fixed, the ranks share it).
+      value  frames/s with every rank's frames rendered and encoded on the device (K1 + K2 per frame, camera re-posed and the
+             scene constants uploaded every frame), device-timed per rank, max over ranks.
+      e2e    frames/s through OrbitPipeline.stream: trt_render_orbit_to on every rank, device -> shared page-locked ring over
+             the rank's own PCIe link, rank 0 writes every frame to /dev/null strictly in order (one write per frame, TRT.c:1171);
+             wall clock between barriers."""
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    import hashlib
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from terminalraytracer_b200 import abi, pipeline, renderer as R, scene as S, sharding
+
+    width, height = cfg["width"], cfg["height"]
+    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_frames = cfg["frames"] if args.steps is None else args.steps
+    times = [k * (20.0 / cfg["frames"]) for k in range(n_frames)]
+    mine = sharding.frames_for_rank(n_frames, rank, world)
+    rd = R.Renderer(local_rank)
+    sky = S.get_skybox(cfg["skybox"])
+    rd.upload_skybox(sky)
+    peaks = rd.measure_peaks() if rank == 0 else None
+    sc = S.SceneData(width, height, sky)
+    total_bytes = abi.stream_bytes(width, height)
+    stream = torch.cuda.current_stream()
+    rd.use_stream(stream.cuda_stream)
+    quant = torch.empty(width * height * 4, dtype=torch.uint8, device="cuda")
+    dev_stream = torch.empty(total_bytes + 16, dtype=torch.uint8, device="cuda")
+
+    k1_pairs = []
+
+    def device_frame(k, timed):
+        sc.set_time(times[k])
+        rd.set_scene_async(sc)                               # H2D of the re-posed scene, no host wait
+        a = b = None
+        if timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+        rd.render_rows_quant(width, height, 0, height, quant.data_ptr())
+        if timed:
+            b.record(stream)
+            k1_pairs.append((a, b))
+        rd.stream_frame(dev_stream.data_ptr(), width, height)
+        rd.encode_rows_quant(quant.data_ptr(), width, height, dev_stream.data_ptr(), abi.HOME_BYTES)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for k in mine[:max(args.warmup, 3)]:
+        device_frame(k, False)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
+    t0.record(stream)
+    for k in mine:
+        device_frame(k, True)
+    t1.record(stream)
+    barrier()
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = t0.elapsed_time(t1)
+    k1_ms = sum(a.elapsed_time(b) for a, b in k1_pairs)
+
+    # algorithmic flops: three poses of the path, counted by the kernel itself (untimed)
+    flops = []
+    if rank == 0:
+        for k in sorted(set(int(f * n_frames / cfg["frames"]) for f in cfg["cpu_frames"] if int(f * n_frames / cfg["frames"]) < n_frames)):
+            sc.set_time(times[k])
+            rd.set_scene(sc)
+            flops.append(rd.count_rows(width, height, 0, height)[1])
+    rd.use_stream(None)
+
+    # ---- end to end: ordered stream to /dev/null ----------------------------------------------------------------
+    orbit = pipeline.OrbitPipeline(rd, width, height, rank, world)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+
+    def write(k, view):
+        return os.write(devnull, view) != len(view)
+
+    warm = [k * (20.0 / cfg["frames"]) for k in range(min(n_frames, 4 * world))]
+    orbit.stream(S.SceneData(width, height, sky), warm, write)
+    barrier()
+    w0 = time.perf_counter()
+    done, written = orbit.stream(S.SceneData(width, height, sky), times, write)
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    os.close(devnull)
+
+    # untimed check: the first frames of the ordered stream are byte-identical to single-GPU renders of the same poses
+    check_n = min(n_frames, max(2 * world, 4))
+    got = []
+    orbit.stream(S.SceneData(width, height, sky), times[:check_n], lambda k, view: got.append(hashlib.sha256(view).hexdigest()) and False)
+    ordered_ok = None
+    if rank == 0:
+        want = []
+        one = S.SceneData(width, height, sky)
+        for k in range(check_n):
+            one.set_time(times[k])
+            want.append(hashlib.sha256(np.array(rd.render_ansi(one)).tobytes()).hexdigest())
+        ordered_ok = got == want
+    barrier()
+
+    stats = torch.tensor([dev_ms, k1_ms, e2e_s * 1e3, float(done)], dtype=torch.float64, device="cuda")
+    mx, sm = stats.clone(), stats.clone()
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        dev_ms_max, k1_ms_max, e2e_ms = mx[0].item(), mx[1].item(), mx[2].item()
+        fps, e2e_fps = n_frames / (dev_ms_max * 1e-3), n_frames / (e2e_ms * 1e-3)
+        rays = 10.0 * width * height
+        flops_per_frame = sum(flops) / max(len(flops), 1)
+        frames_slowest = len(sharding.frames_for_rank(n_frames, 0, world))
+        achieved = flops_per_frame * frames_slowest / (k1_ms_max * 1e-3) / 1e12
+        peak32, peak64 = peaks["fp32_tflops"], peaks["fp64_tflops"]
+        line = {
+            "metric": "frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": n_frames, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms_max / max(frames_slowest, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(cfg, world),
+            "mrays_per_s": fps * rays / 1e6,
+            "frames_rendered_all_ranks": int(sm[3].item()), "frames_written_in_order": int(written),
+            "roofline": {
+                "bound": "alu-fp32 (issue slots of the CUDA cores)", "achieved": achieved, "peak": peak32, "unit": "TFLOP/s", "frac": achieved / peak32,
+                "achieved_is": "ALGORITHMIC flops (SURVEY 8d counter model, mean of three poses of the path) x frames of a rank / that rank's summed K1 time",
+                "traffic": None, "kernel": "k_render (K1) incl. k_tile_certs", "kernel_ms": k1_ms_max / max(frames_slowest, 1),
+                "flops_per_primary_ray": flops_per_frame / rays, "frac_of_fp64_peak": achieved / peak64, "fp64_peak": peak64,
+                "peak_source": "FFMA / DFMA loops measured in this run by libtrt_b200"},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "mrays_per_s": e2e_fps * rays / 1e6, "ms_per_frame": e2e_ms / n_frames,
+                    "h2d_bytes_per_step": int(C.sizeof(abi.Scene) + C.sizeof(abi.Sphere) * 6 + C.sizeof(abi.DirectionalLight) + C.sizeof(abi.PointLight)),
+                    "d2h_bytes_per_step": int(total_bytes), "host_ingest_gb_per_s": e2e_fps * total_bytes / 1e9,
+                    "call": "OrbitPipeline.stream: trt_render_orbit_to(first=rank, stride=N) per rank into the shared page-locked ring, rank 0 writes "
+                            "every frame to /dev/null in order while later frames render"},
+            # per frame: k_tile_certs, k_render, k_stream_frame, k_encode — in the device-timed region
+            "gpu_launches": 4 * n_frames,
+            "ordered_stream_identical_to_single_gpu": ordered_ok, "frames_checked": check_n,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline_leg(cfg)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    barrier()
+    orbit.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    rd.close()
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------------
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="default: 20 frames (frame configs) / the whole 360-frame path (orbit)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--width", type=int, default=WIDTH)
-    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--config", default="demo8k", choices=sorted(CONFIGS),
+                    help="BASELINE.json configs: demo8k = [2] (default, the headline), demo4k = [1], stress = [3], orbit = [4]")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused", type=int, default=int(os.environ.get("TRT_BENCH_FUSED", "-1")),
                     help="N > 1, device-resident gather: 1 = K1 stores the encoded tiles straight into rank 0's stream over NVLink (no K2, "
                          "no copies), 0 = K1, K2 and copy-engine pushes piece by piece, -1 = by GPU count (measured: pieces win at 2 GPUs, "
                          "14.8 vs 15.7 ms, the fused kernel at 8, 4.21 vs 4.38 ms)")
     args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.width and args.height and (args.width, args.height) != (cfg["width"], cfg["height"]):
+        cfg.update(width=args.width, height=args.height, label=cfg["label"] + " (resized on the command line)",
+                   cpu_rows=[r for r in range(0, args.height, max(1, args.height // 16))])
     if args.impl == "reference":
-        return run_reference_arm(args)
+        if args.steps is None:
+            args.steps = 20 if "frames" not in cfg else 5
+        return run_reference_arm(args, cfg)
+    if "frames" in cfg and args.impl != "reference":
+        return run_orbit(args, cfg)
+    if args.steps is None:
+        args.steps = 20
 
     # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner) goes to stderr instead
     sys.stdout.flush()
@@ -339,7 +534,8 @@ def main():
     import torch.distributed as dist
     from terminalraytracer_b200 import abi, pipeline, renderer as R, scene as S
 
-    width, height = args.width, args.height
+    width, height = cfg["width"], cfg["height"]
+    headline = args.config == "demo8k" and (width, height) == (CONFIGS["demo8k"]["width"], CONFIGS["demo8k"]["height"])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -358,9 +554,9 @@ def main():
         torch.cuda.synchronize()
 
     rd = R.Renderer(local_rank)
-    sky = S.get_skybox(SKYBOX)
+    sky = S.get_skybox(cfg["skybox"])
     rd.upload_skybox(sky)
-    sc = S.SceneData(width, height, sky).set_time(T_POSE)
+    sc = S.SceneData(width, height, sky, kind=cfg["kind"], num_spheres=cfg.get("spheres", 1024)).set_time(cfg["t"])
     # cost-weighted row bands (sky rows are ~5x cheaper than sphere/ground rows): every rank runs the same
     # deterministic 1/8-resolution pre-pass and derives the same bands; untimed, once per scene
     weights = rd.estimate_row_costs(sc) if world > 1 else None
@@ -394,7 +590,8 @@ def main():
     t_begin.record(stream)
     for _ in range(args.steps):
         step()
-    t_end.record(stream)
+    t_end.record(stream)      # rank 0's stream ends with the device-side wait for every rank's last step
+    pipe.finish()
     barrier()
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
@@ -405,7 +602,21 @@ def main():
 
     # ---- algorithmic flops of this rank's band (untimed counting launch of the same kernel) ------------
     rd.set_scene(sc)
-    counters, band_flops = rd.count_rows(width, height, pipe.row0, pipe.row1)
+    flops_note = "work counters of the whole band (counting flavour of K1, untimed)"
+    if cfg["kind"] == "stress" and pipe.row1 - pipe.row0 > 8:
+        # the counting flavour answers every query the reference's way as well (1024 exact sphere tests per query): count 8 evenly
+        # spaced rows of the band and scale — the as-written model is only a yardstick here, the kernel skips most of that work
+        rows = sorted(set(pipe.row0 + (i * (pipe.row1 - pipe.row0 - 1)) // 7 for i in range(8)))
+        counters, band_flops = [0] * abi.NUM_COUNTERS, 0.0
+        for r in rows:
+            c, f = rd.count_rows(width, height, r, r + 1)
+            counters = [a + b for a, b in zip(counters, c)]
+            band_flops += f
+        scale = (pipe.row1 - pipe.row0) / len(rows)
+        counters, band_flops = [int(c * scale) for c in counters], band_flops * scale
+        flops_note = f"work counters of {len(rows)} evenly spaced rows of the band, scaled by rows (the counting flavour tests all 1024 spheres per query)"
+    else:
+        counters, band_flops = rd.count_rows(width, height, pipe.row0, pipe.row1)
 
     # N > 1: the assembled stream must be byte-identical to a single-GPU render of the same frame (untimed check)
     stream_ok = None
@@ -442,8 +653,8 @@ def main():
         # its own PCIe link (no device-side gather); bands start from the converged ones of the device-resident steps
         shared = pipeline.SharedHostStream(rd, total_bytes, rank, world)
         # (PCIe is ~15x slower than NVLink: more, geometrically shrinking pieces keep the exposed last copy short)
-        host_pipe = pipeline.FramePipeline(rd, width, height, rank, world, row_weights=pipe.weights, pieces=(0.4, 0.3, 0.2, 0.1), adapt=True,
-                                           host_stream=shared.ptr)     # (fused zero-copy stores over PCIe were measured slower: 11.5 vs 10.6 ms at 8 GPUs)
+        host_pipe = pipeline.FramePipeline(rd, width, height, rank, world, row_weights=pipe.weights, pieces=host_pieces(world), adapt=True,
+                                           host_stream=shared.ptr, host_sync=shared)     # (fused zero-copy stores over PCIe were measured slower: 11.5 vs 10.6 ms at 8 GPUs)
     elif world > 1 and rank == 0:
         host_out = torch.empty(total_bytes, dtype=torch.uint8).pin_memory()   # no room in /dev/shm: rank 0 copies the gathered stream out
 
@@ -502,34 +713,52 @@ def main():
             hbm_src = "MEASURED_PEAKS.json hbm_gbs"
         except (OSError, KeyError, ValueError):
             hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
+        stamp = traffic_stamp() if (world == 1 and headline) else None
+        k1_traffic = stamp["k_render_dram_bytes_per_launch"] if stamp else None
+        executed = None
+        if stamp and stamp.get("k_render_executed"):
+            ex = stamp["k_render_executed"]
+            executed = {"fp64_flop_per_launch": ex["fp64_flop"], "fp32_flop_per_launch": ex["fp32_flop"],
+                        "fp64_tflops": ex["fp64_flop"] / (k1_ms_max * 1e-3) / 1e12, "fp32_tflops": ex["fp32_flop"] / (k1_ms_max * 1e-3) / 1e12,
+                        "frac_of_fp64_peak": ex["fp64_flop"] / (k1_ms_max * 1e-3) / 1e12 / peak64,
+                        "warp_instructions": ex.get("warp_instructions"), "issue_active_pct": ex.get("issue_active_pct"),
+                        "what": "arithmetic the kernel really executes (ncu sass counters of the stamped capture; packed FFMA2/FADD2/FMUL2 "
+                                "certificate arithmetic is not in the scalar FP32 counters): the certificates rule out most of the "
+                                "reference's as-written sphere tests, so this is well below the algorithmic figure by design"}
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+            "dtype": "f64", "data": "synthetic", "config": workload_config(cfg, world),
             "frames_per_s": args.steps / (ms_total * 1e-3),
             "roofline": {
-                "bound": "alu-fp32", "achieved": achieved, "peak": peak32, "unit": "TFLOP/s", "frac": achieved / peak32,
-                "traffic": NCU_DRAM_BYTES["k_render"] if (world == 1 and (width, height) == (WIDTH, HEIGHT)) else None,
-                "traffic_unit": "bytes of DRAM traffic per launch (ncu, profiles/r01f_k1_k2_ncu_summary.txt)",
-                "kernel": "k_render (K1)", "kernel_ms": k1_ms_max,
+                "bound": "alu-fp32 (issue slots of the CUDA cores; no dense contraction, ~400 flop/byte)", "achieved": achieved, "peak": peak32,
+                "unit": "TFLOP/s", "frac": achieved / peak32,
+                "achieved_is": "ALGORITHMIC flops (the reference's as-written work, SURVEY 8d counter model) per launch / kernel time — "
+                               "not executed flops, see 'executed'",
+                "traffic": k1_traffic,
+                "traffic_source": None if not stamp else {k: stamp[k] for k in ("profile", "commit", "kernel_sources_sha256", "current") if k in stamp},
+                "traffic_unit": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full)",
+                "kernel": "k_render (K1) incl. its tile-certificate prepass k_tile_certs", "kernel_ms": k1_ms_max,
                 "algorithmic_flops_per_launch": frame_flops / world, "flops_per_primary_ray": frame_flops / rays_per_step,
+                "flops_counted_by": flops_note,
                 "peak_source": "FFMA loop measured in this run by libtrt_b200 (trt_measure_fp32_tflops); MEASURED_PEAKS.json "
                                "has no CUDA-core peak. The kernel executes FP64 (bit-exact parity), whose measured DFMA peak is "
                                f"{peak64:.2f} TFLOP/s",
                 "frac_of_fp64_peak": achieved / peak64, "fp64_peak": peak64,
+                "executed": executed,
             },
             "roofline_encode": None if enc_ms is None else {
                 "bound": "hbm", "achieved": (4.0 * width * rows + abi.row_bytes(width) * rows) / (enc_ms * 1e-3) / 1e9,
                 "peak": hbm_peak, "unit": "GB/s", "kernel": "k_encode (K2)", "kernel_ms": enc_ms, "peak_source": hbm_src,
                 "frac": (4.0 * width * rows + abi.row_bytes(width) * rows) / (enc_ms * 1e-3) / 1e9 / hbm_peak,
-                "traffic": NCU_DRAM_BYTES["k_encode"] if (world == 1 and (width, height) == (WIDTH, HEIGHT)) else None},
+                "traffic": stamp["k_encode_dram_bytes_per_launch"] if stamp else None},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(total_bytes),
                     "ms_per_step": e2e_ms_total / args.steps,
                     "call": "trt_render_ansi(scene,w,h,pinned_out,cap)" if world == 1 else
                             ("FramePipeline(host_stream=shared pinned buffer).render: every rank copies its bands to the host over its own PCIe link"
                              if shared is not None else "FramePipeline.render + D2H of the gathered stream on rank 0 (no room in /dev/shm)")},
-            # K1 + K2 per piece on every rank (fused: K1 alone), plus rank 0's trt_stream_frame_device once per step
-            "gpu_launches": int((1 if (world > 1 and fused) else 2) * k1_launches_all + args.steps),
+            # per piece on every rank: k_tile_certs (small scenes) + K1 (+ K2 unless fused), plus rank 0's trt_stream_frame_device once per step
+            "gpu_launches": int(((1 if (world > 1 and fused) else 2) + (1 if cfg["kind"] == "demo" else 0)) * k1_launches_all + args.steps),
             "gather": None if world == 1 else ("fused: K1 stores encoded tiles into rank 0's stream (NVLink peer memory)" if fused else
                                                "pieces: K1, K2, copy-engine push per piece (NVLink peer memory)"),
             "stream_identical_to_single_gpu": stream_ok,
@@ -540,15 +769,8 @@ def main():
             "work_counters_rank0": {"trace_calls": counters[9], "sphere_tests": counters[0], "sky_lookups": counters[8],
                                     "bounce_iters": counters[12], "lighting_calls": counters[11]},
         }
-        if not args.no_cpu_baseline:
-            kind, times = time_reference_cpu(CPU_SAMPLE_W, CPU_SAMPLE_H, 12)
-            best = min(times[1:])
-            mean = sum(times[1:]) / len(times[1:])
-            line["cpu_baseline"] = {
-                "value": 10.0 * CPU_SAMPLE_W * CPU_SAMPLE_H / mean / 1e6, "unit": "Mrays/s", "cores": 1, "kind": kind,
-                "best_value": 10.0 * CPU_SAMPLE_W * CPU_SAMPLE_H / best / 1e6, "host_cores_available": os.cpu_count(),
-                "sample": f"11 timed frames of the same scene, pose and skybox at {CPU_SAMPLE_W}x{CPU_SAMPLE_H} (1/256 of the pixels), "
-                          f"single thread as the reference is written, gcc -O3 -ffp-contract=off"}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline_leg(cfg)
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         if shared is not None:

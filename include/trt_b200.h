@@ -113,6 +113,10 @@ int trt_render_orbit_to(const trt_Scene *scene, int width, int height, const dou
 /* ---- device-resident pieces (row bands; used by the multi-GPU plumbing and by bench.py) ------- */
 /* Upload scene (spheres, ground, lights, camera) for subsequent *_device calls. */
 int trt_set_scene(const trt_Scene *scene);
+/* The same without waiting for the upload: the copies are enqueued on trt_stream() from page-locked staging (two arenas,
+ * an event behind each upload), so a host loop that re-poses the camera every frame never stalls on the device.  The
+ * scene is not retained: the caller's structures may change as soon as the call returns. */
+int trt_set_scene_async(const trt_Scene *scene);
 
 /* Render rows [row0,row1) of a width x height frame into d_pixels (device pointer to
  * (row1-row0)*width*3 doubles, band-local row-major).  Asynchronous on trt_stream(). */
@@ -145,6 +149,19 @@ int trt_ipc_close(void *d_peer_ptr);
 /* after everything enqueued so far on trt_stream(): copy `bytes` from d_src (this GPU) to d_peer_dst (any GPU) */
 int trt_push_to_peer(void *d_peer_dst, const void *d_src, size_t bytes);
 int trt_peer_copies_wait(void);
+/* Step completion without the host.  A frame is complete on rank 0 when every rank's bytes have landed; instead of a host-side
+ * collective per frame, every rank ends its step with trt_signal_step(flag of this rank inside rank 0's allocation, step number,
+ * after_copies) — a one-thread kernel behind the step's kernels (after_copies = 0, fused gather) or behind its copy-engine pushes
+ * (after_copies = 1) that stores the step number with system-scope fences — and rank 0 enqueues trt_wait_steps(flags, n, step): a
+ * kernel on ITS stream that waits (bounded: ~4 s, then flags[32] is set) until all n flags have reached the step.  The hosts never
+ * synchronise: every rank can enqueue step after step.  Back-pressure works the same way in the other direction: rank 0 signals
+ * "frame k consumed" into one more flag word once it has taken the frame, and the other ranks put trt_wait_steps(that word, 1, k)
+ * in front of their first write of frame k+1 (on_copy_stream: in front of the pushes instead of the kernels).
+ * The flag array (128 words, zeroed) lives behind rank 0's stream buffer. */
+int trt_signal_step(void *d_flag, unsigned int value, int after_copies);
+int trt_wait_steps(const void *d_flags, int n_flags, unsigned int value, int on_copy_stream);
+/* orders trt_stream() behind everything enqueued on the library's copy stream so far (the previous step's pushes) */
+int trt_stream_wait_copies(void);
 /* When the caller wants the stream in HOST memory (the buffer it fwrite()s, TRT.c:1171) the device-side gather is not
  * needed at all: every rank maps the same host buffer (POSIX shared memory), page-locks its mapping with
  * trt_host_register, and pushes its own bands there with trt_push_to_peer (the destination may be any address the
@@ -174,6 +191,13 @@ double trt_model_flops(const long long *counters);
  * get_skybox_color (TRT.c:700) for n directions (3 doubles each) -> 5 ints each: face, texel index, r, g, b. */
 int trt_probe_trace_ray(const trt_Scene *scene, const double *rays, int n, double *out);
 int trt_probe_skybox(const double *dirs, int n, int *out);
+/* single-function probes against the reference's own known answers (tests/golden/units.npz):
+ * ray_intersects_sphere TRT.c:638-672 — rays n x 6 (origin, direction), spheres n x 4 (centre, radius) -> out n x 4 (hit, point);
+ * ray_intersects_plane  TRT.c:677-695 against scene->ground — rays n x 6 -> out n x 4 (hit, point);
+ * apply_lighting        TRT.c:894-963 — surface n x 9 (point, unit normal, material colour) -> out n x 3 (lit colour, clamped) */
+int trt_probe_sphere(const double *rays, const double *spheres, int n, double *out);
+int trt_probe_plane(const trt_Scene *scene, const double *rays, int n, double *out);
+int trt_probe_lighting(const trt_Scene *scene, const double *surface, int n, double *out);
 
 /* Self-test of the shared-reciprocal division used by the normalisations (csrc/trt_device.cuh): evaluates
  * about `quotients` random and adversarial a/b on the GPU both ways and returns how many differ from the

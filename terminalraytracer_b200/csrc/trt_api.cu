@@ -85,6 +85,8 @@ struct Context {
     // pinned staging for scene uploads: copies from pageable memory make the runtime wait for the stream first, which
     // would serialise the frames of trt_render_orbit; two arenas so that a frame's upload never overwrites the previous one's
     PinnedBuffer arena[2];
+    cudaEvent_t arena_done[2] = {nullptr, nullptr};   // recorded behind the copies of the upload that last used the arena
+    bool arena_busy[2] = {false, false};
     size_t arena_used = 0;
     int arena_which = 0;
 } g;
@@ -172,6 +174,11 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
         const size_t per_sphere = sizeof(double4) * 2 + sizeof(DevMaterial) + sizeof(float4) * 2 + sizeof(CullPair) + sizeof(int) * 2;
         const size_t need = sizeof(DevScene) + 4096 + per_sphere * ((size_t)scene->num_spheres + 64);
         g.arena_which = wait ? 0 : (g.arena_which ^ 1);
+        // an arena may be rewritten only after the copies of the upload that last used it have run
+        if (g.arena_busy[g.arena_which]) {
+            CK(cudaEventSynchronize(g.arena_done[g.arena_which]));
+            g.arena_busy[g.arena_which] = false;
+        }
         if (g.arena[g.arena_which].cap < need) {
             CK(cudaStreamSynchronize(g.stream));       // nothing may still be reading the arena that is replaced
             g.arena[g.arena_which].reserve(need);
@@ -380,9 +387,8 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
     CK(cudaMemcpyAsync(g.sphere_cull.p, staged(cull.data(), sizeof(float4) * cull.size()), sizeof(float4) * cull.size(), cudaMemcpyHostToDevice, g.stream));
     // Every source goes through staged(): a memcpy into the page-locked arena g.arena[g.arena_which], so the vectors may die
     // when this function returns and the copies are truly asynchronous.  Invariant: an arena may be rewritten only after the
-    // stream work of the upload that last used it has completed — wait == true synchronises below (arena 0);
-    // trt_render_orbit (wait == false) alternates the two arenas and waits for the copied[] event of two frames back
-    // before it uploads again.
+    // copies of the upload that last used it have run — arena_done[] is recorded behind them and waited for at the top of
+    // this function; wait == false alternates the two arenas, so the host runs at most two uploads ahead of the device.
     CK(cudaMemcpyAsync(g.sphere_geom.p, staged(geom.data(), sizeof(double4) * geom.size()), sizeof(double4) * geom.size(), cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(g.sphere_mat.p, staged(mats.data(), sizeof(DevMaterial) * mats.size()), sizeof(DevMaterial) * mats.size(), cudaMemcpyHostToDevice, g.stream));
     // the same records two by two for the packed classification; the odd one out is paired with a sphere of radius 0
@@ -397,8 +403,13 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
     g.cull_pairs.reserve(sizeof(CullPair) * pairs.size());
     CK(cudaMemcpyAsync(g.cull_pairs.p, staged(pairs.data(), sizeof(CullPair) * pairs.size()), sizeof(CullPair) * pairs.size(), cudaMemcpyHostToDevice, g.stream));
     upload_scene_constants(*(const DevScene *)staged(&s, sizeof s), g.stream);
-    // wait: the caller's arena (0) is reused by the next call, and callers that time expect a resident scene on return
-    if (wait) CK(cudaStreamSynchronize(g.stream));
+    CK(cudaEventRecord(g.arena_done[g.arena_which], g.stream));
+    g.arena_busy[g.arena_which] = true;
+    // wait: callers that time expect a resident scene on return
+    if (wait) {
+        CK(cudaStreamSynchronize(g.stream));
+        g.arena_busy[g.arena_which] = false;
+    }
     g.have_scene = true;
 }
 
@@ -455,6 +466,24 @@ RenderParams make_params(int width, int height, int row0, int row1, double *d_pi
     return p;
 }
 
+// common part of the array probes: inputs up, kernel, outputs down
+template <typename Launch>
+void run_probe(const double *in, size_t in_doubles, double *out, size_t out_doubles, const double *in2, size_t in2_doubles, Launch launch)
+{
+    Buffer d_in, d_in2, d_out;
+    d_in.reserve(sizeof(double) * (in_doubles ? in_doubles : 1));
+    d_in2.reserve(sizeof(double) * (in2_doubles ? in2_doubles : 1));
+    d_out.reserve(sizeof(double) * (out_doubles ? out_doubles : 1));
+    CK(cudaMemcpyAsync(d_in.p, in, sizeof(double) * in_doubles, cudaMemcpyHostToDevice, g.stream));
+    if (in2_doubles) CK(cudaMemcpyAsync(d_in2.p, in2, sizeof(double) * in2_doubles, cudaMemcpyHostToDevice, g.stream));
+    launch((const double *)d_in.p, (const double *)d_in2.p, (double *)d_out.p);
+    CK(cudaMemcpyAsync(out, d_out.p, sizeof(double) * out_doubles, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    d_in.release();
+    d_in2.release();
+    d_out.release();
+}
+
 } // namespace
 
 extern "C" {
@@ -480,6 +509,8 @@ int trt_init(int device)
     g.stream = g.own_stream;
     CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
     for (auto &ev : g.ev) CK(cudaEventCreate(&ev));
+    for (auto &ev : g.arena_done) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    g.arena_busy[0] = g.arena_busy[1] = false;
     for (auto &row : g.chunk_ev)
         for (auto &ev : row) CK(cudaEventCreate(&ev));
     g.tile_counter.reserve(256);
@@ -524,6 +555,10 @@ void trt_shutdown(void)
     g.arena[0].release();
     g.arena[1].release();
     for (auto &ev : g.ev) {
+        if (ev) cudaEventDestroy(ev);
+        ev = nullptr;
+    }
+    for (auto &ev : g.arena_done) {
         if (ev) cudaEventDestroy(ev);
         ev = nullptr;
     }
@@ -604,6 +639,13 @@ int trt_set_scene(const trt_Scene *scene)
 {
     require_init("trt_set_scene");
     upload_scene(scene);
+    return 0;
+}
+
+int trt_set_scene_async(const trt_Scene *scene)
+{
+    require_init("trt_set_scene_async");
+    upload_scene(scene, false);
     return 0;
 }
 
@@ -722,6 +764,36 @@ int trt_probe_trace_ray(const trt_Scene *scene, const double *rays, int n, doubl
     CK(cudaStreamSynchronize(g.stream));
     d_in.release();
     d_out.release();
+    return 0;
+}
+
+int trt_probe_sphere(const double *rays, const double *spheres, int n, double *out)
+{
+    require_init("trt_probe_sphere");
+    if (n <= 0) return 0;
+    run_probe(rays, 6 * (size_t)n, out, 4 * (size_t)n, spheres, 4 * (size_t)n,
+              [&](const double *a, const double *b, double *o) { launch_probe_sphere(a, b, n, o, g.stream); });
+    return 0;
+}
+
+int trt_probe_plane(const trt_Scene *scene, const double *rays, int n, double *out)
+{
+    require_init("trt_probe_plane");
+    upload_scene(scene);
+    if (n <= 0) return 0;
+    run_probe(rays, 6 * (size_t)n, out, 4 * (size_t)n, nullptr, 0,
+              [&](const double *a, const double *, double *o) { launch_probe_plane(a, n, o, g.stream); });
+    return 0;
+}
+
+int trt_probe_lighting(const trt_Scene *scene, const double *surface, int n, double *out)
+{
+    require_init("trt_probe_lighting");
+    upload_scene(scene);
+    if (n <= 0) return 0;
+    RenderParams p = make_params(1, 1, 0, 1, nullptr, nullptr, false);
+    run_probe(surface, 9 * (size_t)n, out, 3 * (size_t)n, nullptr, 0,
+              [&](const double *a, const double *, double *o) { launch_probe_lighting(p, a, n, o, g.stream); });
     return 0;
 }
 
@@ -1029,6 +1101,33 @@ int trt_push_to_peer(void *d_peer_dst, const void *d_src, size_t bytes)
     CK(cudaEventRecord(g.ev[3], g.stream));
     CK(cudaStreamWaitEvent(g.copy_stream, g.ev[3], 0));
     CK(cudaMemcpyAsync(d_peer_dst, d_src, bytes, cudaMemcpyDefault, g.copy_stream));
+    return 0;
+}
+
+int trt_signal_step(void *d_flag, unsigned int value, int after_copies)
+{
+    require_init("trt_signal_step");
+    // behind the kernels of this step (trt_stream()) or, after_copies, behind the copy-engine pushes on the copy stream
+    launch_signal((unsigned int *)d_flag, value, after_copies ? g.copy_stream : g.stream);
+    return 0;
+}
+
+int trt_wait_steps(const void *d_flags, int n_flags, unsigned int value, int on_copy_stream)
+{
+    require_init("trt_wait_steps");
+    if (n_flags > 32 || n_flags <= 0) return -1;
+    // word 32 behind the first flag waited for records a timeout (a rank that never signalled)
+    launch_wait_flags((const unsigned int *)d_flags, n_flags, value, (unsigned int *)d_flags + 32, on_copy_stream ? g.copy_stream : g.stream);
+    return 0;
+}
+
+int trt_stream_wait_copies(void)
+{
+    require_init("trt_stream_wait_copies");
+    // work enqueued on trt_stream() from here on starts after everything enqueued on the copy stream so far (the previous
+    // step's pushes still read the buffers the next encode overwrites)
+    CK(cudaEventRecord(g.ev[2], g.copy_stream));
+    CK(cudaStreamWaitEvent(g.stream, g.ev[2], 0));
     return 0;
 }
 

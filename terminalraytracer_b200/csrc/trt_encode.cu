@@ -79,16 +79,19 @@ __device__ __forceinline__ void put_cell(unsigned int (&out)[ENC_CELLS_PER_THREA
     out[(OFF + 24) >> 2] |= 0x6du << (8 * ((OFF + 24) & 3));                 // m
 }
 
-// One CTA = up to 1024 consecutive cells of ONE row (no divisions to find rows).  Each thread formats 4 cells —
-// 100 bytes, 25 whole words built in registers with compile-time byte positions — into shared memory; the CTA's bytes
-// then leave as 16-byte stores aligned to the DESTINATION: a row starts at an odd offset (6 + r(25W+1)), so every
-// output word is funnel-shifted out of two staged words (the shift is uniform over the CTA).  Only the first and last
-// 16-byte chunk of a CTA can straddle its neighbours' bytes and are written bytewise.
+// One CTA = up to 1024 consecutive cells of ONE row (no divisions to find rows).  Each thread formats 4 cells — 100 bytes,
+// 25 whole words built in registers with compile-time byte positions.  Rows start at odd offsets (6 + r(25W+1)), so the CTA's
+// window of the stream begins `a` bytes into a 16-byte chunk of the destination; the window is STAGED AT THAT SAME PHASE in
+// shared memory (staging byte a + j = window byte j): a thread shifts its 100 bytes by a & 3 bytes while they are still in
+// registers (the low bytes of its first word are the tail of its left neighbour's last cell — always "[0m" — so every word
+// is written whole, by one thread, conflict-free: stride 25 words).  The staged chunks then are the destination's chunks, and
+// all complete ones leave with ONE bulk copy (cp.async.bulk shared -> global, the TMA engine: no per-thread loads, shifts or
+// stores); only the first and last chunk of a CTA can straddle a neighbour's bytes and are written bytewise.
 template <typename Src>
 __global__ void __launch_bounds__(ENC_THREADS) k_encode(const Src *__restrict__ src, int width, int rows,
                                                         unsigned char *__restrict__ out_base, unsigned long long byte_offset)
 {
-    __shared__ __align__(16) unsigned int s_win[ENC_WORDS + 8];
+    __shared__ __align__(128) unsigned int s_win[ENC_WORDS + 8];
     __shared__ unsigned int s_lut[256];
     {
         const int v = threadIdx.x;   // ENC_THREADS == 256
@@ -101,14 +104,16 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode(const Src *__restrict__ 
     // first byte of this CTA in the stream, and how many it owns (the last CTA of a row also owns the '\n')
     const unsigned long long g0 = byte_offset + (unsigned long long)row * row_bytes + (unsigned long long)c0 * TRT_CELL_BYTES;
     const int nbytes = ncells * TRT_CELL_BYTES + ((c0 + ncells == width) ? 1 : 0);
+    const unsigned int a = (unsigned int)(g0 & 15ull);           // window byte 0 sits `a` bytes into its 16-byte chunk
     __syncthreads();
 
-    // ---- format: 4 cells per thread -------------------------------------------------------------------------
+    // ---- format: 4 cells per thread, staged at the destination's phase ---------------------------------------------------
     const int first = threadIdx.x * ENC_CELLS_PER_THREAD;
     if (first < ncells) {
-        unsigned int out[ENC_CELLS_PER_THREAD * TRT_CELL_BYTES / 4 + 1];
+        constexpr int NW = ENC_CELLS_PER_THREAD * TRT_CELL_BYTES / 4;   // 25
+        unsigned int out[NW + 1];
 #pragma unroll
-        for (int k = 0; k < ENC_CELLS_PER_THREAD * TRT_CELL_BYTES / 4 + 1; k++) out[k] = 0u;
+        for (int k = 0; k < NW + 1; k++) out[k] = 0u;
         unsigned int d[ENC_CELLS_PER_THREAD][3];
 #pragma unroll
         for (int k = 0; k < ENC_CELLS_PER_THREAD; k++) {
@@ -122,38 +127,48 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode(const Src *__restrict__ 
         put_cell<1 * TRT_CELL_BYTES>(out, d[1][0], d[1][1], d[1][2]);
         put_cell<2 * TRT_CELL_BYTES>(out, d[2][0], d[2][1], d[2][2]);
         put_cell<3 * TRT_CELL_BYTES>(out, d[3][0], d[3][1], d[3][2]);
+        // shift by a & 3 bytes: staging word (a >> 2) + 25 t + k takes the high bytes of out[k-1] and the low bytes of out[k];
+        // out[-1] is the left neighbour's last word, and a cell always ends in ESC [ 0 m
+        const unsigned int sh = 8u * (a & 3u);                   // uniform over the CTA
+        unsigned int *const dst = s_win + (a >> 2) + threadIdx.x * NW;
+        unsigned int prev = 0x6d305b1bu;
 #pragma unroll
-        for (int k = 0; k < ENC_CELLS_PER_THREAD * TRT_CELL_BYTES / 4; k++) s_win[threadIdx.x * 25 + k] = out[k];
-        // end of the row inside this thread's cells: the byte after the last cell is '\n' (TRT.c:1103, 1125).  It lands
-        // on a padding cell of this thread or on the first byte of the next thread's words, which that thread (idle:
-        // the row is over) does not write.
+        for (int k = 0; k < NW; k++) {
+            dst[k] = __funnelshift_l(prev, out[k], sh);           // (out[k] << sh) | (prev >> (32 - sh)); sh == 0: out[k]
+            prev = out[k];
+        }
+        // the word behind a thread's 25 belongs to its right neighbour — unless there is none (end of the row or of the CTA)
+        if (first + ENC_CELLS_PER_THREAD >= ncells) dst[NW] = __funnelshift_l(prev, 0u, sh);
+        // end of the row inside this thread's cells: the byte after the last cell is '\n' (TRT.c:1103, 1125)
         const int mine = min(ENC_CELLS_PER_THREAD, ncells - first);
-        if (c0 + first + mine == width) reinterpret_cast<unsigned char *>(s_win)[threadIdx.x * 100 + mine * TRT_CELL_BYTES] = 0x0a;
+        if (c0 + first + mine == width) reinterpret_cast<unsigned char *>(s_win)[a + threadIdx.x * 100 + mine * TRT_CELL_BYTES] = 0x0a;
     }
+    // the staged bytes are read by the bulk-copy engine (async proxy): make the generic-proxy writes visible to it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
-    // ---- drain: 16-byte chunks aligned to the destination ---------------------------------------------------------
-    const unsigned int a = (unsigned int)(g0 & 15ull);           // window byte 0 sits `a` bytes into its 16-byte chunk
+    // ---- drain ----------------------------------------------------------------------------------------------------------
     unsigned char *const chunk0 = out_base + (g0 - a);            // 16-byte aligned (out_base is)
     const int nchunks = (int)((a + (unsigned)nbytes + 15u) >> 4);
-    const unsigned char *const s_bytes = reinterpret_cast<const unsigned char *>(s_win);
-    for (int q = threadIdx.x; q < nchunks; q += ENC_THREADS) {
-        const int o = q * 16 - (int)a;                            // window byte offset of this chunk
-        if (o >= 0 && o + 16 <= nbytes) {
-            const int wofs = o >> 2;
-            const unsigned int sh = 8u * (unsigned)(o & 3);
-            const unsigned int w0 = s_win[wofs], w1 = s_win[wofs + 1], w2 = s_win[wofs + 2], w3 = s_win[wofs + 3], w4 = s_win[wofs + 4];
-            uint4 v;
-            v.x = __funnelshift_r(w0, w1, sh);
-            v.y = __funnelshift_r(w1, w2, sh);
-            v.z = __funnelshift_r(w2, w3, sh);
-            v.w = __funnelshift_r(w3, w4, sh);
-            *reinterpret_cast<uint4 *>(chunk0 + (size_t)q * 16) = v;
-        } else {
-            for (int j = 0; j < 16; j++)
-                if (o + j >= 0 && o + j < nbytes) chunk0[(size_t)q * 16 + j] = s_bytes[o + j];
-        }
+    const int q_first = a ? 1 : 0;                                // chunk 0 starts before the window unless a == 0
+    const int q_last = (int)((a + (unsigned)nbytes) >> 4);        // first chunk that is not complete
+    if (threadIdx.x == 0 && q_last > q_first) {
+        const unsigned int bytes = (unsigned int)(q_last - q_first) * 16u;
+        const unsigned int s_addr = (unsigned int)__cvta_generic_to_shared(s_win) + (unsigned int)q_first * 16u;
+        unsigned char *const g_addr = chunk0 + (size_t)q_first * 16;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g_addr), "r"(s_addr), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
+    // the at most two partial chunks, bytewise (lanes of the second warp: the first one's lane 0 is busy with the bulk copy)
+    const unsigned char *const s_bytes = reinterpret_cast<const unsigned char *>(s_win);
+    if (threadIdx.x >= 32 && threadIdx.x < 64) {
+        const int j = (int)threadIdx.x - 32;                      // 0..15: head chunk, 16..31: tail chunk
+        const int q = j < 16 ? 0 : q_last;
+        const int b = q * 16 + (j & 15);                          // staging byte
+        const bool partial = j < 16 ? (q_first == 1) : (q_last < nchunks && q_last >= q_first);
+        if (partial && b >= (int)a && b < (int)a + nbytes) chunk0[b] = s_bytes[b];
+    }
+    if (threadIdx.x == 0 && q_last > q_first) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive the read
 }
 
 __global__ void k_stream_frame(unsigned char *base, unsigned long long tail_at)
@@ -162,6 +177,36 @@ __global__ void k_stream_frame(unsigned char *base, unsigned long long tail_at)
     const int t = threadIdx.x;
     if (t < TRT_HOME_BYTES) base[t] = home[t];
     else if (t < TRT_HOME_BYTES + TRT_TAIL_NULS) base[tail_at + (t - TRT_HOME_BYTES)] = 0; // TRT.c:1104, 1130
+}
+
+// ---- step completion without the host (multi-GPU) ---------------------------------------------------------------------
+// k_signal: "everything this rank enqueued before me on this stream has been performed" -> a step number stored into a flag word
+// that lives in rank 0's memory (peer mapping) or in its own.  The kernels and copy-engine transfers that wrote the band's bytes
+// precede it in stream order; the system-scope fence orders the flag behind them for an observer on another GPU.
+__global__ void k_signal(unsigned int *flag, unsigned int value)
+{
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned int *>(flag) = value;
+    __threadfence_system();
+}
+
+// k_wait_flags: rank 0's stream waits until every rank's flag has reached `value` (lane = rank).  Bounded: gives up after
+// ~4 s of GPU clock and raises *timed_out instead of hanging the device if a rank died.
+__global__ void k_wait_flags(const unsigned int *flags, int n, unsigned int value, unsigned int *timed_out)
+{
+    const int r = threadIdx.x;
+    if (r >= n) return;
+    const volatile unsigned int *f = flags + r;
+    const long long t0 = clock64();
+    // (values only grow; the subtraction keeps the comparison right across a wrap of the 32-bit step counter)
+    while ((int)(*f - value) < 0) {
+        if (clock64() - t0 > 8000000000ll) {
+            *timed_out = 1u;
+            break;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
 }
 
 static void ck(cudaError_t e, int line)
@@ -199,6 +244,16 @@ void launch_encode_f64(const double *pixels, int width, int rows, char *out_base
 void launch_encode_quant(const uchar4 *quant, int width, int rows, char *out_base, size_t byte_offset, cudaStream_t stream)
 {
     launch_encode<uchar4>(quant, width, rows, out_base, byte_offset, stream);
+}
+void launch_signal(unsigned int *flag, unsigned int value, cudaStream_t stream)
+{
+    k_signal<<<1, 1, 0, stream>>>(flag, value);
+    ck(cudaGetLastError(), __LINE__);
+}
+void launch_wait_flags(const unsigned int *flags, int n, unsigned int value, unsigned int *timed_out, cudaStream_t stream)
+{
+    k_wait_flags<<<1, 32, 0, stream>>>(flags, n, value, timed_out);
+    ck(cudaGetLastError(), __LINE__);
 }
 void launch_stream_frame(char *stream_base, int width, int height, cudaStream_t stream)
 {

@@ -15,6 +15,9 @@ size_t render_tile_info_bytes(int width, int rows);   // RenderParams::tile_info
 unsigned long long run_selftest_division(unsigned long long seed, int ctas, int iters, unsigned long long *d_scratch, cudaStream_t stream);
 void launch_probe_trace(const RenderParams &p, const double *d_rays, int n, double *d_out, cudaStream_t stream);
 void launch_probe_sky(const RenderParams &p, const double *d_dirs, int n, int *d_out, cudaStream_t stream);
+void launch_probe_sphere(const double *d_rays, const double *d_geom, int n, double *d_out, cudaStream_t stream);
+void launch_probe_plane(const double *d_rays, int n, double *d_out, cudaStream_t stream);
+void launch_probe_lighting(const RenderParams &p, const double *d_in, int n, double *d_out, cudaStream_t stream);
 
 // trt_encode.cu
 // Encode `rows` rows of `width` cells into out_base[byte_offset ...); source is either the FP64
@@ -22,6 +25,8 @@ void launch_probe_sky(const RenderParams &p, const double *d_dirs, int n, int *d
 void launch_encode_f64(const double *pixels, int width, int rows, char *out_base, size_t byte_offset, cudaStream_t stream);
 void launch_encode_quant(const uchar4 *quant, int width, int rows, char *out_base, size_t byte_offset, cudaStream_t stream);
 void launch_stream_frame(char *stream_base, int width, int height, cudaStream_t stream);
+void launch_signal(unsigned int *flag, unsigned int value, cudaStream_t stream);
+void launch_wait_flags(const unsigned int *flags, int n, unsigned int value, unsigned int *timed_out, cudaStream_t stream);
 
 // trt_peak.cu
 double measure_fp32_tflops(cudaStream_t stream);

@@ -1212,6 +1212,122 @@ __global__ void k_probe_trace(const RenderParams P, const double *__restrict__ r
     r[10] = reflectivity;
 }
 
+// ray_intersects_sphere (TRT.c:638-672) for an array of (ray, sphere) pairs: out = hit flag, intersection point
+__global__ void k_probe_sphere(const double *__restrict__ rays, const double *__restrict__ geom, int n, double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const d3 o = mk3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]);
+    const d3 d = mk3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
+    const double radius = geom[i * 4 + 3];
+    const double4 g = make_double4(geom[i * 4 + 0], geom[i * 4 + 1], geom[i * 4 + 2], radius * radius);   // TRT.c:648: one rounded product
+    const Tally<false> no_tally{nullptr};
+    const double a = dot(d, d);                                                                           // TRT.c:646
+    double closest = INFINITY, t_hit = 0.0;
+    int obj = 0, index = -1, best_oi = -1;
+    sphere_exact<false>(g, 0, 0, o, d, 2.0 * a, 4.0 * a, closest, obj, index, best_oi, t_hit, no_tally);
+    double *r = out + (size_t)i * 4;
+    r[0] = (double)obj;
+    r[1] = obj ? o.x + t_hit * d.x : 0.0;                                                                 // TRT.c:663-665
+    r[2] = obj ? o.y + t_hit * d.y : 0.0;
+    r[3] = obj ? o.z + t_hit * d.z : 0.0;
+}
+
+// ray_intersects_plane (TRT.c:677-695) against the scene's ground: out = hit flag, intersection point
+__global__ void k_probe_plane(const double *__restrict__ rays, int n, double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const d3 o = mk3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]);
+    const d3 d = mk3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
+    const Tally<false> no_tally{nullptr};
+    double closest = INFINITY, t_hit = 0.0;
+    int obj = 0;
+    plane_exact_num<false>(plane_numerator(o), o, d, closest, obj, t_hit, no_tally);
+    double *r = out + (size_t)i * 4;
+    r[0] = obj ? 1.0 : 0.0;
+    r[1] = obj ? o.x + t_hit * d.x : 0.0;                                                                 // TRT.c:690-692
+    r[2] = obj ? o.y + t_hit * d.y : 0.0;
+    r[3] = obj ? o.z + t_hit * d.z : 0.0;
+}
+
+// apply_lighting (TRT.c:894-963) for an array of surface points: in = point, normal, material colour (9 doubles), out = the
+// lit, clamped colour.  Mirrors the shading of k_render's consume step statement by statement on the same building blocks
+// (certificate-guided shadow queries when the scene allows them, push_back, unit, the shared-reciprocal division).
+__global__ void k_probe_lighting(const RenderParams P, const double *__restrict__ in, int n, double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const d3 at = mk3(in[i * 9 + 0], in[i * 9 + 1], in[i * 9 + 2]);
+    const d3 nrm = mk3(in[i * 9 + 3], in[i * 9 + 4], in[i * 9 + 5]);
+    const d3 colour = mk3(in[i * 9 + 6], in[i * 9 + 7], in[i * 9 + 8]);
+    const Tally<false> no_tally{nullptr};
+    const bool cert = c_scene.filter_enabled != 0;
+    const float S_max = cert ? c_scene.filter_centre_l1 : INFINITY;
+    Query qy;
+    const float S0 = trt_cert_set_origin(&qy.rf, at.x, at.y, at.z) + S_max;
+    const double num_g = plane_numerator(at);
+    d3 lit = mk3(0.0, 0.0, 0.0);
+    for (int q = 0; q < c_scene.num_dir + c_scene.num_point; q++) {
+        double light_d2 = 0.0;
+        qy.near_limit = INFINITY;
+        qy.far_limit = INFINITY;
+        qy.ground_candidate = false;
+        qy.plane_denom = 0.0;
+        if (q < c_scene.num_dir) {
+            const DevLightDir &Ld = c_scene.dir[q];
+            qy.mode = Q_DIR;
+            qy.d = mk3(Ld.L[0], Ld.L[1], Ld.L[2]);
+            qy.rf.dx = Ld.Lf[0]; qy.rf.dy = Ld.Lf[1]; qy.rf.dz = Ld.Lf[2];
+            qy.rf.slack_t = (32.0f * TRT_CERT_U) * S0;
+            qy.rf.usable = (S0 < 1e15f) && Ld.lf_unit;
+            qy.plane_denom = Ld.plane_denom;
+        } else {
+            const DevLightPoint &Lp = c_scene.point[q - c_scene.num_dir];
+            qy.mode = Q_POINT;
+            const d3 ld = mk3(Lp.pos[0] - at.x, Lp.pos[1] - at.y, Lp.pos[2] - at.z);
+            light_d2 = dot(ld, ld);
+            qy.d = unit(ld);
+            const float dist = trt_cert_set_dir_toward(&qy.rf, Lp.pos_f[0], Lp.pos_f[1], Lp.pos_f[2], S0 + Lp.pos_l1);
+            const float guard = fmaf(2.0f, qy.rf.slack_t, 1e-5f);
+            qy.near_limit = dist - guard;
+            qy.far_limit = dist + guard;
+            qy.ground_candidate = !trt_cert_ground_cannot_block(num_g, Lp.height, c_scene.ground_margin);
+        }
+        int obj2 = 0, index2 = -1;
+        double t2 = 0.0;
+        bool blocked = false;
+        if (!cert) query_reference<false>(P, at, qy.d, obj2, index2, t2, no_tally);
+        else if (!c_scene.clustered) blocked = query_certified<true>(P, reinterpret_cast<const float4 *>(P.cull_pairs), qy, at, num_g, false, 0u, obj2, index2, t2, nullptr);
+        else blocked = query_certified<false>(P, nullptr, qy, at, num_g, false, 0u, obj2, index2, t2, nullptr);
+        bool open = !blocked && obj2 == 0;
+        double f = 1.0;
+        const double *lc;
+        if (qy.mode == Q_DIR) {
+            lc = c_scene.dir[q].color;
+        } else {
+            const DevLightPoint &Lp = c_scene.point[q - c_scene.num_dir];
+            if (!blocked && obj2 != 0) {
+                const d3 bh = mk3(at.x + t2 * qy.d.x, at.y + t2 * qy.d.y, at.z + t2 * qy.d.z);
+                const d3 to_blocker = push_back(at, bh) - at;
+                open = light_d2 < dot(to_blocker, to_blocker);                                      // TRT.c:936-941
+            }
+            lc = Lp.color;
+            f = open ? clampd(ieee_div(Lp.intensity, light_d2), 0.0, 1.0) : 0.0;                    // TRT.c:931
+        }
+        if (open) {
+            const double lambert = fmin(dot(nrm, qy.d), 1.0);                                       // TRT.c:910, 943
+            f = qy.mode == Q_DIR ? lambert : f * lambert;
+            d3 diffuse = mk3(lc[0] * f, lc[1] * f, lc[2] * f);
+            diffuse = hadamard(diffuse, colour);
+            lit = lit + diffuse;
+        }
+    }
+    out[i * 3 + 0] = clampd(lit.x, 0.0, 1.0);                                                       // TRT.c:960
+    out[i * 3 + 1] = clampd(lit.y, 0.0, 1.0);
+    out[i * 3 + 2] = clampd(lit.z, 0.0, 1.0);
+}
+
 // get_skybox_color (TRT.c:700-789) for an array of directions: face, texel index, r, g, b per entry
 __global__ void k_probe_sky(const RenderParams P, const double *__restrict__ dirs, int n, int *__restrict__ out)
 {
@@ -1393,6 +1509,27 @@ void launch_probe_trace(const RenderParams &p, const double *d_rays, int n, doub
 {
     if (n <= 0) return;
     k_probe_trace<<<(n + 127) / 128, 128, 0, stream>>>(p, d_rays, n, d_out);
+    CK(cudaGetLastError());
+}
+
+void launch_probe_sphere(const double *d_rays, const double *d_geom, int n, double *d_out, cudaStream_t stream)
+{
+    if (n <= 0) return;
+    k_probe_sphere<<<(n + 127) / 128, 128, 0, stream>>>(d_rays, d_geom, n, d_out);
+    CK(cudaGetLastError());
+}
+
+void launch_probe_plane(const double *d_rays, int n, double *d_out, cudaStream_t stream)
+{
+    if (n <= 0) return;
+    k_probe_plane<<<(n + 127) / 128, 128, 0, stream>>>(d_rays, n, d_out);
+    CK(cudaGetLastError());
+}
+
+void launch_probe_lighting(const RenderParams &p, const double *d_in, int n, double *d_out, cudaStream_t stream)
+{
+    if (n <= 0) return;
+    k_probe_lighting<<<(n + 127) / 128, 128, 0, stream>>>(p, d_in, n, d_out);
     CK(cudaGetLastError());
 }
 

@@ -41,7 +41,11 @@ SIGNATURES = {
     "trt_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "trt_host_unregister": (C.c_int, [C.c_void_p]),
     "trt_peer_copies_wait": (C.c_int, []),
+    "trt_signal_step": (C.c_int, [C.c_void_p, C.c_uint, C.c_int]),
+    "trt_wait_steps": (C.c_int, [C.c_void_p, C.c_int, C.c_uint, C.c_int]),
+    "trt_stream_wait_copies": (C.c_int, []),
     "trt_set_scene": (C.c_int, [C.POINTER(abi.Scene)]),
+    "trt_set_scene_async": (C.c_int, [C.POINTER(abi.Scene)]),
     "trt_render_rows_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "trt_encode_rows_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "trt_render_rows_quant_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -53,6 +57,9 @@ SIGNATURES = {
     "trt_model_flops": (C.c_double, [C.POINTER(C.c_longlong)]),
     "trt_probe_trace_ray": (C.c_int, [C.POINTER(abi.Scene), C.c_void_p, C.c_int, C.c_void_p]),
     "trt_probe_skybox": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "trt_probe_sphere": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "trt_probe_plane": (C.c_int, [C.POINTER(abi.Scene), C.c_void_p, C.c_int, C.c_void_p]),
+    "trt_probe_lighting": (C.c_int, [C.POINTER(abi.Scene), C.c_void_p, C.c_int, C.c_void_p]),
     "trt_selftest_division": (C.c_longlong, [C.c_ulonglong, C.c_longlong]),
     "trt_device_alloc": (C.c_void_p, [C.c_size_t]),
     "trt_device_free": (None, [C.c_void_p]),

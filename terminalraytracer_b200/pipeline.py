@@ -41,31 +41,46 @@ class SharedHostStream:
         import os
         import numpy as np
         self.r, self.nbytes = renderer, int(nbytes)
+        self.rank, self.world_size = rank, world_size
+        self.flags_at = (self.nbytes + 4095) & ~4095          # one int64 per rank behind the stream: the step it has delivered
+        self.map_bytes = self.flags_at + 4096
         box = [None]
         if rank == 0:
             box[0] = "/dev/shm/trt_b200_stream_%d_%x" % (os.getpid(), id(self) & 0xffffff)
             fd = os.open(box[0], os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
-            os.ftruncate(fd, self.nbytes)
+            os.ftruncate(fd, self.map_bytes)
         if world_size > 1:
             import torch.distributed as dist
             dist.broadcast_object_list(box, src=0, group=group)
             if rank != 0:
                 fd = os.open(box[0], os.O_RDWR)
-        self.map = mmap.mmap(fd, self.nbytes)
+        self.map = mmap.mmap(fd, self.map_bytes)
         os.close(fd)
         if world_size > 1:
             dist.barrier(group=group)
         if rank == 0:
             os.unlink(box[0])                 # the mappings keep the memory alive; nothing is left behind on a crash
-        self.array = np.frombuffer(self.map, dtype=np.uint8)
+        self.array = np.frombuffer(self.map, dtype=np.uint8, count=self.nbytes)
+        self.flags = np.frombuffer(self.map, dtype=np.int64, count=max(world_size, 1), offset=self.flags_at)
         self.ptr = C.addressof(C.c_char.from_buffer(self.map))
         self.r.L.trt_host_register(self.ptr, self.nbytes)
+
+    def arrive_and_wait(self, step, timeout_s=60.0):
+        """this rank's bytes of frame `step` are in the buffer (its copies have completed); returns when everybody's are —
+        a barrier through the shared mapping itself: no collective, no device work"""
+        import time
+        self.flags[self.rank] = step
+        deadline = time.monotonic() + timeout_s
+        while int(self.flags.min()) < step:
+            if time.monotonic() > deadline:
+                raise RuntimeError("SharedHostStream: a rank did not deliver frame %d" % step)
+            time.sleep(0)
 
     def close(self):
         if self.ptr:
             self.r.L.trt_host_unregister(self.ptr)
             self.ptr = None
-            self.array = None     # the mmap itself is released with the object (ctypes keeps an export on it)
+            self.array = self.flags = None     # the mmap itself is released with the object (ctypes keeps an export on it)
 
 
 class FramePipeline:
@@ -91,8 +106,12 @@ class FramePipeline:
     split."""
 
     def __init__(self, renderer, width, height, rank=0, world_size=1, row_weights=None, group=None, peer=False, pieces=(0.7, 0.3),
-                 adapt=False, host_stream=None, fused=False):
+                 adapt=False, host_stream=None, fused=False, host_sync=None):
         self.r = renderer
+        self.host_sync = host_sync           # SharedHostStream whose arrival flags end a host_stream step (else: a collective)
+        self.step_no = 0
+        self.level_steps = 0                 # adapt: consecutive steps whose K1 times were level; feedback pauses while it lasts
+        self.k1_times = None
         self.width, self.height = width, height
         self.rank, self.world_size, self.group = rank, world_size, group
         self.device = torch.device("cuda", renderer.device)
@@ -114,13 +133,20 @@ class FramePipeline:
         self.quant = torch.empty(max(rows * width, 1) * 4, dtype=torch.uint8, device=self.device)
         self.stream_ptr = self.peer_base = None
         self.k1_span, self.k1_launches = None, 0
+        self.flags_offset = (abi.stream_bytes(width, height) + 16 + 255) & ~255
         self.rebalance_above = 1.005          # adapt: move the cuts when the slowest rank is this far above the mean
         total = abi.stream_bytes(width, height)
         if rank == 0 and not self.host_stream:
             if self.peer:
                 # cudaMalloc'ed by the library (an IPC handle needs the base of an allocation), viewed as a torch tensor
-                self.stream_ptr = self.r.L.trt_device_alloc(total + 16)
+                # + 64 flag words behind the stream: every rank's completed step number (trt_signal_step / trt_wait_steps)
+                # + 128 flag words behind the stream (trt_signal_step / trt_wait_steps): word r = rank r's completed step,
+                # word 32 = a wait timed out, word 40 = the last frame rank 0 has consumed
+                self.flags_offset = (total + 16 + 255) & ~255
+                self.stream_ptr = self.r.L.trt_device_alloc(self.flags_offset + 512)
                 self.stream = torch.as_tensor(_DevicePointer(self.stream_ptr, total), device=self.device)
+                torch.as_tensor(_DevicePointer(self.stream_ptr + self.flags_offset, 512), device=self.device).zero_()
+                torch.cuda.synchronize(self.device)
             else:
                 self.stream = torch.empty(total, dtype=torch.uint8, device=self.device)
             self.band_bytes = None
@@ -164,14 +190,20 @@ class FramePipeline:
         is sent on its way while the next one renders.  k1_events: optional list receiving one (start, end) pair of torch
         events per call: start of the first K1 launch, end of the last."""
         rb = abi.row_bytes(self.width)
-        self.r.set_scene(scene)
+        self.r.set_scene_async(scene)        # ordered on the stream like the kernels behind it: no host wait per frame
         if self.stream is not None:
             self.r.stream_frame(self.stream.data_ptr(), self.width, self.height)
         # (Pieces on two alternating streams — the next piece's K1 filling the SMs that the tail of the previous one leaves
         # idle — were measured: the tails are short, ~0.04 ms, and the persistent K1 of the next piece then keeps the
         # previous piece's K2 and with it its transfer off the SMs until it ends.  One stream it is.)
-        timed = self.adapt or k1_events is not None
+        timed = (self.adapt and self._feedback_due_next()) or k1_events is not None
         first = last = None
+        remote = self.peer and self.stream is None           # this rank writes into rank 0's memory
+        if remote and self.step_no > 0:
+            # back-pressure: rank 0 must have taken frame step_no before its bytes are overwritten; fused: the kernel itself
+            # stores there, so it waits; pieces: only the pushes wait (on the copy stream), K1 and K2 run ahead
+            self.r.L.trt_wait_steps(self.peer_base + self.flags_offset + 4 * 40, 1, self.step_no, 0 if self.fused else 1)
+        ordered = False
         for i, (r0, r1) in enumerate(self.pieces):
             q = self.quant.data_ptr() + (r0 - self.base_row) * self.width * 4
             if timed and first is None:
@@ -191,6 +223,9 @@ class FramePipeline:
                 self.r.encode_rows_quant(q, self.width, r1 - r0, self.stream.data_ptr(), abi.HOME_BYTES + r0 * rb)
             else:
                 off = (r0 - self.base_row) * rb
+                if self.peer and not ordered:
+                    self.r.L.trt_stream_wait_copies()       # the previous step's pushes still read band_bytes
+                    ordered = True
                 self.r.encode_rows_quant(q, self.width, r1 - r0, self.band_bytes.data_ptr(), off)
                 dst = self.host_stream if self.host_stream else self.peer_base
                 if dst:
@@ -201,22 +236,45 @@ class FramePipeline:
             k1_events.append(self.k1_span)
         self.k1_launches += len(self.pieces)
 
+    def _feedback_due_next(self):
+        return self.level_steps < 3 or (self.step_no + 1) % 64 == 0
+
+    def _feedback_due(self):
+        """adapt: measure and exchange the K1 times on this step?  Every step until the ranks have been level (slowest within
+        rebalance_above of the mean) three steps running, then every 64th step — a slowly changing picture keeps its balance,
+        and a step without feedback needs no host synchronisation at all."""
+        return self.level_steps < 3 or self.step_no % 64 == 0
+
     def gather(self):
+        self.step_no += 1
         if self.async_pieces:
             import torch.distributed as dist
-            if self.fused:
-                torch.cuda.current_stream(self.device).synchronize()   # K1 has ended: its stores have been performed
-            elif self.stream is None:
-                self.r.L.trt_peer_copies_wait()      # this rank's bytes have landed (rank 0's memory / the host buffer)
-            if not self.adapt:
-                if self.world_size > 1:
-                    dist.barrier(group=self.group)   # ... and so have everybody else's
-                elif self.stream is not None:
+            feedback = self.adapt and self._feedback_due()
+            if self.peer:
+                # completion on the device: this rank's step number lands in rank 0's flag array behind its bytes, rank 0's
+                # stream waits for all of them; no host takes part
+                base = self.stream_ptr if self.stream_ptr else self.peer_base
+                self.r.L.trt_signal_step(base + self.flags_offset + 4 * self.rank, self.step_no, 0 if (self.fused or self.stream is not None) else 1)
+                if self.rank == 0:
+                    self.r.L.trt_wait_steps(self.stream_ptr + self.flags_offset, self.world_size, self.step_no, 0)
+                    # (a consumer of the finished frame — a device-to-host copy, a display — is enqueued here, on this stream)
+                    self.r.L.trt_signal_step(self.stream_ptr + self.flags_offset + 4 * 40, self.step_no, 0)
+            else:
+                # host stream: the bytes must be in host memory when the step ends — wait for this rank's copies (or, fused, for
+                # the kernel that stored them), then meet the others through the flags of the shared mapping
+                if self.fused:
                     torch.cuda.current_stream(self.device).synchronize()
+                else:
+                    self.r.L.trt_peer_copies_wait()
+                if self.host_sync is not None:
+                    self.host_sync.arrive_and_wait(self.step_no)
+                elif self.world_size > 1 and not feedback:
+                    dist.barrier(group=self.group)
+            if not feedback:
                 return self.stream
-            # the collective that ends the step doubles as the feedback channel: every rank's K1 time of this frame
-            if self.stream is not None:
-                torch.cuda.current_stream(self.device).synchronize()
+            # feedback step: every rank's K1 time of this frame through one small collective
+            if self.k1_span:
+                self.k1_span[1].synchronize()
             where = self.device if dist.get_backend(self.group) == "nccl" else "cpu"
             mine = torch.tensor([self.k1_span[0].elapsed_time(self.k1_span[1]) if self.k1_span else 0.0], dtype=torch.float32, device=where)
             times = torch.empty(self.world_size, dtype=torch.float32, device=where)
@@ -225,8 +283,11 @@ class FramePipeline:
             # every rank sees the same numbers and takes the same decision; bands that are already level are left alone
             busy = [t for t in self.k1_times if t > 0]
             if busy and max(busy) * len(busy) > self.rebalance_above * sum(busy):
+                self.level_steps = 0
                 self.weights = sharding.reweight(self.weights, self.bands, self.k1_times)
                 self._set_bands(sharding.row_bands(self.height, self.world_size, self.weights))
+            else:
+                self.level_steps += 1
             return self.stream
         band = None
         if self.rank != 0:
@@ -234,11 +295,29 @@ class FramePipeline:
             band = self.band_bytes[:n]
         return tdist.gather_bands(self.stream, band, self.width, self.bands, self.rank, self.world_size, self.group)
 
+    def finish(self):
+        """after the last step: the stream is complete on rank 0 (device-side completion leaves the hosts un-synchronised)"""
+        torch.cuda.synchronize(self.device)
+        if self.peer:
+            self.r.L.trt_peer_copies_wait()
+            if self.world_size > 1:
+                import torch.distributed as dist
+                dist.barrier(group=self.group)
+            torch.cuda.synchronize(self.device)
+            if self.rank == 0:
+                flags = torch.as_tensor(_DevicePointer(self.stream_ptr + self.flags_offset, 512), device=self.device).view(torch.int32).cpu()
+                if int(flags[32]) != 0 or int(flags[72]) != 0:
+                    raise RuntimeError("FramePipeline: a rank never signalled its step (trt_wait_steps timed out)")
+        return self.stream
+
     def render(self, scene, k1_events=None):
         """Full step: returns the complete byte stream (device tensor) on rank 0, None elsewhere (and None everywhere with
         host_stream: the bytes are in the host buffer)."""
         self.render_local(scene, k1_events)
-        return self.gather()
+        out = self.gather()
+        if self.peer:
+            self.finish()        # callers of render() read the stream right away
+        return out
 
 
 class OrderedFrameRing:
@@ -306,7 +385,13 @@ class OrderedFrameRing:
         self.header[1] = 1
 
     # ---- the one consumer ------------------------------------------------------------------------------------------
-    def consume(self, write, poll_s=20e-6, timeout_s=600.0):
+    def reset(self, n_frames=None):
+        """before a new animation (one process, between barriers): nothing ready, nothing consumed"""
+        self.ready[:self.n_frames if n_frames is None else n_frames] = 0
+        self.header[0] = 0
+        self.header[1] = 0
+
+    def consume(self, write, n_frames=None, poll_s=20e-6, timeout_s=600.0):
         """frames 0..n_frames-1 in order: write(frame_index, memoryview of its bytes) as soon as frame k is ready; returns the
         number of frames written (fewer than n_frames after stop() or when write returns a true value)"""
         import time
@@ -314,8 +399,9 @@ class OrderedFrameRing:
         off0 = self.HEADER + self.flags_bytes
         deadline = time.monotonic() + timeout_s
         k = 0
+        total = self.n_frames if n_frames is None else n_frames
         try:
-            while k < self.n_frames:
+            while k < total:
                 while not self.ready[k]:
                     if self.header[1] or time.monotonic() > deadline:
                         return k
@@ -345,12 +431,24 @@ class OrbitPipeline:
     rank's own PCIe link, and rank 0 writes the frames out strictly in order while later ones render.  Nothing is gathered
     at the end and no rank ever holds more than `slots_per_rank` finished frames."""
 
-    def __init__(self, renderer, width, height, rank=0, world_size=1, group=None, slots_per_rank=3):
+    def __init__(self, renderer, width, height, rank=0, world_size=1, group=None, slots_per_rank=3, max_frames=4096):
         self.r = renderer
         self.width, self.height = width, height
         self.rank, self.world_size, self.group = rank, world_size, group
         self.slots_per_rank = slots_per_rank
         self.frame_bytes = abi.stream_bytes(width, height)
+        # mapped and page-locked once (registering a gigabyte takes longer than rendering it); every stream() reuses it
+        self.ring = OrderedFrameRing(self.frame_bytes, max_frames, slots_per_rank * world_size, rank, world_size, group, renderer)
+
+    def close(self):
+        if self.ring is not None:
+            self.ring.close()
+            self.ring = None
+
+    def _barrier(self):
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
 
     def stream(self, scene, times, write=None):
         """Render this rank's frames of the camera path `times` (scene: un-posed camera, as SceneData builds it); rank 0 also
@@ -360,12 +458,18 @@ class OrbitPipeline:
         import threading
         from . import lib as _lib
         n = len(times)
-        ring = OrderedFrameRing(self.frame_bytes, n, self.slots_per_rank * self.world_size, self.rank, self.world_size, self.group, self.r)
+        ring = self.ring
+        if n > ring.n_frames:
+            raise ValueError("OrbitPipeline: %d frames, ring sized for %d (max_frames)" % (n, ring.n_frames))
+        self._barrier()                          # nobody is still inside the previous stream()
+        if self.rank == 0:
+            ring.reset(n)
+        self._barrier()
         written = [0]
         consumer = None
         if self.rank == 0:
             sink = write if write is not None else (lambda k, view: False)
-            consumer = threading.Thread(target=lambda: written.__setitem__(0, ring.consume(sink)), daemon=True)
+            consumer = threading.Thread(target=lambda: written.__setitem__(0, ring.consume(sink, n)), daemon=True)
             consumer.start()
         arr = (C.c_double * n)(*[float(t) for t in times])
 
@@ -382,10 +486,6 @@ class OrbitPipeline:
                                             C.cast(acq, C.c_void_p), C.cast(snk, C.c_void_p), None)
         if consumer is not None:
             consumer.join()
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.barrier(group=self.group)      # nobody unmaps the ring while the consumer may still read it
-        ring.close()
         return done, written[0]
 
     def collect(self, scene, times):

@@ -85,6 +85,10 @@ class Renderer:
     def set_scene(self, scene):
         self.L.trt_set_scene(C.byref(scene.c))
 
+    def set_scene_async(self, scene):
+        """trt_set_scene without the host wait (the upload is ordered on the stream like the kernels that follow it)"""
+        self.L.trt_set_scene_async(C.byref(scene.c))
+
     def render_rows(self, width, height, row0, row1, d_pixels_ptr):
         self.L.trt_render_rows_device(width, height, row0, row1, d_pixels_ptr)
 

@@ -381,6 +381,9 @@ def test_gpu_pipeline_single_rank(renderer, orc):
         sc2 = S.SceneData(64, 36, sc.skybox)
         times = sharding.orbit_times(4)
         frames = orbit.collect(sc2, times)          # trt_render_orbit_to into the ordered shared ring, one rank
+        frames2 = orbit.collect(sc2, times[:2])     # the ring is reused
+        orbit.close()
+        assert len(frames2) == 2 and np.array_equal(frames2[1], frames[1])
         torch.cuda.synchronize()
         for k, t in enumerate(times):
             sc2.set_time(t)
@@ -436,6 +439,8 @@ def _orbit_worker(rank, world, port, w, h, nframes, out_path):
         assert done == len(sharding.frames_for_rank(nframes, rank, world))
         if rank == 0:
             assert written == nframes and order == list(range(nframes))
+        dist.barrier()
+        orbit.close()
     finally:
         rd.close()
         dist.destroy_process_group()
@@ -613,3 +618,94 @@ def test_gpu_full_size_config_properties(renderer, orc, cfg):
         assert np.array_equal(values[r], (want[0] * 255).astype(np.int32)), r
     # idempotence: a second render gives the same bytes
     assert np.array_equal(np.array(renderer.render_ansi(sc)), stream)
+
+
+# ---- unit-level probes against the reference's known answers (tests/golden/units.npz) -----------------------------
+
+def test_gpu_sphere_and_plane_known_answers(renderer):
+    """ray_intersects_sphere (TRT.c:638-672) and ray_intersects_plane (TRT.c:677-695) on the device against the reference's own
+    outputs: hit flag and intersection point, bit for bit (un-normalised directions, origins inside the sphere, rays around the
+    |denominator| > 1e-5 guard)"""
+    units = np.load(os.path.join(U.GOLDEN, "units.npz"))
+    rays, geom, want = np.ascontiguousarray(units["sphere_rays"]), np.ascontiguousarray(units["sphere_geom"]), units["sphere_out"]
+    out = np.zeros((len(rays), 4))
+    renderer.L.trt_probe_sphere(rays.ctypes.data, geom.ctypes.data, len(rays), out.ctypes.data)
+    assert np.array_equal(out, want)
+    assert 0.05 < want[:, 0].mean() < 0.95
+    rays, want = np.ascontiguousarray(units["plane_rays"]), units["plane_out"]
+    sc = S.SceneData(64, 36, S.synthetic_cubemap("uv_gradient", 64))          # the demo ground: point (0,-2,0), normal (0,1,0)
+    renderer.upload_skybox(sc.skybox)
+    out = np.zeros((len(rays), 4))
+    renderer.L.trt_probe_plane(C.byref(sc.c), rays.ctypes.data, len(rays), out.ctypes.data)
+    assert np.array_equal(out, want)
+
+
+def test_gpu_apply_lighting_known_answers(renderer):
+    """apply_lighting (TRT.c:894-963) on the device for the surface points the reference's trace_ray found (units.npz:
+    trace_out -> lighting_out): shadow query per light, un-floored Lambert, point-light falloff and "blocker beyond the light"
+    rule, clamp — bit for bit; also with the certificates switched off (all-FP64 queries)"""
+    units = np.load(os.path.join(U.GOLDEN, "units.npz"))
+    tr, lit = units["trace_out"], units["lighting_out"]
+    hit = tr[:, 0] != 0
+    surface = np.ascontiguousarray(tr[hit][:, 1:10])          # point, normal, material colour
+    sc = S.SceneData(64, 36, S.synthetic_cubemap("uv_gradient", 64)).set_time(3.7)
+    renderer.upload_skybox(sc.skybox)
+    for cull in (1, 0):
+        renderer.L.trt_set_cull(cull)
+        try:
+            out = np.zeros((len(surface), 3))
+            renderer.L.trt_probe_lighting(C.byref(sc.c), surface.ctypes.data, len(surface), out.ctypes.data)
+        finally:
+            renderer.L.trt_set_cull(1)
+        assert np.array_equal(out, lit[hit]), cull
+    assert (lit[hit] > 0).any() and (lit[hit] == 0).all(axis=1).any()          # lit and fully shadowed points both occur
+
+
+def test_gpu_skybox_uploaded_after_the_scene(renderer, orc):
+    """trt_set_scene -> trt_upload_skybox(another dim) -> band render: the scene constants carry the skybox geometry and must
+    follow the upload (the header allows this order)"""
+    import torch
+    w, h = 80, 45
+    small, big = S.synthetic_cubemap("uv_gradient", 64), S.synthetic_cubemap("milky_way", 128)
+    sc = S.SceneData(w, h, small).set_time(3.7)
+    renderer.upload_skybox(small)
+    renderer.use_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        renderer.set_scene(sc)
+        renderer.upload_skybox(big)                                # after the scene
+        px = torch.zeros((h, w, 3), dtype=torch.float64, device="cuda")
+        renderer.render_rows(w, h, 0, h, px.data_ptr())
+        torch.cuda.synchronize()
+    finally:
+        renderer.use_stream(None)
+    want = U.cpu_render(orc, "orc_project_scene", S.SceneData(w, h, big).set_time(3.7))
+    assert np.array_equal(px.cpu().numpy(), want)
+
+
+# ---- the C side of the boundary ---------------------------------------------------------------------------------------
+
+def _cc(args, **kw):
+    import subprocess
+    return subprocess.run(args, capture_output=True, **kw)
+
+
+def test_gpu_c_host_program_streams_the_oracle_bytes(orc, tmp_path):
+    """host/trt_demo.c — the reference's frame loop with the two hot calls redirected (TRT.c:1241-1244, 1339-1342) — compiled
+    with gcc against include/ and libtrt_b200.so and run: `--orbit 3 uv_checker 96 54` must write the oracle's three streams"""
+    if not os.path.isdir(os.path.join(U.ROOT, "skybox", "uv_checker")):
+        pytest.skip("skybox/uv_checker not shipped")
+    exe = str(tmp_path / "trt_demo")
+    libdir = os.path.join(U.ROOT, "terminalraytracer_b200")
+    r = _cc(["gcc", "-O2", "-I" + os.path.join(U.ROOT, "include"), os.path.join(U.ROOT, "host", "trt_demo.c"), "-L" + libdir, "-ltrt_b200",
+             "-Wl,-rpath," + libdir, "-lm", "-o", exe])
+    assert r.returncode == 0, r.stderr.decode()
+    w, h, n = 96, 54, 3
+    run = _cc([exe, "--orbit", str(n), "uv_checker", str(w), str(h)], cwd=U.ROOT)
+    assert run.returncode == 0, run.stderr.decode()[-2000:]
+    got = np.frombuffer(run.stdout, dtype=np.uint8)
+    assert got.size == n * abi.stream_bytes(w, h)
+    sky = S.load_skybox_dir(os.path.join(U.ROOT, "skybox", "uv_checker"))
+    for k in range(n):
+        sc = S.SceneData(w, h, sky).set_time(k * (20.0 / n))
+        want = U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc))
+        assert np.array_equal(got[k * want.size:(k + 1) * want.size], want), k

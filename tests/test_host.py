@@ -271,3 +271,30 @@ def test_committed_bench_line_has_the_contract_keys():
     assert line["clocks"]["reasons"] == [] or "sw_power_cap" in line["clocks"]["reasons"]
     # value = primary rays per second over the timed steps
     assert abs(line["value"] - 10.0 * 7680 * 4320 / (line["ms_per_step"] * 1e-3) / 1e6) < 1e-6 * line["value"]
+
+
+def test_bench_stress_scene_restatement_matches_the_library(trt):
+    """bench.py's reference arm builds the 1024-sphere scene without loading libtrt_b200.so; the restatement must be the same bytes"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(U.ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    sc = S.SceneData(64, 36, S.synthetic_cubemap("colors", 16), kind="stress", num_spheres=1024)
+    assert bytes(bench._stress_spheres(1024)) == bytes(sc.spheres)
+
+
+def test_reference_arm_never_maps_the_product_library():
+    """bench.py --impl reference: the scene comes from the reference's own init_camera / literals / camera recipe and the timed
+    call is its project_scene; libtrt_b200.so must not be mapped into that process (reference-arm hygiene)"""
+    if not U.have_reference_build():
+        pytest.skip("oracle/_ref not built")
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import bench\n"
+            "cfg = dict(bench.CONFIGS['demo8k']); cfg['cpu_rows'] = [2000]\n"
+            "cpu = bench.ReferenceCPU(cfg); s = cpu.one_pass(); assert cpu.kind == 'reference' and s > 0 and cpu.px.any()\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libtrt_ref_rows.so' in maps and 'libtrt_b200' not in maps, maps\n"
+            "print('clean')") % U.ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "clean" in r.stdout, r.stderr[-2000:]
