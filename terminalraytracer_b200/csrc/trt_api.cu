@@ -74,7 +74,7 @@ struct Context {
     bool have_scene = false;
     bool cull_allowed = true;   // trt_set_cull(); the FP32 miss test can be switched off for A/B runs
     bool cull = true;           // cull_allowed && this scene's magnitudes are inside the bound's range
-    Buffer sphere_geom, sphere_cull, sphere_mat, sphere_prim, cull_pairs, sphere_orig, sphere_pos, clusters, subballs;
+    Buffer sphere_geom, sphere_cull, sphere_mat, cull_pairs, sphere_orig, sphere_pos, clusters, subballs;
     // skybox
     Buffer sky;
     int sky_dim = -1, sky_face_stride = 0;
@@ -171,7 +171,7 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
     }
     DevScene &s = g.scene;
     {
-        const size_t per_sphere = sizeof(double4) * 2 + sizeof(DevMaterial) + sizeof(float4) * 2 + sizeof(CullPair) + sizeof(int) * 2;
+        const size_t per_sphere = sizeof(double4) + sizeof(DevMaterial) + sizeof(float4) * 2 + sizeof(CullPair) + sizeof(int) * 2;
         const size_t need = sizeof(DevScene) + 4096 + per_sphere * ((size_t)scene->num_spheres + 64);
         g.arena_which = wait ? 0 : (g.arena_which ^ 1);
         // an arena may be rewritten only after the copies of the upload that last used it have run
@@ -296,7 +296,6 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
 
     const int n = s.num_spheres;
     std::vector<double4> geom((size_t)(n > 0 ? n : 1));
-    std::vector<double4> prim((size_t)(n > 0 ? n : 1));
     std::vector<DevMaterial> mats((size_t)(n > 0 ? n : 1));
     std::vector<float4> cull((size_t)n + 2, make_float4(0.f, 0.f, 0.f, 0.f));   // padded to an even count (+1 spare)
     bool in_range = true;       // magnitudes for which the FP32 cull's error bound was derived
@@ -305,17 +304,6 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
         const trt_Sphere &sp = scene->spheres[i];
         volatile double r2 = sp.radius * sp.radius;   // TRT.c:648, a single rounded product
         geom[i] = make_double4(sp.center.x, sp.center.y, sp.center.z, r2);
-        {
-            // oc = origin - centre and c = oc.oc - r*r of TRT.c:640-648 for rays leaving the eye
-            double oc[3];
-            const double ctr[3] = {sp.center.x, sp.center.y, sp.center.z};
-            for (int k = 0; k < 3; k++) {
-                volatile double d = s.eye[k] - ctr[k];
-                oc[k] = d;
-            }
-            volatile double c = dot3_ref(oc, oc) - r2;
-            prim[i] = make_double4(oc[0], oc[1], oc[2], c);
-        }
         set_material(mats[i], sp.material);
         // FP32 cull record: centre rounded to nearest, radius padded and rounded UP (trt_render.cu, sphere_cull)
         const double l1 = fabs(sp.center.x) + fabs(sp.center.y) + fabs(sp.center.z);
@@ -337,14 +325,13 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
     s.clustered = n > TRT_CLUSTER_MIN_SPHERES ? 1 : 0;
     if (s.clustered) {
         trt_cert_kd_order(reinterpret_cast<const float *>(cull.data()), n, orig.data());
-        std::vector<double4> geom2(geom), prim2(prim);
+        std::vector<double4> geom2(geom);
         std::vector<DevMaterial> mats2(mats);
         std::vector<float4> cull2(cull);
         for (int j = 0; j < n; j++) {
             const int i = orig[j];
             pos[i] = j;
             geom[j] = geom2[i];
-            prim[j] = prim2[i];
             mats[j] = mats2[i];
             cull[j] = cull2[i];
         }
@@ -382,8 +369,6 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
     g.sphere_geom.reserve(sizeof(double4) * geom.size());
     g.sphere_mat.reserve(sizeof(DevMaterial) * mats.size());
     g.sphere_cull.reserve(sizeof(float4) * cull.size());
-    g.sphere_prim.reserve(sizeof(double4) * prim.size());
-    CK(cudaMemcpyAsync(g.sphere_prim.p, staged(prim.data(), sizeof(double4) * prim.size()), sizeof(double4) * prim.size(), cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(g.sphere_cull.p, staged(cull.data(), sizeof(float4) * cull.size()), sizeof(float4) * cull.size(), cudaMemcpyHostToDevice, g.stream));
     // Every source goes through staged(): a memcpy into the page-locked arena g.arena[g.arena_which], so the vectors may die
     // when this function returns and the copies are truly asynchronous.  Invariant: an arena may be rewritten only after the
@@ -446,7 +431,6 @@ RenderParams make_params(int width, int height, int row0, int row1, double *d_pi
     p.ansi = nullptr;
     p.sphere_geom = (const double4 *)g.sphere_geom.p;
     p.sphere_cull = (const float4 *)g.sphere_cull.p;
-    p.sphere_prim = (const double4 *)g.sphere_prim.p;
     p.cull_pairs = (const CullPair *)g.cull_pairs.p;
     p.sphere_orig = (const int *)g.sphere_orig.p;
     p.sphere_pos = (const int *)g.sphere_pos.p;
@@ -536,7 +520,6 @@ void trt_shutdown(void)
     g.sphere_geom.release();
     g.sphere_cull.release();
     g.sphere_mat.release();
-    g.sphere_prim.release();
     g.cull_pairs.release();
     g.sphere_orig.release();
     g.sphere_pos.release();
@@ -809,7 +792,6 @@ int trt_probe_skybox(const double *dirs, int n, int *out)
         upload_scene_constants(g.scene, g.stream);
         g.sphere_geom.reserve(sizeof(double4));
         g.sphere_cull.reserve(sizeof(float4));
-        g.sphere_prim.reserve(sizeof(double4));
         g.cull_pairs.reserve(sizeof(CullPair));
         g.sphere_orig.reserve(sizeof(int));
         g.sphere_pos.reserve(sizeof(int));
@@ -898,7 +880,7 @@ size_t trt_render_ansi(const trt_Scene *scene, int width, int height, char *out,
     require_init("trt_render_ansi");
     const size_t total = TRT_STREAM_BYTES(width, height);
     if (cap < total || width <= 0 || height <= 0) return 0;
-    upload_scene(scene);
+    upload_scene(scene, false);            // ordered on the stream in front of the kernels: no host wait
     g.quant.reserve(sizeof(uchar4) * (size_t)width * (size_t)height);
     g.bytes.reserve(total + 16);
     // Big frames are rendered as up to MAX_CHUNKS row chunks so that the device-to-host copy of a chunk's

@@ -44,6 +44,9 @@ __constant__ DevScene c_scene;
 // of sm_100: one issue slot, two spheres; .x = sphere 2p, .y = sphere 2p+1, a pad sphere has r = 0 — live in global memory,
 // RenderParams::cull_pairs; small scenes copy theirs into shared memory at kernel start.)
 
+#ifndef TRT_FUSED_SHADOWS
+#define TRT_FUSED_SHADOWS 1     // small scenes, 1 + 1 lights: both shadow rays of a record classified in one loop (0: A/B runs)
+#endif
 #ifndef TRT_SUM_UNROLL
 #define TRT_SUM_UNROLL 10       // per-pixel sum of the ten samples at the end of a tile: unroll factor (code size vs loop overhead)
 #endif
@@ -243,10 +246,6 @@ __device__ __forceinline__ void sphere_exact(const double4 g, int i, int oi, con
     sphere_exact_oc<COUNT, ANY_ORDER>(oc, c, i, oi, o, d, two_a, four_a, closest, obj, index, best_oi, t_hit, tally);
 }
 
-// reference index of the sphere at position i (identity unless the scene is k-d-sorted)
-template <bool CLUSTERED>
-__device__ __forceinline__ int reference_index(const RenderParams &P, int i) { return CLUSTERED ? __ldg(&P.sphere_orig[i]) : i; }
-
 // ray_intersects_plane (TRT.c:677-695) + the ground branch of trace_ray (TRT.c:831-853); `num` is
 // dot(ground point - origin, normal) (TRT.c:684-685), passed in because several callers share it
 template <bool COUNT>
@@ -344,10 +343,15 @@ struct Query {
 // CONST_RECORDS: small scene (at most TRT_CLUSTER_MIN_SPHERES spheres): records in shared memory (s_pairs, copied at kernel
 // start), reference order, no clusters.  Otherwise the scene is k-d-sorted with bounding balls and its records are read
 // from global memory.
-template <bool CONST_RECORDS>
+// raw outcome of pass 1 (the float classification of a small scene's single chunk) when it was taken elsewhere: see classify_two_shadows
+struct Classified { unsigned int survivors; bool blocked; };
+
+template <bool CONST_RECORDS, bool PRE = false>
 __device__ __forceinline__ bool query_certified(const RenderParams &P, const float4 *s_pairs, const Query &qy, const d3 &o, double num_g, bool use_patch,
-                                                unsigned int patch_mask, int &obj, int &index, double &t_hit, unsigned int *exact_tests)
+                                                unsigned int patch_mask, int &obj, int &index, double &t_hit, unsigned int *exact_tests,
+                                                const Classified pre = Classified{0u, false})
 {
+    static_assert(!PRE || CONST_RECORDS, "a precomputed classification covers the single chunk of a small scene");
     const Tally<false> no_tally{nullptr};
     const d3 d = qy.d;
     double closest = INFINITY;
@@ -408,10 +412,11 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const flo
         // (small scenes: the mask of existing spheres is a per-scene constant, host-evaluated)
         const unsigned int valid = CONST_RECORDS ? c_scene.sphere_mask : (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u));
         const unsigned int candidates = use_patch ? (patch_mask & valid) : (valid & reachable);
-        unsigned int survivors = 0;
+        unsigned int survivors = PRE ? pre.survivors : 0u;
+        if (PRE) blocked = pre.blocked;
         // two spheres per trip: the arithmetic of trt_cert_sphere2 (same operations, same rounding) on float pairs
 #pragma unroll 1
-        for (unsigned int m = (candidates | (candidates >> 1)) & 0x55555555u; m; m &= m - 1) {
+        for (unsigned int m = PRE ? 0u : ((candidates | (candidates >> 1)) & 0x55555555u); m; m &= m - 1) {
             const int j = __ffs(m) - 1;             // even: spheres base + j and base + j + 1
             CullPair g;
             if (CONST_RECORDS) {
@@ -479,6 +484,71 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const flo
         if (TRT_UNLIKELY(!blocked && qy.ground_candidate)) plane_exact_num<false>(num_g, o, d, closest, obj, t_hit, no_tally);
     }
     return blocked;
+}
+
+// Pass 1 of BOTH shadow queries of a record in one loop (small scenes with 1 + 1 lights): the two rays leave the same point, so
+// a pair's records are loaded once and its centre offsets formed once; the two classifications are independent chains that
+// interleave, and the loop overhead is paid once.  Per ray exactly the operations of query_certified's own pass 1 (same
+// rounding, same comparisons): the results are the ones the separate loops would give.  Candidates: the union of the two
+// queries' candidate masks; each query keeps its own afterwards (query_certified<.., PRE>).
+__device__ __forceinline__ void classify_two_shadows(const float4 *s_pairs, const Query &qa, const Query &qb, unsigned int candidates,
+                                                     Classified &ca, Classified &cb)
+{
+    const float2 nox = make_float2(-qa.rf.ox, -qa.rf.ox), noy = make_float2(-qa.rf.oy, -qa.rf.oy), noz = make_float2(-qa.rf.oz, -qa.rf.oz);
+    const float2 adx = make_float2(qa.rf.dx, qa.rf.dx), ady = make_float2(qa.rf.dy, qa.rf.dy), adz = make_float2(qa.rf.dz, qa.rf.dz);
+    const float2 bdx = make_float2(qb.rf.dx, qb.rf.dx), bdy = make_float2(qb.rf.dy, qb.rf.dy), bdz = make_float2(qb.rf.dz, qb.rf.dz);
+    const float sa = qa.rf.slack_t, sb = qb.rf.slack_t;
+    const float2 sa2 = make_float2(sa, sa), nsa2 = make_float2(-sa, -sa), sb2 = make_float2(sb, sb), nsb2 = make_float2(-sb, -sb);
+    const float2 neg1 = make_float2(-1.0f, -1.0f), shrink2 = make_float2(0.99999237060546875f, 0.99999237060546875f);
+    unsigned int surv_a = 0u, surv_b = 0u;
+    bool blk_a = false, blk_b = false;
+#pragma unroll 1
+    for (unsigned int m = (candidates | (candidates >> 1)) & 0x55555555u; m; m &= m - 1) {
+        const int j = __ffs(m) - 1;
+        const float4 lo = s_pairs[j], hi = s_pairs[j + 1];
+        const float2 gcx = make_float2(lo.x, lo.y), gcy = make_float2(lo.z, lo.w), gcz = make_float2(hi.x, hi.y), gr = make_float2(hi.z, hi.w);
+        const float2 ocx = __fadd2_rn(gcx, nox), ocy = __fadd2_rn(gcy, noy), ocz = __fadd2_rn(gcz, noz);
+        // ray a (directional light: no length)
+        {
+            const float2 tc = __ffma2_rn(ocz, adz, __ffma2_rn(ocy, ady, __fmul2_rn(ocx, adx)));
+            const float2 ntc = __fmul2_rn(tc, neg1);
+            const float2 wx = __ffma2_rn(ntc, adx, ocx), wy = __ffma2_rn(ntc, ady, ocy), wz = __ffma2_rn(ntc, adz, ocz);
+            const float2 h2 = __ffma2_rn(wz, wz, __ffma2_rn(wy, wy, __fmul2_rn(wx, wx)));
+            const float2 outer = __fadd2_rn(gr, sa2);
+            const float2 outer_sq = __fmul2_rn(outer, outer);
+            const float2 front = __ffma2_rn(gr, neg1, tc);
+            const bool miss0 = (h2.x > outer_sq.x) || (tc.x < -sa) || (front.x > qa.far_limit);
+            const bool miss1 = (h2.y > outer_sq.y) || (tc.y < -sa) || (front.y > qa.far_limit);
+            if (!miss0) surv_a |= 1u << j;
+            if (!miss1) surv_a |= 2u << j;
+            const float2 inner = __ffma2_rn(gr, shrink2, nsa2);
+            const float2 inner_sq = __fmul2_rn(inner, inner);
+            const bool blocks0 = (inner.x > 0.0f) && (h2.x < inner_sq.x) && (front.x > sa) && (tc.x < qa.near_limit);
+            const bool blocks1 = (inner.y > 0.0f) && (h2.y < inner_sq.y) && (front.y > sa) && (tc.y < qa.near_limit);
+            blk_a = blk_a || blocks0 || blocks1;
+        }
+        // ray b (point light: near and far limits)
+        {
+            const float2 tc = __ffma2_rn(ocz, bdz, __ffma2_rn(ocy, bdy, __fmul2_rn(ocx, bdx)));
+            const float2 ntc = __fmul2_rn(tc, neg1);
+            const float2 wx = __ffma2_rn(ntc, bdx, ocx), wy = __ffma2_rn(ntc, bdy, ocy), wz = __ffma2_rn(ntc, bdz, ocz);
+            const float2 h2 = __ffma2_rn(wz, wz, __ffma2_rn(wy, wy, __fmul2_rn(wx, wx)));
+            const float2 outer = __fadd2_rn(gr, sb2);
+            const float2 outer_sq = __fmul2_rn(outer, outer);
+            const float2 front = __ffma2_rn(gr, neg1, tc);
+            const bool miss0 = (h2.x > outer_sq.x) || (tc.x < -sb) || (front.x > qb.far_limit);
+            const bool miss1 = (h2.y > outer_sq.y) || (tc.y < -sb) || (front.y > qb.far_limit);
+            if (!miss0) surv_b |= 1u << j;
+            if (!miss1) surv_b |= 2u << j;
+            const float2 inner = __ffma2_rn(gr, shrink2, nsb2);
+            const float2 inner_sq = __fmul2_rn(inner, inner);
+            const bool blocks0 = (inner.x > 0.0f) && (h2.x < inner_sq.x) && (front.x > sb) && (tc.x < qb.near_limit);
+            const bool blocks1 = (inner.y > 0.0f) && (h2.y < inner_sq.y) && (front.y > sb) && (tc.y < qb.near_limit);
+            blk_b = blk_b || blocks0 || blocks1;
+        }
+    }
+    ca.survivors = surv_a; ca.blocked = blk_a;
+    cb.survivors = surv_b; cb.blocked = blk_b;
 }
 
 // hit point pushed back toward the ray origin by EPSILON, TRT.c:871-874
@@ -750,14 +820,13 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                         const double a = dot(d, d);
                         const double two_a = 2.0 * a, four_a = 4.0 * a;
                         for (int wd = 0; wd < mask_words; wd++) {
-                            unsigned int m = W.tmask[wd];
+                            const unsigned int m = W.tmask[wd];
                             exact += (unsigned int)__popc(m);
-                            while (m) {
-                                const int i = wd * 32 + __ffs(m) - 1;
-                                m &= m - 1;
-                                const double4 g = ldg4(P.sphere_prim, i);
-                                sphere_exact_oc<false, CULL == 2>(mk3(g.x, g.y, g.z), g.w, i, reference_index<CULL == 2>(P, i), eye, d, two_a, four_a, closest, obj2, index2, best_oi,
-                                                       t2, no_tally);
+                            if (m) {
+                                const ClosestHit hh = walk_survivors<CULL == 2>(P.sphere_geom, P.sphere_orig, m, wd * 32, eye, d, ClosestHit{closest, t2, obj2, index2, best_oi});
+                                closest = hh.closest; t2 = hh.t_hit; obj2 = hh.obj; index2 = hh.index; best_oi = hh.best_oi;
+                                // (the shared out-of-line walk, not a second inlined copy of the exact test with its sqrt and
+                                // division: 1.5 KB less hot code)
                             }
                         }
                         if (!tile_ground_miss) plane_exact_num<false>(c_scene.prim_num, eye, d, closest, obj2, t2, no_tally);
@@ -864,6 +933,24 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                     d3 lit = mk3(0.0, 0.0, 0.0);
                     bool done = false;
                     const int nq = num_dir + num_point + 1;
+                    // small scenes with 1 + 1 lights: the float classification of BOTH shadow rays runs in one loop at q == 0
+                    // (classify_two_shadows); the point-light query, set up there, and its raw classification wait for q == 1
+                    constexpr bool FUSE = TRT_FUSED_SHADOWS && CULL == 1 && LIGHTS == 1;
+                    Query qy_point;
+                    double light_d2_point = 0.0;
+                    Classified pre_dir{0u, false}, pre_point{0u, false};
+                    auto setup_point_query = [&](Query &qp, const DevLightPoint &Lp, double &light_d2) {
+                        d3 ld = mk3(Lp.pos[0] - at.x, Lp.pos[1] - at.y, Lp.pos[2] - at.z);            // TRT.c:929
+                        light_d2 = dot(ld, ld);
+                        qp.mode = Q_POINT;
+                        qp.plane_denom = 0.0;
+                        qp.d = unit(ld);                                                              // TRT.c:933
+                        const float dist = trt_cert_set_dir_toward(&qp.rf, Lp.pos_f[0], Lp.pos_f[1], Lp.pos_f[2], S0 + Lp.pos_l1);
+                        const float guard = fmaf(2.0f, qp.rf.slack_t, 1e-5f);
+                        qp.near_limit = dist - guard;
+                        qp.far_limit = dist + guard;
+                        qp.ground_candidate = !trt_cert_ground_cannot_block(num_g, Lp.height, c_scene.ground_margin);
+                    };
                     auto one_query = [&](const int q) {
                         // ---- set-up: warp-uniform branch on the kind of query ------------------------------------
                         bool run = true;
@@ -872,7 +959,10 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                         qy.far_limit = INFINITY;
                         qy.ground_candidate = false;
                         qy.plane_denom = 0.0;
-                        if (q < num_dir) {
+                        if (FUSE && q == 1) {
+                            qy = qy_point;
+                            light_d2 = light_d2_point;
+                        } else if (q < num_dir) {
                             const DevLightDir &Ld = c_scene.dir[q];
                             qy.mode = Q_DIR;
                             qy.d = mk3(Ld.L[0], Ld.L[1], Ld.L[2]);                  // unit(-direction), TRT.c:903-904
@@ -880,17 +970,14 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                             qy.rf.slack_t = (32.0f * TRT_CERT_U) * S0;
                             qy.rf.usable = (S0 < 1e15f) && Ld.lf_unit;     // |Lf| = 1 within 1e-5: checked once on the host
                             qy.plane_denom = Ld.plane_denom;
+                            if (FUSE) {
+                                qy_point.rf = qy.rf;                    // same origin
+                                setup_point_query(qy_point, c_scene.point[0], light_d2_point);
+                                const unsigned int cand = use_patch ? ((W.pmask[0] | W.pmask[1]) & c_scene.sphere_mask) : c_scene.sphere_mask;
+                                classify_two_shadows(s_pairs, qy, qy_point, cand, pre_dir, pre_point);
+                            }
                         } else if (q < num_dir + num_point) {
-                            const DevLightPoint &Lp = c_scene.point[q - num_dir];
-                            qy.mode = Q_POINT;
-                            d3 ld = mk3(Lp.pos[0] - at.x, Lp.pos[1] - at.y, Lp.pos[2] - at.z);            // TRT.c:929
-                            light_d2 = dot(ld, ld);
-                            qy.d = unit(ld);                                                              // TRT.c:933
-                            const float dist = trt_cert_set_dir_toward(&qy.rf, Lp.pos_f[0], Lp.pos_f[1], Lp.pos_f[2], S0 + Lp.pos_l1);
-                            const float guard = fmaf(2.0f, qy.rf.slack_t, 1e-5f);
-                            qy.near_limit = dist - guard;
-                            qy.far_limit = dist + guard;
-                            qy.ground_candidate = !trt_cert_ground_cannot_block(num_g, Lp.height, c_scene.ground_margin);
+                            setup_point_query(qy, c_scene.point[q - num_dir], light_d2);
                         } else {
                             // all lights done: finish apply_lighting (TRT.c:960) and accumulate (TRT.c:1034-1051) ...
                             qy.mode = Q_CLOSEST;
@@ -931,8 +1018,13 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                                 int obj3, index3;
                                 double t3;
                                 unsigned int exact = 0;
-                                const bool blocked3 = query_certified<CULL == 1>(P, s_pairs, qy, at, num_g, use_patch, use_patch ? W.pmask[q] : 0u, obj3, index3, t3,
-                                                                                 COUNT ? &exact : nullptr);
+                                bool blocked3;
+                                if (FUSE && q < 2)
+                                    blocked3 = query_certified<true, true>(P, s_pairs, qy, at, num_g, use_patch, use_patch ? W.pmask[q] : 0u, obj3, index3, t3,
+                                                                           COUNT ? &exact : nullptr, q == 0 ? pre_dir : pre_point);
+                                else
+                                    blocked3 = query_certified<CULL == 1>(P, s_pairs, qy, at, num_g, use_patch, use_patch ? W.pmask[q] : 0u, obj3, index3, t3,
+                                                                          COUNT ? &exact : nullptr);
                                 if (COUNT) {
                                     // the audit: both paths must lead to the same decision / the same hit
                                     tally.add(CTR_EXACT_SPHERE_TESTS, exact);
@@ -1395,6 +1487,11 @@ __global__ void k_selftest_division(unsigned long long seed, int iters, unsigned
             if (__double_as_longlong(u.x) != __double_as_longlong(w.x) && !(u.x != u.x && w.x != w.x)) bad++;
             if (__double_as_longlong(u.y) != __double_as_longlong(w.y) && !(u.y != u.y && w.y != w.y)) bad++;
             if (__double_as_longlong(u.z) != __double_as_longlong(w.z) && !(u.z != u.z && w.z != w.z)) bad++;
+            // the guarded square root alone, wherever it claims its fast path
+            bool ok = true;
+            const double ss = v.x * v.x + v.y * v.y + v.z * v.z;
+            const double root = sqrt_guarded(ss, ok);
+            if (ok && __double_as_longlong(root) != __double_as_longlong(__dsqrt_rn(ss))) bad++;
         }
         const Reciprocal inv = reciprocal_of(b);
 #pragma unroll
