@@ -293,15 +293,14 @@ def cpu_baseline_leg(cfg, budget_s=20.0):
 
 def host_pieces(world):
     """Piece schedule of the host-stream path (e2e, N > 1): a rank's band leaves for the host piece by piece, each copy behind
-    the next piece's K1.  Per rank K1 takes T = K1_frame / N and its copy C = bytes / (N * link rate); the step ends at
-    max(T + last copy, first piece's K1 + C) — so the first piece must be SMALL (the copy engine starts early) when C is close to
-    or above T (few GPUs: the copy is the floor), and the last piece small in any case.  Measured rates on this box class:
-    K1 ~23.7 ms per frame, ~50 GB/s per link, ~80 GB/s aggregate host ingest (scripts/pcie_bw.py)."""
-    k1, link, ingest, total = 23.7e-3 / world, 50e9, 80e9, 829.4e6
-    copy = total / min(world * link, ingest)
-    if copy >= 0.8 * k1:
-        return (0.06, 0.14, 0.22, 0.26, 0.2, 0.12)      # copy-bound: start copying after ~6 % of K1, keep the engine fed
-    return (0.3, 0.3, 0.25, 0.15)                        # K1-bound: fewer launches, small exposed tail
+    the next piece's K1.  With N >= 2 the copies are the floor (829 MB into one host buffer: ~10.5 ms at the ~80 GB/s the host
+    ingests, scripts/pcie_bw.py; K1 per rank is 23 ms / N), so the copy engine has to start early and never wait: many pieces,
+    small ones first (the first copy starts after ~4 % of the band) and last (the exposed tail).  Measured at N = 2 (one box,
+    back to back, profiles/r02_e2e_pieces_n2.txt): 4 pieces 0.4/0.3/0.2/0.1 (round 1) 17.5 ms, 4 even-ish 16.7, 5 pieces 16.2,
+    6 pieces 15.6, 8 pieces 14.9."""
+    if os.environ.get("TRT_HOST_PIECES"):            # experiments: "0.1,0.3,0.3,0.2,0.1"
+        return tuple(float(x) for x in os.environ["TRT_HOST_PIECES"].split(","))
+    return (0.04, 0.08, 0.12, 0.14, 0.14, 0.14, 0.12, 0.1, 0.08, 0.04)
 
 
 def traffic_stamp():
@@ -506,9 +505,11 @@ def main():
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=None, help="steps of the end-to-end leg (default: --steps)")
     ap.add_argument("--fused", type=int, default=int(os.environ.get("TRT_BENCH_FUSED", "-1")),
                     help="N > 1, device-resident gather: 1 = K1 stores the encoded tiles straight into rank 0's stream over NVLink (no K2, "
-                         "no copies), 0 = K1, K2 and copy-engine pushes piece by piece, -1 = by GPU count (measured: pieces win at 2 GPUs, "
+                         "no copies), 0 = K1, K2 and copy-engine pushes piece by piece, 2 = K1 then ONE K2 per band that stores into rank 0's stream "
+                         "through the peer mapping, -1 = by GPU count (measured: pieces win at 2 GPUs, "
                          "14.8 vs 15.7 ms, the fused kernel at 8, 4.21 vs 4.38 ms)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
@@ -560,11 +561,12 @@ def main():
     # cost-weighted row bands (sky rows are ~5x cheaper than sphere/ground rows): every rank runs the same
     # deterministic 1/8-resolution pre-pass and derives the same bands; untimed, once per scene
     weights = rd.estimate_row_costs(sc) if world > 1 else None
-    fused = (world >= 8) if args.fused < 0 else bool(args.fused)
+    fused = (world >= 8) if args.fused < 0 else args.fused == 1
+    direct = args.fused == 2
     # N > 1: every rank pushes its encoded pieces into rank 0's stream over NVLink peer memory while its next piece renders
     # (or, fused: K1 itself stores every finished tile's bytes there);
     # the collective that ends a step carries the ranks' K1 times and the next step's bands follow from them (adapt)
-    pipe = pipeline.FramePipeline(rd, width, height, rank, world, row_weights=weights, peer=world > 1, pieces=(0.7, 0.3), adapt=world > 1, fused=fused)
+    pipe = pipeline.FramePipeline(rd, width, height, rank, world, row_weights=weights, peer=world > 1, pieces=(0.7, 0.3), adapt=world > 1, fused=fused, direct=direct)
     stream = torch.cuda.current_stream()
 
     peaks = rd.measure_peaks() if rank == 0 else None
@@ -674,11 +676,12 @@ def main():
     for _ in range(3):
         e2e_step()
     barrier()
+    e2e_steps = args.e2e_steps or args.steps
     w0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         e2e_step()
     barrier()
-    e2e_s = time.perf_counter() - w0
+    e2e_s = (time.perf_counter() - w0) * (args.steps / e2e_steps)      # per-step time x steps, as the reduction below expects
     host_ok = None
     if world > 1:
         if rank == 0:
@@ -760,7 +763,8 @@ def main():
             # per piece on every rank: k_tile_certs (small scenes) + K1 (+ K2 unless fused), plus rank 0's trt_stream_frame_device once per step
             "gpu_launches": int(((1 if (world > 1 and fused) else 2) + (1 if cfg["kind"] == "demo" else 0)) * k1_launches_all + args.steps),
             "gather": None if world == 1 else ("fused: K1 stores encoded tiles into rank 0's stream (NVLink peer memory)" if fused else
-                                               "pieces: K1, K2, copy-engine push per piece (NVLink peer memory)"),
+                                               ("direct: K1, then K2 stores the band's bytes into rank 0's stream (NVLink peer memory)" if direct else
+                                                "pieces: K1, K2, copy-engine push per piece (NVLink peer memory)")),
             "stream_identical_to_single_gpu": stream_ok,
             "host_stream_identical_to_single_gpu": host_ok,
             "bands": None if world == 1 else {"rows": final_bands, "k1_ms_max_rank": k1_ms_max, "k1_ms_mean_rank": k1_ms_mean,

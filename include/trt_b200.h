@@ -213,6 +213,11 @@ int trt_copy_to_host(void *dst, const void *d_src, size_t bytes);
 int trt_copy_to_device(void *d_dst, const void *src, size_t bytes);
 int trt_synchronize(void);
 
+/* Self-checking build (libtrt_b200 compiled with -DTRT_BOUNDS_CHECK; scripts/bounds_check.py): every computed index of the kernels
+ * is checked on the device; out32[0..15] = violations per check site of the render kernels, [16..31] of the encode kernel, read and
+ * cleared.  Returns 1 when the checks are compiled in, 0 in the product build (all counters 0). */
+int trt_debug_bounds(unsigned int *out32);
+
 /* timing of the last trt_project_scene / trt_render_ansi call, CUDA events on trt_stream(), ms */
 float trt_last_render_ms(void);
 float trt_last_encode_ms(void);

@@ -101,4 +101,19 @@ dirs = np.ascontiguousarray(rays[:, 3:])
 o5 = np.zeros((64, 5), dtype=np.int32)
 L.trt_probe_skybox(dirs.ctypes.data, 64, o5.ctypes.data)
 print("probes ok", flush=True)
+# a few random scenes as well (scripts/fuzz_parity.py: sphere counts across the chunk and cluster limits, tilted grounds, many lights)
+import importlib.util
+spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz_parity.py"))
+fuzz = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(fuzz)
+rng = np.random.default_rng(7)
+for k in range(12):
+    fsc = fuzz.random_scene(rng, sky)
+    rd.project_scene(fsc)
+    np.array(rd.render_ansi(fsc))
+print("fuzz scenes ok", flush=True)
+# self-checking build (-DTRT_BOUNDS_CHECK): the kernels' own index checks
+counts = (C.c_uint * 32)()
+compiled = L.trt_debug_bounds(counts)
+print("bounds checks compiled in:", bool(compiled), " violations per site (render 0-15, encode 16-31):", list(counts), flush=True)
 rd.close()

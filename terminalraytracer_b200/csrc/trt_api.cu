@@ -74,7 +74,10 @@ struct Context {
     bool have_scene = false;
     bool cull_allowed = true;   // trt_set_cull(); the FP32 miss test can be switched off for A/B runs
     bool cull = true;           // cull_allowed && this scene's magnitudes are inside the bound's range
-    Buffer sphere_geom, sphere_cull, sphere_mat, cull_pairs, sphere_orig, sphere_pos, clusters, subballs;
+    // every per-scene array (sphere geometry, certificate records, materials, k-d order, ball tree) lives in ONE device blob with
+    // the layout of the staging arena, so that an upload is one host-to-device copy plus the constant block
+    Buffer scene_blob;
+    size_t off_geom = 0, off_cull = 0, off_mat = 0, off_pairs = 0, off_orig = 0, off_pos = 0, off_ball = 0, off_link = 0;   // off_ball / off_link: cluster balls / their sub-balls
     // skybox
     Buffer sky;
     int sky_dim = -1, sky_face_stride = 0;
@@ -82,6 +85,11 @@ struct Context {
     Buffer tile_counter, counters, byte_to_unit, scratch, tile_info;
     Buffer pixels, quant, bytes;
     PinnedBuffer stage;
+    // the streaming sink's double buffers and events: kept across calls (page-locking and freeing 100 MB per call took longer
+    // than rendering 360 frames)
+    Buffer orbit_dev[2];
+    PinnedBuffer orbit_host[2];
+    cudaEvent_t orbit_encoded[2] = {nullptr, nullptr}, orbit_copied[2] = {nullptr, nullptr};
     // pinned staging for scene uploads: copies from pageable memory make the runtime wait for the stream first, which
     // would serialise the frames of trt_render_orbit; two arenas so that a frame's upload never overwrites the previous one's
     PinnedBuffer arena[2];
@@ -102,6 +110,13 @@ const void *staged(const void *src, size_t bytes)
     memcpy((char *)g.arena[g.arena_which].p + at, src, bytes);
     g.arena_used = at + bytes;
     return (const char *)g.arena[g.arena_which].p + at;
+}
+
+// the same, returning the offset inside the arena (= the offset inside the device blob)
+size_t staged_at(const void *src, size_t bytes)
+{
+    const char *p = (const char *)staged(src, bytes);
+    return (size_t)(p - (const char *)g.arena[g.arena_which].p);
 }
 
 void require_init(const char *who)
@@ -171,7 +186,7 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
     }
     DevScene &s = g.scene;
     {
-        const size_t per_sphere = sizeof(double4) + sizeof(DevMaterial) + sizeof(float4) * 2 + sizeof(CullPair) + sizeof(int) * 2;
+        const size_t per_sphere = sizeof(double4) + sizeof(DevMaterial) + sizeof(float4) * 2 + sizeof(CullPair) + sizeof(int) * 2 + 32;
         const size_t need = sizeof(DevScene) + 4096 + per_sphere * ((size_t)scene->num_spheres + 64);
         g.arena_which = wait ? 0 : (g.arena_which ^ 1);
         // an arena may be rewritten only after the copies of the upload that last used it have run
@@ -355,27 +370,16 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
             }
         }
     }
-    g.sphere_orig.reserve(sizeof(int) * orig.size());
-    g.sphere_pos.reserve(sizeof(int) * pos.size());
-    g.clusters.reserve(sizeof(float4) * clusters.size());
-    g.subballs.reserve(sizeof(CullPair) * subballs.size());
-    CK(cudaMemcpyAsync(g.subballs.p, staged(subballs.data(), sizeof(CullPair) * subballs.size()), sizeof(CullPair) * subballs.size(), cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(g.sphere_orig.p, staged(orig.data(), sizeof(int) * orig.size()), sizeof(int) * orig.size(), cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(g.sphere_pos.p, staged(pos.data(), sizeof(int) * pos.size()), sizeof(int) * pos.size(), cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(g.clusters.p, staged(clusters.data(), sizeof(float4) * clusters.size()), sizeof(float4) * clusters.size(), cudaMemcpyHostToDevice, g.stream));
+    g.off_ball = staged_at(clusters.data(), sizeof(float4) * clusters.size());
+    g.off_link = staged_at(subballs.data(), sizeof(CullPair) * subballs.size());
+    g.off_orig = staged_at(orig.data(), sizeof(int) * orig.size());
+    g.off_pos = staged_at(pos.data(), sizeof(int) * pos.size());
     g.cull = g.cull_allowed && in_range && ground_in_range;
     s.filter_enabled = g.cull ? 1 : 0;
     s.filter_centre_l1 = float_round_up(centre_l1 * (1.0 + 1.0 / 1048576.0));
-    g.sphere_geom.reserve(sizeof(double4) * geom.size());
-    g.sphere_mat.reserve(sizeof(DevMaterial) * mats.size());
-    g.sphere_cull.reserve(sizeof(float4) * cull.size());
-    CK(cudaMemcpyAsync(g.sphere_cull.p, staged(cull.data(), sizeof(float4) * cull.size()), sizeof(float4) * cull.size(), cudaMemcpyHostToDevice, g.stream));
-    // Every source goes through staged(): a memcpy into the page-locked arena g.arena[g.arena_which], so the vectors may die
-    // when this function returns and the copies are truly asynchronous.  Invariant: an arena may be rewritten only after the
-    // copies of the upload that last used it have run — arena_done[] is recorded behind them and waited for at the top of
-    // this function; wait == false alternates the two arenas, so the host runs at most two uploads ahead of the device.
-    CK(cudaMemcpyAsync(g.sphere_geom.p, staged(geom.data(), sizeof(double4) * geom.size()), sizeof(double4) * geom.size(), cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(g.sphere_mat.p, staged(mats.data(), sizeof(DevMaterial) * mats.size()), sizeof(DevMaterial) * mats.size(), cudaMemcpyHostToDevice, g.stream));
+    g.off_cull = staged_at(cull.data(), sizeof(float4) * cull.size());
+    g.off_geom = staged_at(geom.data(), sizeof(double4) * geom.size());
+    g.off_mat = staged_at(mats.data(), sizeof(DevMaterial) * mats.size());
     // the same records two by two for the packed classification; the odd one out is paired with a sphere of radius 0
     std::vector<CullPair> pairs((size_t)(n / 2 + 1));
     for (size_t p = 0; p < pairs.size(); p++) {
@@ -385,8 +389,18 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
         pairs[p].cz = make_float2(a.z, b.z);
         pairs[p].r = make_float2(a.w, b.w);
     }
-    g.cull_pairs.reserve(sizeof(CullPair) * pairs.size());
-    CK(cudaMemcpyAsync(g.cull_pairs.p, staged(pairs.data(), sizeof(CullPair) * pairs.size()), sizeof(CullPair) * pairs.size(), cudaMemcpyHostToDevice, g.stream));
+    g.off_pairs = staged_at(pairs.data(), sizeof(CullPair) * pairs.size());
+    // Every source went through staged(): a memcpy into the page-locked arena g.arena[g.arena_which], so the vectors may die when
+    // this function returns and the copy is truly asynchronous.  Invariant: an arena may be rewritten only after the copies of the
+    // upload that last used it have run — arena_done[] is recorded behind them and waited for at the top of this function;
+    // wait == false alternates the two arenas, so the host runs at most two uploads ahead of the device.  The device blob itself is
+    // rewritten in stream order, behind the kernels of the previous frame.
+    const size_t blob_bytes = g.arena_used;
+    if (g.scene_blob.cap < blob_bytes) {
+        CK(cudaStreamSynchronize(g.stream));       // nothing may still be reading the blob that is replaced
+        g.scene_blob.reserve(blob_bytes + 4096);
+    }
+    CK(cudaMemcpyAsync(g.scene_blob.p, g.arena[g.arena_which].p, blob_bytes, cudaMemcpyHostToDevice, g.stream));
     upload_scene_constants(*(const DevScene *)staged(&s, sizeof s), g.stream);
     CK(cudaEventRecord(g.arena_done[g.arena_which], g.stream));
     g.arena_busy[g.arena_which] = true;
@@ -429,14 +443,15 @@ RenderParams make_params(int width, int height, int row0, int row1, double *d_pi
     p.pixels = d_pixels;
     p.quant = d_quant;
     p.ansi = nullptr;
-    p.sphere_geom = (const double4 *)g.sphere_geom.p;
-    p.sphere_cull = (const float4 *)g.sphere_cull.p;
-    p.cull_pairs = (const CullPair *)g.cull_pairs.p;
-    p.sphere_orig = (const int *)g.sphere_orig.p;
-    p.sphere_pos = (const int *)g.sphere_pos.p;
-    p.clusters = (const float4 *)g.clusters.p;
-    p.subballs = (const CullPair *)g.subballs.p;
-    p.sphere_mat = (const DevMaterial *)g.sphere_mat.p;
+    const char *blob = (const char *)g.scene_blob.p;
+    p.sphere_geom = (const double4 *)(blob + g.off_geom);
+    p.sphere_cull = (const float4 *)(blob + g.off_cull);
+    p.cull_pairs = (const CullPair *)(blob + g.off_pairs);
+    p.sphere_orig = (const int *)(blob + g.off_orig);
+    p.sphere_pos = (const int *)(blob + g.off_pos);
+    p.clusters = (const float4 *)(blob + g.off_ball);
+    p.subballs = (const CullPair *)(blob + g.off_link);
+    p.sphere_mat = (const DevMaterial *)(blob + g.off_mat);
     p.byte_to_unit = (const double *)g.byte_to_unit.p;
     p.sky = (const uchar4 *)g.sky.p;
     // sized for the whole frame, so that bands of any height (adaptive bands, row chunks) never reallocate
@@ -445,6 +460,8 @@ RenderParams make_params(int width, int height, int row0, int row1, double *d_pi
     p.tile_counter = (unsigned int *)g.tile_counter.p;
     g.scratch.reserve(render_scratch_bytes(g.num_sms));
     p.sample_scratch = (double *)g.scratch.p;
+    p.scratch_bytes = g.scratch.cap;
+    p.tile_info_bytes = g.tile_info.cap;
     p.counters = count ? (unsigned long long *)g.counters.p : nullptr;
     p.row_cost = nullptr;
     return p;
@@ -517,14 +534,7 @@ void trt_shutdown(void)
 {
     if (!g.ready) return;
     cudaStreamSynchronize(g.stream);
-    g.sphere_geom.release();
-    g.sphere_cull.release();
-    g.sphere_mat.release();
-    g.cull_pairs.release();
-    g.sphere_orig.release();
-    g.sphere_pos.release();
-    g.clusters.release();
-    g.subballs.release();
+    g.scene_blob.release();
     g.sky.release();
     g.tile_counter.release();
     g.scratch.release();
@@ -535,6 +545,13 @@ void trt_shutdown(void)
     g.quant.release();
     g.bytes.release();
     g.stage.release();
+    for (int b = 0; b < 2; b++) {
+        g.orbit_dev[b].release();
+        g.orbit_host[b].release();
+        if (g.orbit_encoded[b]) cudaEventDestroy(g.orbit_encoded[b]);
+        if (g.orbit_copied[b]) cudaEventDestroy(g.orbit_copied[b]);
+        g.orbit_encoded[b] = g.orbit_copied[b] = nullptr;
+    }
     g.arena[0].release();
     g.arena[1].release();
     for (auto &ev : g.ev) {
@@ -790,14 +807,8 @@ int trt_probe_skybox(const double *dirs, int n, int *out)
         g.scene.sky_dim = g.sky_dim;
         g.scene.sky_face_stride = g.sky_face_stride;
         upload_scene_constants(g.scene, g.stream);
-        g.sphere_geom.reserve(sizeof(double4));
-        g.sphere_cull.reserve(sizeof(float4));
-        g.cull_pairs.reserve(sizeof(CullPair));
-        g.sphere_orig.reserve(sizeof(int));
-        g.sphere_pos.reserve(sizeof(int));
-        g.clusters.reserve(sizeof(float4));
-        g.subballs.reserve(sizeof(CullPair) * 2);
-        g.sphere_mat.reserve(sizeof(DevMaterial));
+        g.scene_blob.reserve(4096);
+        g.off_geom = g.off_cull = g.off_mat = g.off_pairs = g.off_orig = g.off_pos = g.off_ball = g.off_link = 0;
         g.have_scene = true;
     } else {
         g.scene.sky_dim = g.sky_dim;
@@ -946,12 +957,12 @@ static int orbit_loop(const trt_Scene *scene, int width, int height, const doubl
 {
     const size_t total = TRT_STREAM_BYTES(width, height);
     g.quant.reserve(sizeof(uchar4) * (size_t)width * (size_t)height);
-    Buffer d_bytes[2];
-    cudaEvent_t encoded[2], copied[2];
+    Buffer (&d_bytes)[2] = g.orbit_dev;
+    cudaEvent_t (&encoded)[2] = g.orbit_encoded, (&copied)[2] = g.orbit_copied;
     for (int b = 0; b < 2; b++) {
         d_bytes[b].reserve(total + 16);
-        CK(cudaEventCreateWithFlags(&encoded[b], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+        if (!encoded[b]) CK(cudaEventCreateWithFlags(&encoded[b], cudaEventDisableTiming));
+        if (!copied[b]) CK(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
     }
     trt_Scene posed = *scene;
     int launched = 0, delivered = 0, pending_frame[2] = {-1, -1};
@@ -998,17 +1009,11 @@ static int orbit_loop(const trt_Scene *scene, int width, int height, const doubl
     }
     CK(cudaStreamSynchronize(g.stream));
     CK(cudaStreamSynchronize(g.copy_stream));
-    for (int b = 0; b < 2; b++) {
-        d_bytes[b].release();
-        cudaEventDestroy(encoded[b]);
-        cudaEventDestroy(copied[b]);
-    }
     return delivered;
 }
 
 namespace {
 struct OwnBuffers {
-    PinnedBuffer h[2];
     int next = 0;
     trt_frame_sink sink = nullptr;
     void *user = nullptr;
@@ -1016,7 +1021,7 @@ struct OwnBuffers {
 char *own_acquire(int, size_t, void *u)
 {
     OwnBuffers *o = (OwnBuffers *)u;
-    return (char *)o->h[(o->next++) & 1].p;     // frame k-2's buffer: orbit_loop delivered that frame before asking again
+    return (char *)g.orbit_host[(o->next++) & 1].p;     // frame k-2's buffer: orbit_loop delivered that frame before asking again
 }
 int own_sink(const char *bytes, size_t n, int frame, void *u)
 {
@@ -1033,10 +1038,8 @@ int trt_render_orbit(const trt_Scene *scene, int width, int height, const double
     OwnBuffers own;
     own.sink = sink;
     own.user = user;
-    for (int b = 0; b < 2; b++) own.h[b].reserve(TRT_STREAM_BYTES(width, height));
-    const int delivered = orbit_loop(scene, width, height, times, n_frames, first, stride, own_acquire, own_sink, &own);
-    for (int b = 0; b < 2; b++) own.h[b].release();
-    return delivered;
+    for (int b = 0; b < 2; b++) g.orbit_host[b].reserve(TRT_STREAM_BYTES(width, height));
+    return orbit_loop(scene, width, height, times, n_frames, first, stride, own_acquire, own_sink, &own);
 }
 
 int trt_render_orbit_to(const trt_Scene *scene, int width, int height, const double *times, int n_frames, int first, int stride,
@@ -1176,6 +1179,12 @@ int trt_synchronize(void)
     require_init("trt_synchronize");
     CK(cudaStreamSynchronize(g.stream));
     return 0;
+}
+int trt_debug_bounds(unsigned int *out32)
+{
+    require_init("trt_debug_bounds");
+    const int a = render_bounds_read(out32), b = encode_bounds_read(out32 + 16);
+    return a && b;
 }
 float trt_last_render_ms(void) { return g.last_render_ms; }
 float trt_last_encode_ms(void) { return g.last_encode_ms; }

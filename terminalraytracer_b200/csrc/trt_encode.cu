@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode(const Src *__restrict__ 
         // out[-1] is the left neighbour's last word, and a cell always ends in ESC [ 0 m
         const unsigned int sh = 8u * (a & 3u);                   // uniform over the CTA
         unsigned int *const dst = s_win + (a >> 2) + threadIdx.x * NW;
+        TRT_BOUND((a >> 2) + threadIdx.x * NW + NW < ENC_WORDS + 8, 0);
         unsigned int prev = 0x6d305b1bu;
 #pragma unroll
         for (int k = 0; k < NW; k++) {
@@ -156,6 +157,9 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode(const Src *__restrict__ 
         const unsigned int bytes = (unsigned int)(q_last - q_first) * 16u;
         const unsigned int s_addr = (unsigned int)__cvta_generic_to_shared(s_win) + (unsigned int)q_first * 16u;
         unsigned char *const g_addr = chunk0 + (size_t)q_first * 16;
+        TRT_BOUND(g0 >= byte_offset && g0 + (unsigned long long)nbytes <= byte_offset + (unsigned long long)rows * row_bytes &&
+                  (unsigned long long)q_first * 16ull >= a && (unsigned long long)q_last * 16ull <= a + (unsigned long long)nbytes &&
+                  (reinterpret_cast<unsigned long long>(g_addr) & 15ull) == 0ull && (s_addr & 15u) == 0u && q_last * 16 <= (ENC_WORDS + 8) * 4, 1);
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g_addr), "r"(s_addr), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
@@ -166,7 +170,10 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode(const Src *__restrict__ 
         const int q = j < 16 ? 0 : q_last;
         const int b = q * 16 + (j & 15);                          // staging byte
         const bool partial = j < 16 ? (q_first == 1) : (q_last < nchunks && q_last >= q_first);
-        if (partial && b >= (int)a && b < (int)a + nbytes) chunk0[b] = s_bytes[b];
+        if (partial && b >= (int)a && b < (int)a + nbytes) {
+            TRT_BOUND(b < (ENC_WORDS + 8) * 4, 2);
+            chunk0[b] = s_bytes[b];
+        }
     }
     if (threadIdx.x == 0 && q_last > q_first) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive the read
 }
@@ -215,6 +222,20 @@ static void ck(cudaError_t e, int line)
         fprintf(stderr, "%s:%d: CUDA error: %s\n", __FILE__, line, cudaGetErrorString(e));
         exit(1);
     }
+}
+
+int encode_bounds_read(unsigned int *out16)
+{
+#ifdef TRT_BOUNDS_CHECK
+    ck(cudaDeviceSynchronize(), __LINE__);
+    ck(cudaMemcpyFromSymbol(out16, g_trt_bounds, sizeof(unsigned int) * 16), __LINE__);
+    const unsigned int zero[16] = {0};
+    ck(cudaMemcpyToSymbol(g_trt_bounds, zero, sizeof zero), __LINE__);
+    return 1;
+#else
+    for (int i = 0; i < 16; i++) out16[i] = 0u;
+    return 0;
+#endif
 }
 
 template <typename Src>

@@ -10,6 +10,8 @@ void upload_scene_constants(const DevScene &scene, cudaStream_t stream);
 // one_plus_one: the scene has exactly one directional and one point light (specialised kernel flavour)
 void launch_render(const RenderParams &p, bool count, int cull, bool one_plus_one, int num_sms, cudaStream_t stream);
 int render_ctas_per_sm();
+int render_bounds_read(unsigned int *out16);   // self-checking build (-DTRT_BOUNDS_CHECK): violation counters of trt_render.cu
+int encode_bounds_read(unsigned int *out16);   // ... of trt_encode.cu
 size_t render_scratch_bytes(int num_sms);   // RenderParams::sample_scratch must be at least this big
 size_t render_tile_info_bytes(int width, int rows);   // RenderParams::tile_info for a launch of `rows` rows (k_tile_certs)
 unsigned long long run_selftest_division(unsigned long long seed, int ctas, int iters, unsigned long long *d_scratch, cudaStream_t stream);

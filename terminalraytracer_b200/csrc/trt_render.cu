@@ -44,6 +44,9 @@ __constant__ DevScene c_scene;
 // of sm_100: one issue slot, two spheres; .x = sphere 2p, .y = sphere 2p+1, a pad sphere has r = 0 — live in global memory,
 // RenderParams::cull_pairs; small scenes copy theirs into shared memory at kernel start.)
 
+#ifndef TRT_TILES_BOTTOM_UP
+#define TRT_TILES_BOTTOM_UP 1
+#endif
 #ifndef TRT_FUSED_SHADOWS
 #define TRT_FUSED_SHADOWS 1     // small scenes, 1 + 1 lights: both shadow rays of a record classified in one loop (0: A/B runs)
 #endif
@@ -188,6 +191,7 @@ static __device__ TRT_SKY_INLINE d3 sky_colour_of(const uchar4 *sky, const doubl
     int face, texel;
     if (TRT_UNLIKELY(!(c_scene.filter_enabled && trt_cert_sky_texel((float)d.x, (float)d.y, (float)d.z, c_scene.sky_dim, &face, &texel))))
         texel = sky_texel_index(unit(d), c_scene.sky_dim, face);
+    TRT_BOUND(face >= 0 && face < 6 && texel >= 0 && texel < c_scene.sky_face_stride, 5);
     const uchar4 t = __ldg(&sky[(size_t)face * (size_t)c_scene.sky_face_stride + (size_t)texel]);
     return mk3(s_byte_to_unit[t.x], s_byte_to_unit[t.y], s_byte_to_unit[t.z]);   // TRT.c:866
 }
@@ -346,12 +350,44 @@ struct Query {
 // raw outcome of pass 1 (the float classification of a small scene's single chunk) when it was taken elsewhere: see classify_two_shadows
 struct Classified { unsigned int survivors; bool blocked; };
 
-template <bool CONST_RECORDS, bool PRE = false>
-__device__ __forceinline__ bool query_certified(const RenderParams &P, const float4 *s_pairs, const Query &qy, const d3 &o, double num_g, bool use_patch,
-                                                unsigned int patch_mask, int &obj, int &index, double &t_hit, unsigned int *exact_tests,
-                                                const Classified pre = Classified{0u, false})
+// the ground's part of a query, after the spheres (TRT.c:831-853 through 907 / 936-941): shared by both query forms
+__device__ __forceinline__ void finish_query(const Query &qy, const d3 &o, double num_g, bool blocked, double &closest, int &obj, double &t_hit)
 {
-    static_assert(!PRE || CONST_RECORDS, "a precomputed classification covers the single chunk of a small scene");
+    const Tally<false> no_tally{nullptr};
+    const bool usable = qy.rf.usable != 0;
+    if (qy.mode == Q_CLOSEST) {
+        // (num_g is the reference's own numerator for this origin: only the denominator's sign is left to the float certificate)
+        if (!(usable && trt_cert_plane_miss_num(&qy.rf, num_g, c_scene.ground_normal_f[0], c_scene.ground_normal_f[1], c_scene.ground_normal_f[2])))
+            plane_exact_num<false>(num_g, o, qy.d, closest, obj, t_hit, no_tally);
+    } else if (qy.mode == Q_DIR) {
+        // any hit blocks.  The ground (TRT.c:677-695): numerator and denominator are the reference's own doubles
+        // (the denominator is a per-light constant); opposite signs or a zero numerator give t <= 0, a miss,
+        // without the division.
+        if (TRT_UNLIKELY(!blocked && obj == 0 && fabs(qy.plane_denom) > 0.00001 && num_g != 0.0 && ((num_g < 0.0) == (qy.plane_denom < 0.0)))) {
+            const double t = ieee_div(num_g, qy.plane_denom);
+            if (t > 0.00001) obj = 2;
+        }
+    } else {
+        if (TRT_UNLIKELY(!blocked && qy.ground_candidate)) plane_exact_num<false>(num_g, o, qy.d, closest, obj, t_hit, no_tally);
+    }
+}
+
+// Many-sphere scenes (CULL == 2): the spheres are in k-d order, every 32 consecutive ones — one chunk of this loop — under a bounding
+// ball and every 8 under a ball inside it (trt_cert_cluster_miss).  The WARP walks the chunks together: record addresses stay
+// warp-uniform (one transaction per load), a chunk no lane's ray can reach is skipped by all, and every lane drops what its own ray
+// cannot reach.  (A per-lane stackless walk of a bounding-ball tree over the same order, leaves of 8 — 50 ball tests and 7 leaves per
+// query on the CPU model instead of 32 + 64 balls and ~60 spheres — was measured twice: 61.7 ms with the leaf work inside the walk
+// loop, 68.4 ms as a while-while traversal, against 60.4 ms for this form at 1920x1080: every lane then loads its own nodes and
+// records, 32 transactions per load instead of one.)
+__device__ __forceinline__ bool query_clustered(const RenderParams &P, const Query &qy, const d3 &o, double num_g, int &obj, int &index, double &t_hit,
+                                                unsigned int *exact_tests)
+{
+    constexpr bool CONST_RECORDS = false, PRE = false;
+    const bool use_patch = false;
+    const unsigned int patch_mask = 0u;
+    const float4 *const s_pairs = nullptr;
+    const Classified pre{0u, false};
+    (void)s_pairs; (void)pre; (void)PRE;
     const Tally<false> no_tally{nullptr};
     const d3 d = qy.d;
     double closest = INFINITY;
@@ -486,11 +522,96 @@ __device__ __forceinline__ bool query_certified(const RenderParams &P, const flo
     return blocked;
 }
 
-// Pass 1 of BOTH shadow queries of a record in one loop (small scenes with 1 + 1 lights): the two rays leave the same point, so
-// a pair's records are loaded once and its centre offsets formed once; the two classifications are independent chains that
-// interleave, and the loop overhead is paid once.  Per ray exactly the operations of query_certified's own pass 1 (same
-// rounding, same comparisons): the results are the ones the separate loops would give.  Candidates: the union of the two
-// queries' candidate masks; each query keeps its own afterwards (query_certified<.., PRE>).
+// Small scenes (CONST_RECORDS: at most TRT_CLUSTER_MIN_SPHERES = 32 spheres, one chunk, records in shared memory) classify their
+// candidates in one warp-uniform loop; many-sphere scenes go to query_clustered.
+template <bool CONST_RECORDS, bool PRE = false>
+__device__ __forceinline__ bool query_certified(const RenderParams &P, const float4 *s_pairs, const Query &qy, const d3 &o, double num_g, bool use_patch,
+                                                unsigned int patch_mask, int &obj, int &index, double &t_hit, unsigned int *exact_tests,
+                                                const Classified pre = Classified{0u, false})
+{
+    static_assert(!PRE || CONST_RECORDS, "a precomputed classification covers the single chunk of a small scene");
+    if (!CONST_RECORDS) return query_clustered(P, qy, o, num_g, obj, index, t_hit, exact_tests);
+    const d3 d = qy.d;
+    double closest = INFINITY;
+    obj = 0;
+    index = -1;
+    t_hit = 0.0;
+    const bool usable = qy.rf.usable != 0;
+    const bool shadow = qy.mode != Q_CLOSEST;
+    bool blocked = false;
+    // the certificate ray in packed form: both halves of every pair carry the same value
+    struct { float2 nox, noy, noz, dx, dy, dz; } rp;
+    rp.nox = make_float2(-qy.rf.ox, -qy.rf.ox); rp.noy = make_float2(-qy.rf.oy, -qy.rf.oy); rp.noz = make_float2(-qy.rf.oz, -qy.rf.oz);
+    rp.dx = make_float2(qy.rf.dx, qy.rf.dx); rp.dy = make_float2(qy.rf.dy, qy.rf.dy); rp.dz = make_float2(qy.rf.dz, qy.rf.dz);
+    const float slack = qy.rf.slack_t;
+    const float2 slack2 = make_float2(slack, slack), nslack2 = make_float2(-slack, -slack);
+    const float2 neg1 = make_float2(-1.0f, -1.0f), shrink2 = make_float2(0.99999237060546875f, 0.99999237060546875f);
+    int best_oi = -1;
+    {
+        // pass 1 (float, warp-uniform record addresses): classify the candidate spheres — all of them, or, for the
+        // first-generation hits of a patch tile, the few the patch certificate left (use_patch)
+        // (the mask of existing spheres is a per-scene constant, host-evaluated)
+        const unsigned int valid = c_scene.sphere_mask;
+        const unsigned int candidates = use_patch ? (patch_mask & valid) : valid;
+        unsigned int survivors = PRE ? pre.survivors : 0u;
+        if (PRE) blocked = pre.blocked;
+        // two spheres per trip: the arithmetic of trt_cert_sphere2 (same operations, same rounding) on float pairs
+#pragma unroll 1
+        for (unsigned int m = PRE ? 0u : ((candidates | (candidates >> 1)) & 0x55555555u); m; m &= m - 1) {
+            const int j = __ffs(m) - 1;             // even: spheres j and j + 1
+            const float4 lo = s_pairs[j], hi = s_pairs[j + 1];      // pair j / 2 = float4 j and j + 1 (j is even)
+            CullPair g;
+            g.cx = make_float2(lo.x, lo.y); g.cy = make_float2(lo.z, lo.w);
+            g.cz = make_float2(hi.x, hi.y); g.r = make_float2(hi.z, hi.w);
+            const float2 ocx = __fadd2_rn(g.cx, rp.nox), ocy = __fadd2_rn(g.cy, rp.noy), ocz = __fadd2_rn(g.cz, rp.noz);
+            const float2 tc = __ffma2_rn(ocz, rp.dz, __ffma2_rn(ocy, rp.dy, __fmul2_rn(ocx, rp.dx)));
+            const float2 ntc = __fmul2_rn(tc, neg1);
+            const float2 wx = __ffma2_rn(ntc, rp.dx, ocx), wy = __ffma2_rn(ntc, rp.dy, ocy), wz = __ffma2_rn(ntc, rp.dz, ocz);
+            const float2 h2 = __ffma2_rn(wz, wz, __ffma2_rn(wy, wy, __fmul2_rn(wx, wx)));
+            const float2 outer = __fadd2_rn(g.r, slack2);
+            const float2 outer_sq = __fmul2_rn(outer, outer);
+            const float2 front = __ffma2_rn(g.r, neg1, tc);
+            const bool miss0 = (h2.x > outer_sq.x) || (tc.x < -slack) || (front.x > qy.far_limit);
+            const bool miss1 = (h2.y > outer_sq.y) || (tc.y < -slack) || (front.y > qy.far_limit);
+            if (!miss0) survivors |= 1u << j;
+            if (!miss1) survivors |= 2u << j;
+            if (shadow) {
+                const float2 inner = __ffma2_rn(g.r, shrink2, nslack2);
+                const float2 inner_sq = __fmul2_rn(inner, inner);
+                const bool blocks0 = (inner.x > 0.0f) && (h2.x < inner_sq.x) && (front.x > slack) && (tc.x < qy.near_limit);
+                const bool blocks1 = (inner.y > 0.0f) && (h2.y < inner_sq.y) && (front.y > slack) && (tc.y < qy.near_limit);
+                // a pad sphere (r = 0) has inner < 0 and cannot block; a non-candidate of a patch tile that "blocks" is
+                // impossible as well: the patch certificate proved that none of the tile's rays can reach it
+                blocked = blocked || blocks0 || blocks1;
+            }
+        }
+        survivors &= candidates;
+        if (!usable) survivors = candidates;
+        if (shadow && usable && blocked) survivors = 0;
+        if (exact_tests) *exact_tests += (unsigned int)__popc(survivors);
+        // pass 2 (double, exact): each lane walks its own survivors in index order
+        if (TRT_UNLIKELY(survivors != 0)) {
+            // out of line: three unrolled queries would each carry a copy of the exact test, and the kernel's hot code
+            // has to fit the instruction cache (no_instruction was 20 % of the stall samples with the copies inline)
+            const ClosestHit h = walk_survivors<false>(P.sphere_geom, P.sphere_orig, survivors, 0, o, d, ClosestHit{closest, t_hit, obj, index, best_oi});
+            closest = h.closest;
+            t_hit = h.t_hit;
+            obj = h.obj;
+            index = h.index;
+            best_oi = h.best_oi;
+        }
+    }
+    blocked = blocked && usable && shadow;
+    finish_query(qy, o, num_g, blocked, closest, obj, t_hit);
+    return blocked;
+}
+
+// Pass 1 of BOTH shadow queries of a record in one loop (small scenes with 1 + 1 lights): the two rays leave the same point, so a
+// pair's records are loaded once and its centre offsets formed once; the two classifications are independent chains that
+// interleave, and the loop overhead is paid once.  Per ray exactly the operations of query_certified's own pass 1 (same rounding,
+// same comparisons): the results are the ones the separate loops would give.  Candidates: the union of the two queries' candidate
+// masks; each query keeps its own afterwards (query_certified<.., PRE>).  (The bounce ray in the same loop as well — it needs the
+// reflected direction before the shadow queries — was measured: 23.2 vs 22.8 ms.)
 __device__ __forceinline__ void classify_two_shadows(const float4 *s_pairs, const Query &qa, const Query &qb, unsigned int candidates,
                                                      Classified &ca, Classified &cb)
 {
@@ -682,6 +803,11 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
         if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= num_tiles) break;
+#if TRT_TILES_BOTTOM_UP
+        // bottom rows first: ground and reflections are the expensive tiles, sky rows the cheap ones — the persistent kernel's
+        // tail (warps waiting for the last tiles) is then made of cheap tiles
+        tile = num_tiles - 1u - tile;
+#endif
         const int ty = (int)(tile / (unsigned)tiles_x), tx = (int)(tile % (unsigned)tiles_x);
         const int col = tx * TILE_W + (lane & (TILE_W - 1));
         const int brow = ty * TILE_H + (lane >> 3); // band-local row
@@ -700,6 +826,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
         if (PREPASS) {
             // the tile's certificates were taken by k_tile_certs (same functions, same inputs, one thread per tile): the
             // per-tile code of this kernel is a 32-byte load instead of 8 KB of instructions that would evict the hot loop
+            TRT_BOUND(tile < num_tiles, 4);
             const uint4 m = __ldg(P.tile_info + 2 * (size_t)tile), f = __ldg(P.tile_info + 2 * (size_t)tile + 1);
             if (lane == 0) {
                 W.tmask[0] = m.x;
@@ -847,6 +974,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                         if (COUNT) atomicAdd(&P.counters[CTR_BOUNCE_HIST0], 1ull);
                         const d3 c = sky_colour(P, s_byte_to_unit, d);
                         if (COUNT && CULL != 0 && sky_certificate_disagrees(d)) tally.add(CTR_CULL_VIOLATIONS);
+                        TRT_BOUND(k >= 0 && k < TRT_RAYS_PER_PIXEL && (size_t)(blockIdx.x * WARPS_PER_CTA + warp + 1) * (3 * TILE_SAMPLES) * sizeof(double) <= P.scratch_bytes, 2);
                         __stcg(&res[0 * TILE_SAMPLES + k * 32 + lane], c.x);
                         __stcg(&res[1 * TILE_SAMPLES + k * 32 + lane], c.y);
                         __stcg(&res[2 * TILE_SAMPLES + k * 32 + lane], c.z);
@@ -858,6 +986,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                 const unsigned int pushers = __ballot_sync(0xffffffffu, hit_surface);
                 if (hit_surface) {
                     const int slot = (a_head + a_count + __popc(pushers & ((1u << lane) - 1u))) & (QCAP - 1);
+                    TRT_BOUND(a_count + __popc(pushers) <= QCAP && slot >= 0 && slot < QCAP, 0);
                     W.a_dx[slot] = d.x; W.a_dy[slot] = d.y; W.a_dz[slot] = d.z;
                     W.a_t[slot] = t_hit;
                     W.a_meta[slot] = (unsigned)lane | ((unsigned)k << 5) | ((unsigned)obj << 13);
@@ -1115,7 +1244,8 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                     if (done) {
                         if (COUNT) atomicAdd(&P.counters[CTR_BOUNCE_HIST0 + bounces], 1ull);
                         sample = sample * ieee_div(1.0, weight_sum);                 // TRT.c:1061
-                        __stcg(&res[0 * TILE_SAMPLES + k * 32 + pix], sample.x);
+                        TRT_BOUND(k >= 0 && k < TRT_RAYS_PER_PIXEL && pix >= 0 && pix < 32, 2);
+                    __stcg(&res[0 * TILE_SAMPLES + k * 32 + pix], sample.x);
                         __stcg(&res[1 * TILE_SAMPLES + k * 32 + pix], sample.y);
                         __stcg(&res[2 * TILE_SAMPLES + k * 32 + pix], sample.z);
                     }
@@ -1123,6 +1253,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                 const unsigned int pushers = __ballot_sync(0xffffffffu, push);
                 if (push) {
                     const int ps = (qhead + qcount + __popc(pushers & ((1u << lane) - 1u))) & (QCAP - 1);
+                    TRT_BOUND(qcount + __popc(pushers) <= QCAP && ps >= 0 && ps < QCAP, 1);
                     W.ox[ps] = o.x; W.oy[ps] = o.y; W.oz[ps] = o.z;
                     W.dx[ps] = d.x; W.dy[ps] = d.y; W.dz[ps] = d.z;
                     W.t[ps] = t_hit;
@@ -1148,6 +1279,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
             average = average * (1.0 / TRT_RAYS_PER_PIXEL);
             if (COUNT && P.row_cost) atomicAdd(&P.row_cost[brow], 50u);
             const size_t pix = (size_t)brow * (size_t)P.width + (size_t)col;
+            TRT_BOUND(brow >= 0 && brow < band_rows && col >= 0 && col < P.width, 3);
             if (P.pixels) {
                 P.pixels[pix * 3 + 0] = average.x;
                 P.pixels[pix * 3 + 1] = average.y;
@@ -1177,6 +1309,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
             __syncwarp();
             const size_t row_bytes = (size_t)TRT_CELL_BYTES * (size_t)P.width + 1;
             const int n = cols * TRT_CELL_BYTES + (row_end ? 1 : 0);
+            TRT_BOUND(n > 0 && n <= TILE_W * TRT_CELL_BYTES + 1 && P.row0 + ty * TILE_H + min(TILE_H, band_rows - ty * TILE_H) <= P.row1 && tx * TILE_W + cols <= P.width, 6);
             copy_tile_rows(P.ansi + TRT_HOME_BYTES + (size_t)(P.row0 + ty * TILE_H) * row_bytes + (size_t)(tx * TILE_W) * TRT_CELL_BYTES, row_bytes,
                            stage, n, min(TILE_H, band_rows - ty * TILE_H), lane);
             if (narrow) {
@@ -1203,6 +1336,7 @@ __global__ void __launch_bounds__(128) k_tile_certs(const RenderParams P, uint4 
     const unsigned int tile = blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= (unsigned int)(tiles_x * tiles_y)) return;
     const int ty = (int)(tile / (unsigned)tiles_x), tx = (int)(tile % (unsigned)tiles_x);
+    TRT_BOUND((size_t)(tile + 1) * 2 * sizeof(uint4) <= P.tile_info_bytes && c_scene.num_spheres <= 32, 8);
     const int num_spheres = c_scene.num_spheres;          // <= 32 here
     const trt_cert_camera &cam = c_scene.cam_f;
     float Dx, Dy, Dz, hx, hy;
@@ -1515,6 +1649,21 @@ static void die(cudaError_t e, const char *file, int line)
     }
 }
 #define CK(x) die((x), __FILE__, __LINE__)
+
+// self-checking build: the violation counters of this translation unit (16 words), read and cleared; returns 1 when compiled in
+int render_bounds_read(unsigned int *out16)
+{
+#ifdef TRT_BOUNDS_CHECK
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out16, g_trt_bounds, sizeof(unsigned int) * 16));
+    const unsigned int zero[16] = {0};
+    CK(cudaMemcpyToSymbol(g_trt_bounds, zero, sizeof zero));
+    return 1;
+#else
+    for (int i = 0; i < 16; i++) out16[i] = 0u;
+    return 0;
+#endif
+}
 
 void upload_scene_constants(const DevScene &scene, cudaStream_t stream)
 {

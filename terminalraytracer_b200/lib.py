@@ -68,6 +68,7 @@ SIGNATURES = {
     "trt_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "trt_copy_to_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "trt_synchronize": (C.c_int, []),
+    "trt_debug_bounds": (C.c_int, [C.c_void_p]),
     "trt_last_render_ms": (C.c_float, []),
     "trt_last_encode_ms": (C.c_float, []),
     "trt_measure_fp32_tflops": (C.c_double, []),

@@ -100,14 +100,17 @@ class FramePipeline:
     and stores its bytes directly at their place in the destination stream (trt_render_rows_ansi_device), rank 0's memory
     over NVLink or the shared host buffer over PCIe: one kernel launch per rank and frame, the transfer rides along tile by
     tile.
+    `direct=True` (with peer): K1 writes quantised cells locally and K2 — one launch per band — stores the encoded bytes straight
+    into rank 0's stream through the peer mapping (its bulk copies target the peer address); no copy engine, no K1 epilogue.
     `adapt=True` (with peer or host_stream): the collective that ends a step carries every rank's measured K1 time, and the
     bands of the next step follow from it (sharding.reweight): the picture changes slowly from frame to frame, so after a
     few frames the ranks finish together.  Bands only decide who renders which rows: the stream is byte-identical for any
     split."""
 
     def __init__(self, renderer, width, height, rank=0, world_size=1, row_weights=None, group=None, peer=False, pieces=(0.7, 0.3),
-                 adapt=False, host_stream=None, fused=False, host_sync=None):
+                 adapt=False, host_stream=None, fused=False, host_sync=None, direct=False):
         self.r = renderer
+        self.direct = bool(direct)           # peer: K2 itself stores into rank 0's stream through the peer mapping (no push)
         self.host_sync = host_sync           # SharedHostStream whose arrival flags end a host_stream step (else: a collective)
         self.step_no = 0
         self.level_steps = 0                 # adapt: consecutive steps whose K1 times were level; feedback pauses while it lasts
@@ -120,7 +123,8 @@ class FramePipeline:
         self.async_pieces = self.peer or bool(self.host_stream)
         self.adapt = bool(adapt) and world_size > 1 and self.async_pieces
         self.fused = bool(fused) and self.async_pieces
-        self.piece_fractions = pieces if (self.async_pieces and not self.fused) else 1
+        self.direct = self.direct and self.peer and not self.fused
+        self.piece_fractions = pieces if (self.async_pieces and not self.fused and not self.direct) else 1
         self.weights = None if row_weights is None else [float(x) for x in row_weights]
         if self.adapt and self.weights is None:
             self.weights = [1.0] * height
@@ -199,9 +203,9 @@ class FramePipeline:
         timed = (self.adapt and self._feedback_due_next()) or k1_events is not None
         first = last = None
         remote = self.peer and self.stream is None           # this rank writes into rank 0's memory
-        if remote and self.step_no > 0:
+        if remote and self.step_no > 0 and not self.direct:
             # back-pressure: rank 0 must have taken frame step_no before its bytes are overwritten; fused: the kernel itself
-            # stores there, so it waits; pieces: only the pushes wait (on the copy stream), K1 and K2 run ahead
+            # stores there, so it waits; pieces: only the pushes wait (on the copy stream), K1 and K2 run ahead; direct: K2 waits
             self.r.L.trt_wait_steps(self.peer_base + self.flags_offset + 4 * 40, 1, self.step_no, 0 if self.fused else 1)
         ordered = False
         for i, (r0, r1) in enumerate(self.pieces):
@@ -221,6 +225,12 @@ class FramePipeline:
                 continue
             if self.stream is not None:
                 self.r.encode_rows_quant(q, self.width, r1 - r0, self.stream.data_ptr(), abi.HOME_BYTES + r0 * rb)
+            elif self.direct:
+                # K2's bulk stores (cp.async.bulk shared -> global) go through the peer mapping: the band's bytes cross NVLink
+                # as they are encoded, no copy engine, no second pass over them
+                if self.step_no > 0:
+                    self.r.L.trt_wait_steps(self.peer_base + self.flags_offset + 4 * 40, 1, self.step_no, 0)
+                self.r.encode_rows_quant(q, self.width, r1 - r0, self.peer_base, abi.HOME_BYTES + r0 * rb)
             else:
                 off = (r0 - self.base_row) * rb
                 if self.peer and not ordered:
@@ -254,7 +264,8 @@ class FramePipeline:
                 # completion on the device: this rank's step number lands in rank 0's flag array behind its bytes, rank 0's
                 # stream waits for all of them; no host takes part
                 base = self.stream_ptr if self.stream_ptr else self.peer_base
-                self.r.L.trt_signal_step(base + self.flags_offset + 4 * self.rank, self.step_no, 0 if (self.fused or self.stream is not None) else 1)
+                self.r.L.trt_signal_step(base + self.flags_offset + 4 * self.rank, self.step_no,
+                                         0 if (self.fused or self.direct or self.stream is not None) else 1)
                 if self.rank == 0:
                     self.r.L.trt_wait_steps(self.stream_ptr + self.flags_offset, self.world_size, self.step_no, 0)
                     # (a consumer of the finished frame — a device-to-host copy, a display — is enqueued here, on this stream)

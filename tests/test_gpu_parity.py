@@ -481,13 +481,14 @@ def _peer_worker(rank, world, port, w, h, out_path, mode):
         weights = rd.estimate_row_costs(sc)
         shared = None
         fused = mode.endswith("fused")
+        direct = mode.endswith("direct")
         if mode.startswith("host"):
             shared = pipeline.SharedHostStream(rd, abi.stream_bytes(w, h), rank, world)
             pipe = pipeline.FramePipeline(rd, w, h, rank, world, row_weights=weights, pieces=(0.6, 0.4), adapt=True, host_stream=shared.ptr,
                                           fused=fused)
         else:
             pipe = pipeline.FramePipeline(rd, w, h, rank, world, row_weights=weights, peer=True, pieces=(0.6, 0.4), adapt=(mode != "peer"),
-                                          fused=fused)
+                                          fused=fused, direct=direct)
         seen = set()
         for _ in range(4):                                          # several frames: buffers and events are reused, bands move
             seen.add(tuple(pipe.bands))
@@ -510,7 +511,7 @@ def _peer_worker(rank, world, port, w, h, out_path, mode):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["peer", "peer_adapt", "host", "peer_fused", "host_fused"])
+@pytest.mark.parametrize("mode", ["peer", "peer_adapt", "host", "peer_fused", "host_fused", "peer_direct"])
 def test_gpu_gather_three_ranks(orc, tmp_path, mode):
     """the multi-GPU exchange with three processes — on one device here, one per GPU in bench.py: same code, same bytes.
     peer: every rank writes its encoded pieces into rank 0's stream through a CUDA IPC mapping (trt_push_to_peer);
@@ -709,3 +710,21 @@ def test_gpu_c_host_program_streams_the_oracle_bytes(orc, tmp_path):
         sc = S.SceneData(w, h, sky).set_time(k * (20.0 / n))
         want = U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc))
         assert np.array_equal(got[k * want.size:(k + 1) * want.size], want), k
+
+
+def test_gpu_reference_main_with_the_two_calls_redirected():
+    """The reference's own main() with exactly the edit INTEGRATION.md shows (trt_init for initialize_screenbuffer, trt_upload_skybox
+    after its own load_skybox, trt_project_scene / trt_buffered_draw_screen for the two hot calls; oracle/Makefile `hosts` pipes the
+    reference TU through sed, plus a fixed camera time and a one-frame exit so that it terminates) writes the same bytes to stdout as
+    the unmodified program: 480x280 cells, the reference's own uv_checker skybox through the reference's own loader."""
+    one = os.path.join(U.ROOT, "oracle", "_ref", "trt_ref_oneframe")
+    red = os.path.join(U.ROOT, "oracle", "_ref", "trt_ref_redirected")
+    if not (os.path.exists(one) and os.path.exists(red) and os.path.isdir(os.path.join(U.ROOT, "skybox", "uv_checker"))):
+        pytest.skip("oracle/_ref one-frame hosts or skybox/uv_checker not shipped (built where /root/reference exists)")
+    for t in ("3.7", "0.0"):
+        env = dict(os.environ, TRT_SKYBOX="uv_checker", TRT_T=t)
+        want = _cc([one], cwd=U.ROOT, env=env)
+        got = _cc([red], cwd=U.ROOT, env=env)
+        assert want.returncode == 0 and got.returncode == 0, (want.stderr[-500:], got.stderr[-500:])
+        assert len(want.stdout) == abi.stream_bytes(480, 280)
+        assert got.stdout == want.stdout, t
