@@ -113,8 +113,8 @@ class FramePipeline:
         self.direct = bool(direct)           # peer: K2 itself stores into rank 0's stream through the peer mapping (no push)
         self.host_sync = host_sync           # SharedHostStream whose arrival flags end a host_stream step (else: a collective)
         self.step_no = 0
-        self.level_steps = 0                 # adapt: consecutive steps whose K1 times were level; feedback pauses while it lasts
         self.k1_times = None
+        self.settled = False                 # adapt: the last feedback step saw the slowest rank within 2 % of the mean
         self.width, self.height = width, height
         self.rank, self.world_size, self.group = rank, world_size, group
         self.device = torch.device("cuda", renderer.device)
@@ -246,14 +246,23 @@ class FramePipeline:
             k1_events.append(self.k1_span)
         self.k1_launches += len(self.pieces)
 
+    FEEDBACK_STEPS = 5        # adapt: the first steps of a pipeline exchange their K1 times every step ...
+    FEEDBACK_UNTIL = 16       # ... and go on doing so while the slowest rank is more than 2 % above the mean, at most this long;
+    FEEDBACK_EVERY = 32       # later only every so many steps
+
+    def _feedback_at(self, step):
+        return step <= self.FEEDBACK_STEPS or (not self.settled and step <= self.FEEDBACK_UNTIL) or step % self.FEEDBACK_EVERY == 0
+
     def _feedback_due_next(self):
-        return self.level_steps < 3 or (self.step_no + 1) % 64 == 0
+        return self._feedback_at(self.step_no + 1)
 
     def _feedback_due(self):
-        """adapt: measure and exchange the K1 times on this step?  Every step until the ranks have been level (slowest within
-        rebalance_above of the mean) three steps running, then every 64th step — a slowly changing picture keeps its balance,
-        and a step without feedback needs no host synchronisation at all."""
-        return self.level_steps < 3 or self.step_no % 64 == 0
+        """adapt: measure and exchange the K1 times on this step?  Every one of the first five steps, on while the slowest rank is
+        more than 2 % above the mean (at most 16 steps), then every 32nd — a slowly changing picture keeps its balance, and a step
+        without feedback needs no host synchronisation at all.  (Round 2's first policy, "until the ranks are level within 0.5 % three steps running", never
+        stopped at 8 GPUs — row granularity and timing noise leave 1-1.5 % — and its per-step synchronisation cost 0.25 ms of a
+        3.4 ms step.)"""
+        return self._feedback_at(self.step_no)
 
     def gather(self):
         self.step_no += 1
@@ -293,12 +302,10 @@ class FramePipeline:
             self.k1_times = times.tolist()
             # every rank sees the same numbers and takes the same decision; bands that are already level are left alone
             busy = [t for t in self.k1_times if t > 0]
+            self.settled = bool(busy) and max(busy) * len(busy) <= 1.02 * sum(busy)
             if busy and max(busy) * len(busy) > self.rebalance_above * sum(busy):
-                self.level_steps = 0
                 self.weights = sharding.reweight(self.weights, self.bands, self.k1_times)
                 self._set_bands(sharding.row_bands(self.height, self.world_size, self.weights))
-            else:
-                self.level_steps += 1
             return self.stream
         band = None
         if self.rank != 0:
