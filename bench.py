@@ -509,8 +509,8 @@ def main():
     ap.add_argument("--fused", type=int, default=int(os.environ.get("TRT_BENCH_FUSED", "-1")),
                     help="N > 1, device-resident gather: 1 = K1 stores the encoded tiles straight into rank 0's stream over NVLink (no K2, "
                          "no copies), 0 = K1, K2 and copy-engine pushes piece by piece, 2 = K1 then ONE K2 per band that stores into rank 0's stream "
-                         "through the peer mapping, -1 = by GPU count (measured: pieces win at 2 GPUs, "
-                         "14.8 vs 15.7 ms, the fused kernel at 8, 4.21 vs 4.38 ms)")
+                         "through the peer mapping, -1 = by GPU count (measured, profiles/r02f_*: pieces and direct within 1 %% at 2 and 4 GPUs, "
+                         "12.18 / 12.12 and 6.28 / 6.35 ms; the fused kernel wins at 8, 3.45 vs 3.63 ms)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.width and args.height and (args.width, args.height) != (cfg["width"], cfg["height"]):

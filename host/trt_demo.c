@@ -7,13 +7,17 @@
  *   run  :  host/trt_demo [skybox-name [width height [frames]]]        (cwd must contain skybox/<name>/, TRT.c:403)
  *           host/trt_demo --orbit N [skybox-name [width height]]       N frames of one full camera turn, streamed to
  *                                                                      stdout through trt_render_orbit (BASELINE config 4)
+ *           host/trt_demo --keys [skybox-name [width height]]          camera from the keyboard (the reference README's open
+ *                                                                      TODO): a/d yaw, w/s pitch, +/- distance, q quits
  *
  * `TRT.c` = /root/reference/TerminalRayTracer.c
  */
 #include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <termios.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "trt_b200.h"
 
@@ -62,9 +66,69 @@ static int orbit_mode(int argc, char **argv)
     return 0;
 }
 
+/* camera controls from keyboard input: the terminal in non-canonical, non-blocking mode; every key moves the pose that
+ * trt_pose_camera turns into the camera frame (the reference's own recipe, TRT.c:1327-1336, with the angles from the keys) */
+static int keys_mode(int argc, char **argv)
+{
+    const char *skybox_name = argc > 2 ? argv[2] : "milky_way";
+    const int width = argc > 4 ? atoi(argv[3]) : TRT_DEFAULT_WIDTH, height = argc > 4 ? atoi(argv[4]) : TRT_DEFAULT_HEIGHT;
+    struct termios saved, raw;
+    const int tty = isatty(STDIN_FILENO);
+    if (tty) {
+        tcgetattr(STDIN_FILENO, &saved);
+        raw = saved;
+        raw.c_lflag &= (tcflag_t) ~(ICANON | ECHO);
+        raw.c_cc[VMIN] = 0;
+        raw.c_cc[VTIME] = 0;
+        tcsetattr(STDIN_FILENO, TCSANOW, &raw);
+    }
+    trt_init(0);
+    Skybox skybox;
+    trt_load_skybox(&skybox, (char *)skybox_name);
+    trt_upload_skybox(&skybox);
+    signal(SIGINT, sigint_handler);
+    Sphere spheres[TRT_DEMO_SPHERES];
+    DirectionalLight directional_light;
+    PointLight point_light;
+    Scene scene;
+    scene.skybox = skybox;
+    trt_demo_scene(&scene, spheres, &directional_light, &point_light, width, height);
+    char *stream = (char *)trt_host_alloc_pinned(TRT_STREAM_BYTES(width, height));
+    double pitch = -0.3, yaw = 0.6, radius = 1.99;
+    const double step = 0.05;
+    int quit = 0;
+    while (!quit && !sigint_received) {
+        char key;
+        int got = 0;
+        while (read(STDIN_FILENO, &key, 1) == 1) {
+            got = 1;
+            if (key == 'a') yaw -= step;
+            else if (key == 'd') yaw += step;
+            else if (key == 'w') pitch -= step;
+            else if (key == 's') pitch += step;
+            else if (key == '+' || key == '=') radius = radius > 0.3 ? radius - 0.1 : radius;
+            else if (key == '-') radius += 0.1;
+            else if (key == 'q') quit = 1;
+        }
+        if (!tty && !got) quit = 1;                                /* piped input: leave when it is used up */
+        trt_pose_camera(&scene.camera, pitch, yaw, radius);
+        size_t n = trt_render_ansi(&scene, width, height, stream, TRT_STREAM_BYTES(width, height));
+        fwrite(stream, sizeof(char), n, stdout);
+        fflush(stdout);
+        const struct timespec delay = {.tv_sec = 0, .tv_nsec = FRAME_DURATION_NS};
+        nanosleep(&delay, NULL);
+    }
+    if (tty) tcsetattr(STDIN_FILENO, TCSANOW, &saved);
+    trt_host_free_pinned(stream);
+    trt_free_skybox(&skybox);
+    trt_shutdown();
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     if (argc > 2 && argv[1][0] == '-' && argv[1][1] == '-' && argv[1][2] == 'o') return orbit_mode(argc, argv);
+    if (argc > 1 && argv[1][0] == '-' && argv[1][1] == '-' && argv[1][2] == 'k') return keys_mode(argc, argv);
     const char *skybox_name = argc > 1 ? argv[1] : "milky_way"; /* TRT.c:1244 */
     const int width = argc > 3 ? atoi(argv[2]) : TRT_DEFAULT_WIDTH;
     const int height = argc > 3 ? atoi(argv[3]) : TRT_DEFAULT_HEIGHT;

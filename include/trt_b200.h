@@ -229,6 +229,8 @@ double trt_measure_fp64_tflops(void);
 /* ---- host-side helpers (trt_host.c; no CUDA) -------------------------------------------------- */
 void trt_init_camera(trt_Camera *camera, int width, int height);                     /* TRT.c:299 */
 void trt_orbit_camera(trt_Camera *camera, double t);                                 /* TRT.c:1327-1336 */
+/* the same pose recipe from explicit angles (radians) and distance: keyboard-driven cameras (README TODO of the reference) */
+void trt_pose_camera(trt_Camera *camera, double pitch, double yaw, double radius);
 void trt_subpixel_offsets(double dx[TRT_RAYS_PER_PIXEL], double dy[TRT_RAYS_PER_PIXEL]); /* TRT.c:992-993 */
 void trt_demo_scene(trt_Scene *scene, trt_Sphere spheres[TRT_DEMO_SPHERES], trt_DirectionalLight *dl, trt_PointLight *pl,
                     int width, int height);                                          /* TRT.c:1256-1306 */

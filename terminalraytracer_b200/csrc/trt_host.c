@@ -111,6 +111,25 @@ void trt_orbit_camera(trt_Camera *camera, double t)
     frame_apply(&camera->frame, &spin); /* :1336 */
 }
 
+/* The same recipe with the angles and the distance given instead of derived from the clock: pitch about x, then yaw about y (both in
+ * radians), the camera `radius` away from the scene root — what a keyboard-driven camera needs (the reference README's open TODO
+ * "camera controls from keyboard input"; host/trt_demo.c --keys).  trt_orbit_camera(c, t) == trt_pose_camera(c, 2 pi t * -0.03,
+ * 2 pi t * 0.05, 1.99) bit for bit (tests/test_host.py). */
+void trt_pose_camera(trt_Camera *camera, double pitch, double yaw, double radius)
+{
+    trt_Frame spin, lift;
+    frame_identity(&spin);
+    frame_identity(&lift);
+    frame_identity(&camera->frame);
+    spin_about_x(&spin.basis, pitch);
+    spin_about_y(&spin.basis, yaw);
+    lift.origin.x += 0.0;
+    lift.origin.y += 0.0;
+    lift.origin.z += radius;
+    frame_apply(&camera->frame, &lift);
+    frame_apply(&camera->frame, &spin);
+}
+
 void trt_subpixel_offsets(double dx[TRT_RAYS_PER_PIXEL], double dy[TRT_RAYS_PER_PIXEL])
 {
     for (int k = 0; k < TRT_RAYS_PER_PIXEL; k++)

@@ -75,6 +75,7 @@ SIGNATURES = {
     "trt_measure_fp64_tflops": (C.c_double, []),
     "trt_init_camera": (None, [C.POINTER(abi.Camera), C.c_int, C.c_int]),
     "trt_orbit_camera": (None, [C.POINTER(abi.Camera), C.c_double]),
+    "trt_pose_camera": (None, [C.POINTER(abi.Camera), C.c_double, C.c_double, C.c_double]),
     "trt_subpixel_offsets": (None, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "trt_demo_scene": (None, [C.POINTER(abi.Scene), C.POINTER(abi.Sphere), C.POINTER(abi.DirectionalLight),
                               C.POINTER(abi.PointLight), C.c_int, C.c_int]),

@@ -710,6 +710,17 @@ def test_gpu_c_host_program_streams_the_oracle_bytes(orc, tmp_path):
         sc = S.SceneData(w, h, sky).set_time(k * (20.0 / n))
         want = U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc))
         assert np.array_equal(got[k * want.size:(k + 1) * want.size], want), k
+    # camera from the keyboard (the reference README's TODO): keys piped in, every frame equals the oracle's for the posed camera
+    run = _cc([exe, "--keys", "uv_checker", str(w), str(h)], cwd=U.ROOT, input=b"ddw-")
+    assert run.returncode == 0, run.stderr.decode()[-2000:]
+    got = np.frombuffer(run.stdout, dtype=np.uint8)
+    sc = S.SceneData(w, h, sky)
+    renderer_lib = __import__("terminalraytracer_b200.lib", fromlist=["load"]).load()
+    renderer_lib.trt_pose_camera(C.byref(sc.c.camera), -0.3 - 0.05, (0.6 + 0.05) + 0.05, 1.99 + 0.1)   # the key loop's own additions
+    want = U.oracle_stream(orc, U.cpu_render(orc, "orc_project_scene", sc))
+    assert got.size >= want.size and got.size % want.size == 0
+    for k in range(got.size // want.size):
+        assert np.array_equal(got[k * want.size:(k + 1) * want.size], want), k
 
 
 def test_gpu_reference_main_with_the_two_calls_redirected():

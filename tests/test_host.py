@@ -248,16 +248,16 @@ def test_shared_host_stream_availability_probe():
 
 
 def test_committed_bench_line_has_the_contract_keys():
-    """the JSON line bench.py printed on the B200 (profiles/r01f_bench_n1.json) carries every key of the bench contract"""
+    """the JSON line bench.py printed on the B200 (profiles/r02_bench_n1.json) carries every key of the bench contract"""
     import json
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    with open(os.path.join(root, "profiles", "r01f_bench_n1.json")) as f:
+    with open(os.path.join(root, "profiles", "r02_bench_n1.json")) as f:
         line = json.loads(f.read())
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
                 "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert key in line, key
     assert line["metric"] == "Mrays/s" and line["unit"] == "Mrays/s" and line["higher_is_better"] is True
-    assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["gpu_launches"] == 3 * line["steps"]
+    assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["gpu_launches"] == 4 * line["steps"]      # k_tile_certs, K1, K2, k_stream_frame
     assert "workload" in line["config"] and "model" not in line["config"]
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert key in line["roofline"], key
@@ -298,3 +298,15 @@ def test_reference_arm_never_maps_the_product_library():
             "print('clean')") % U.ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "clean" in r.stdout, r.stderr[-2000:]
+
+
+def test_pose_camera_generalises_the_orbit_recipe(trt):
+    """trt_pose_camera (keyboard-driven cameras) with the reference's angles is the reference's orbit camera, bit for bit"""
+    import math
+    for t in (0.0, 0.5, 3.7, 19.99, 123.456):
+        a, b = abi.Camera(), abi.Camera()
+        trt.trt_init_camera(C.byref(a), 480, 280)
+        trt.trt_init_camera(C.byref(b), 480, 280)
+        trt.trt_orbit_camera(C.byref(a), t)
+        trt.trt_pose_camera(C.byref(b), 2.0 * math.pi * t * -0.03, 2.0 * math.pi * t * 0.05, 1.99)
+        assert bytes(a) == bytes(b), t
