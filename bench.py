@@ -511,6 +511,8 @@ def main():
                          "no copies), 0 = K1, K2 and copy-engine pushes piece by piece, 2 = K1 then ONE K2 per band that stores into rank 0's stream "
                          "through the peer mapping, -1 = by GPU count (measured, profiles/r02f_*: pieces and direct within 1 %% at 2 and 4 GPUs, "
                          "12.18 / 12.12 and 6.28 / 6.35 ms; the fused kernel wins at 8, 3.45 vs 3.63 ms)")
+    ap.add_argument("--pieces", default=os.environ.get("TRT_BENCH_PIECES", "0.7,0.3"),
+                    help="N > 1, pieces and direct gather: the fractions of a rank's band rendered, encoded and sent on their way one after the other")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.width and args.height and (args.width, args.height) != (cfg["width"], cfg["height"]):
@@ -566,7 +568,7 @@ def main():
     # N > 1: every rank pushes its encoded pieces into rank 0's stream over NVLink peer memory while its next piece renders
     # (or, fused: K1 itself stores every finished tile's bytes there);
     # the collective that ends a step carries the ranks' K1 times and the next step's bands follow from them (adapt)
-    pipe = pipeline.FramePipeline(rd, width, height, rank, world, row_weights=weights, peer=world > 1, pieces=(0.7, 0.3), adapt=world > 1, fused=fused, direct=direct)
+    pipe = pipeline.FramePipeline(rd, width, height, rank, world, row_weights=weights, peer=world > 1, pieces=tuple(float(x) for x in args.pieces.split(",")), adapt=world > 1, fused=fused, direct=direct)
     stream = torch.cuda.current_stream()
 
     peaks = rd.measure_peaks() if rank == 0 else None
@@ -761,10 +763,13 @@ def main():
                             ("FramePipeline(host_stream=shared pinned buffer).render: every rank copies its bands to the host over its own PCIe link"
                              if shared is not None else "FramePipeline.render + D2H of the gathered stream on rank 0 (no room in /dev/shm)")},
             # per piece on every rank: k_tile_certs (small scenes) + K1 (+ K2 unless fused), plus rank 0's trt_stream_frame_device once per step
-            "gpu_launches": int(((1 if (world > 1 and fused) else 2) + (1 if cfg["kind"] == "demo" else 0)) * k1_launches_all + args.steps),
+            # N > 1 adds the one-thread flag kernels of the device-side step completion: every rank's k_signal, rank 0's k_wait_flags +
+            # k_signal ("consumed"), and the other ranks' k_wait_flags in front of their first write of the next frame
+            "gpu_launches": int(((1 if (world > 1 and fused) else 2) + (1 if cfg["kind"] == "demo" else 0)) * k1_launches_all + args.steps
+                                + ((2 * world + 1) * args.steps if world > 1 else 0)),
             "gather": None if world == 1 else ("fused: K1 stores encoded tiles into rank 0's stream (NVLink peer memory)" if fused else
-                                               ("direct: K1, then K2 stores the band's bytes into rank 0's stream (NVLink peer memory)" if direct else
-                                                "pieces: K1, K2, copy-engine push per piece (NVLink peer memory)")),
+                                               ("direct: K1, then K2 stores the piece's bytes into rank 0's stream (NVLink peer memory), pieces " + args.pieces if direct else
+                                                "pieces: K1, K2, copy-engine push per piece (NVLink peer memory), pieces " + args.pieces)),
             "stream_identical_to_single_gpu": stream_ok,
             "host_stream_identical_to_single_gpu": host_ok,
             "bands": None if world == 1 else {"rows": final_bands, "k1_ms_max_rank": k1_ms_max, "k1_ms_mean_rank": k1_ms_mean,

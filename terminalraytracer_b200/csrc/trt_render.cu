@@ -109,6 +109,19 @@ constexpr size_t SMEM_PAIRS_OFFSET = 256 * sizeof(double);
 constexpr int SMEM_PAIRS = TRT_CLUSTER_MIN_SPHERES / 2 + 1;
 constexpr size_t SMEM_TABLE_BYTES = SMEM_PAIRS_OFFSET + ((SMEM_PAIRS * sizeof(CullPair) + 127) & ~(size_t)127);
 constexpr size_t SMEM_BYTES = SMEM_TABLE_BYTES + WARPS_PER_CTA * sizeof(WarpShared);
+// Many-sphere flavours (CULL == 2) add a per-warp scratch behind the rings (classify_chunk): the float records of the current
+// query's rays, the work list of the chunk being classified and the survivor words.  The other flavours' layout does not change.
+struct ClusterScratch {
+    float4 ray[32][2];            // per ray (lane): (ox, oy, oz, slack), (dx, dy, dz, far limit)
+    float near_limit[32];
+    unsigned int surv[32];        // per ray: spheres of the current chunk its certificate could not rule out
+    unsigned int blk[32];         // per ray: a sphere of the current chunk certainly blocks the light
+    unsigned char item[128];      // work list of the current chunk: ray << 2 | group of 8
+};
+constexpr size_t SMEM_BYTES_CLUSTERED = SMEM_BYTES + WARPS_PER_CTA * sizeof(ClusterScratch);
+template <int CULL> constexpr size_t smem_bytes_of() { return CULL == 2 ? SMEM_BYTES_CLUSTERED : SMEM_BYTES; }
+static_assert(SMEM_BYTES % 16 == 0, "the clustered scratch starts 16-byte aligned");
+static_assert(TRT_MIN_CTAS_PER_SM * (SMEM_BYTES_CLUSTERED + 1024) <= 228 * 1024, "the resident CTAs' shared memory (plus 1 KB each the system reserves) must fit an SM's 228 KB");
 
 // (cx,cy,cz,r*r) of sphere i through the read-only path
 __device__ __forceinline__ double4 ldg4(const double4 *geom, int i)
@@ -372,6 +385,79 @@ __device__ __forceinline__ void finish_query(const Query &qy, const d3 &o, doubl
     }
 }
 
+// One chunk of a many-sphere query, float classification (pass 1) with the WORK compacted across the warp.  With lane = ray and a loop
+// over the chunk's pairs the warp classified the UNION of what its rays could reach: ncu showed 101 pair trips per warp and query where
+// one ray needs about 30 — bounce and shadow rays of a warp diverge — and that loop was 56 % of the kernel's instructions.  Here every
+// (ray, group of 8 spheres the ray's certificate could not skip) is one work item, items are dealt to QUADS of lanes (lane = one pair of
+// the group's spheres, packed FP32 as before: the 4 pair records are one 128-byte line), and only the items that exist are processed: a
+// round of the loop classifies eight items, 64 spheres.  A ray's float record is read from shared memory (written once per query), the few spheres it cannot rule out are
+// OR-ed into its survivor word there.  The arithmetic per (ray, sphere) is trt_cert_sphere's.
+// `groups`: bit g set = this lane's ray needs group g of the chunk.  Returns (the lane's survivor mask, a sphere certainly blocks its light).
+static __device__ __noinline__ uint2 classify_chunk(const CullPair *__restrict__ cull_pairs, ClusterScratch *cs, int base, int cnt, unsigned int groups,
+                                                   bool shadow, const unsigned int lanes)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned int below = lanes & ((1u << lane) - 1u);
+    const int my_rank = __popc(below), n_act = __popc(lanes);
+    // the work list: items ordered by group, then by ray
+    int total = 0;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const bool mine = (groups >> g) & 1u;
+        const unsigned int b = __ballot_sync(lanes, mine);
+        if (mine) cs->item[total + __popc(b & below)] = (unsigned char)((lane << 2) | g);
+        total += __popc(b);
+    }
+    cs->surv[lane] = 0u;
+    cs->blk[lane] = 0u;
+    __syncwarp(lanes);
+    // the lanes of a QUAD share an item, each takes one pair of its 8 spheres (the 4 pair records are one 128-byte line); with
+    // fewer than 4 active lanes one "quad" of n_act lanes takes the pairs in turns
+    const int width = min(4, n_act), quads = n_act / width;
+    const int quad = my_rank / width, first = my_rank - quad * width;
+    const float2 neg1 = make_float2(-1.0f, -1.0f), shrink2 = make_float2(0.99999237060546875f, 0.99999237060546875f);
+    if (quad < quads) {
+        for (int it = quad; it < total; it += quads) {
+            const unsigned int item = cs->item[it];
+            const int r = (int)(item >> 2), g = (int)(item & 3u);
+            const float4 ro = cs->ray[r][0], rd = cs->ray[r][1];
+            const float slack = ro.w, far_limit = rd.w;
+            const float2 nox = make_float2(-ro.x, -ro.x), noy = make_float2(-ro.y, -ro.y), noz = make_float2(-ro.z, -ro.z);
+            const float2 dx = make_float2(rd.x, rd.x), dy = make_float2(rd.y, rd.y), dz = make_float2(rd.z, rd.z);
+            const float2 slack2 = make_float2(slack, slack);
+            for (int pp = first; pp < 4; pp += width) {
+                const int j = 8 * g + 2 * pp;               // spheres base + j and base + j + 1
+                if (j >= cnt) break;                         // (the scene's last chunk may be short; an odd count ends in a pad record)
+                const CullPair sp = ldg_pair(cull_pairs, (base + j) >> 1);
+                // the arithmetic of trt_cert_sphere2 (same operations, same rounding) on float pairs
+                const float2 ocx = __fadd2_rn(sp.cx, nox), ocy = __fadd2_rn(sp.cy, noy), ocz = __fadd2_rn(sp.cz, noz);
+                const float2 tc = __ffma2_rn(ocz, dz, __ffma2_rn(ocy, dy, __fmul2_rn(ocx, dx)));
+                const float2 ntc = __fmul2_rn(tc, neg1);
+                const float2 wx = __ffma2_rn(ntc, dx, ocx), wy = __ffma2_rn(ntc, dy, ocy), wz = __ffma2_rn(ntc, dz, ocz);
+                const float2 h2 = __ffma2_rn(wz, wz, __ffma2_rn(wy, wy, __fmul2_rn(wx, wx)));
+                const float2 outer = __fadd2_rn(sp.r, slack2);
+                const float2 outer_sq = __fmul2_rn(outer, outer);
+                const float2 front = __ffma2_rn(sp.r, neg1, tc);
+                const bool miss0 = (h2.x > outer_sq.x) || (tc.x < -slack) || (front.x > far_limit);
+                const bool miss1 = (h2.y > outer_sq.y) || (tc.y < -slack) || (front.y > far_limit);
+                const unsigned int keep = (miss0 ? 0u : 1u) | (miss1 ? 0u : 2u);
+                if (keep) atomicOr(&cs->surv[r], keep << j);
+                if (shadow) {
+                    const float near_limit = cs->near_limit[r];
+                    const float2 inner = __ffma2_rn(sp.r, shrink2, make_float2(-slack, -slack));
+                    const float2 inner_sq = __fmul2_rn(inner, inner);
+                    const bool blocks0 = (inner.x > 0.0f) && (h2.x < inner_sq.x) && (front.x > slack) && (tc.x < near_limit);
+                    const bool blocks1 = (inner.y > 0.0f) && (h2.y < inner_sq.y) && (front.y > slack) && (tc.y < near_limit);
+                    // (a pad sphere, r = 0, has inner < 0 and cannot block)
+                    if (blocks0 || blocks1) cs->blk[r] = 1u;
+                }
+            }
+        }
+    }
+    __syncwarp(lanes);
+    return make_uint2(cs->surv[lane], cs->blk[lane]);
+}
+
 // Many-sphere scenes (CULL == 2): the spheres are in k-d order, every 32 consecutive ones — one chunk of this loop — under a bounding
 // ball and every 8 under a ball inside it (trt_cert_cluster_miss).  The WARP walks the chunks together: record addresses stay
 // warp-uniform (one transaction per load), a chunk no lane's ray can reach is skipped by all, and every lane drops what its own ray
@@ -379,16 +465,12 @@ __device__ __forceinline__ void finish_query(const Query &qy, const d3 &o, doubl
 // query on the CPU model instead of 32 + 64 balls and ~60 spheres — was measured twice: 61.7 ms with the leaf work inside the walk
 // loop, 68.4 ms as a while-while traversal, against 60.4 ms for this form at 1920x1080: every lane then loads its own nodes and
 // records, 32 transactions per load instead of one.)
-__device__ __forceinline__ bool query_clustered(const RenderParams &P, const Query &qy, const d3 &o, double num_g, int &obj, int &index, double &t_hit,
-                                                unsigned int *exact_tests)
+__device__ __forceinline__ bool query_clustered(const RenderParams &P, ClusterScratch *cs, const unsigned int lanes, const Query &qy, const d3 &o, double num_g,
+                                                int &obj, int &index, double &t_hit, unsigned int *exact_tests)
 {
-    constexpr bool CONST_RECORDS = false, PRE = false;
-    const bool use_patch = false;
-    const unsigned int patch_mask = 0u;
-    const float4 *const s_pairs = nullptr;
-    const Classified pre{0u, false};
-    (void)s_pairs; (void)pre; (void)PRE;
-    const Tally<false> no_tally{nullptr};
+    // `lanes`: the lanes that run this query together — named by the caller, not taken from __activemask(): they share the warp's
+    // scratch (classify_chunk), so they must really be here together
+    __syncwarp(lanes);
     const d3 d = qy.d;
     double closest = INFINITY;
     obj = 0;
@@ -396,72 +478,40 @@ __device__ __forceinline__ bool query_clustered(const RenderParams &P, const Que
     t_hit = 0.0;
     const int n = c_scene.num_spheres;
     const bool usable = qy.rf.usable != 0;
-    const bool shadow = qy.mode != Q_CLOSEST;
+    const bool shadow = qy.mode != Q_CLOSEST;        // warp-uniform: a step runs the same query of all its records
     bool blocked = false;
     // the certificate ray in packed form: both halves of every pair carry the same value
     struct { float2 nox, noy, noz, dx, dy, dz; } rp;
     rp.nox = make_float2(-qy.rf.ox, -qy.rf.ox); rp.noy = make_float2(-qy.rf.oy, -qy.rf.oy); rp.noz = make_float2(-qy.rf.oz, -qy.rf.oz);
     rp.dx = make_float2(qy.rf.dx, qy.rf.dx); rp.dy = make_float2(qy.rf.dy, qy.rf.dy); rp.dz = make_float2(qy.rf.dz, qy.rf.dz);
     const float slack = qy.rf.slack_t;
-    const float2 slack2 = make_float2(slack, slack), nslack2 = make_float2(-slack, -slack);
-    const float2 neg1 = make_float2(-1.0f, -1.0f), shrink2 = make_float2(0.99999237060546875f, 0.99999237060546875f);
+    const float2 slack2 = make_float2(slack, slack);
+    const float2 neg1 = make_float2(-1.0f, -1.0f);
     int best_oi = -1;
-    constexpr bool clustered = !CONST_RECORDS;
-    // small scenes (CONST_RECORDS: at most 32 spheres) are a single chunk: the loop and its index arithmetic fold away
-    for (int base = 0; base < (CONST_RECORDS ? 1 : n); base += 32) {
-        const int cnt = CONST_RECORDS ? n : min(32, n - base);
-        // many-sphere scenes: the chunk is a cluster of the k-d order with a bounding ball, and four balls of 8 inside
-        // it (trt_cert_cluster_miss): skip what no lane's ray can reach, and let every lane drop what its own ray cannot
-        bool ball_missed = false;
-        unsigned int reachable = 0xffffffffu;      // warp-uniform: spheres of this chunk some lane may still hit
-        unsigned int own = 0xffffffffu;            // this lane's
-        if (clustered) {
-            const float4 ball = __ldg(&P.clusters[base >> 5]);
-            ball_missed = usable && trt_cert_cluster_miss(&qy.rf, ball.x, ball.y, ball.z, ball.w, qy.far_limit);
-            const unsigned int lanes = __activemask();
-            if (__all_sync(lanes, ball_missed)) continue;
-            reachable = 0u;
-            own = 0u;
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-                const CullPair g = ldg_pair(P.subballs, 2 * (base >> 5) + half);
-                const float2 ocx = __fadd2_rn(g.cx, rp.nox), ocy = __fadd2_rn(g.cy, rp.noy), ocz = __fadd2_rn(g.cz, rp.noz);
-                const float2 tc = __ffma2_rn(ocz, rp.dz, __ffma2_rn(ocy, rp.dy, __fmul2_rn(ocx, rp.dx)));
-                const float2 ntc = __fmul2_rn(tc, neg1);
-                const float2 wx = __ffma2_rn(ntc, rp.dx, ocx), wy = __ffma2_rn(ntc, rp.dy, ocy), wz = __ffma2_rn(ntc, rp.dz, ocz);
-                const float2 h2 = __ffma2_rn(wz, wz, __ffma2_rn(wy, wy, __fmul2_rn(wx, wx)));
-                const float2 outer = __fadd2_rn(g.r, slack2);
-                const float2 outer_sq = __fmul2_rn(outer, outer);
-                const float2 front = __ffma2_rn(g.r, neg1, tc), back = __fadd2_rn(g.r, tc);
-                const bool m0 = usable && !ball_missed && ((h2.x > outer_sq.x) || (back.x < -slack) || (front.x > qy.far_limit));
-                const bool m1 = usable && !ball_missed && ((h2.y > outer_sq.y) || (back.y < -slack) || (front.y > qy.far_limit));
-                const bool keep0 = !m0 && !ball_missed, keep1 = !m1 && !ball_missed;
-                if (keep0) own |= 0xffu << (16 * half);
-                if (keep1) own |= 0xff00u << (16 * half);
-                if (__any_sync(lanes, keep0)) reachable |= 0xffu << (16 * half);
-                if (__any_sync(lanes, keep1)) reachable |= 0xff00u << (16 * half);
-            }
-            if (reachable == 0u) continue;
+    // this ray's float record where the lanes that classify for it find it (classify_chunk)
+    {
+        const int lane = threadIdx.x & 31;
+        cs->ray[lane][0] = make_float4(qy.rf.ox, qy.rf.oy, qy.rf.oz, slack);
+        cs->ray[lane][1] = make_float4(qy.rf.dx, qy.rf.dy, qy.rf.dz, qy.far_limit);
+        cs->near_limit[lane] = qy.near_limit;
+    }
+    for (int base = 0; base < n; base += 32) {
+        const int cnt = min(32, n - base);
+        // the chunk is a cluster of the k-d order with a bounding ball, and four balls of 8 inside it (trt_cert_cluster_miss):
+        // skip what no lane's ray can reach, and let every lane drop what its own ray cannot.  A shadow ray whose answer is known —
+        // certainly blocked, or (directional light: any hit blocks, TRT.c:907-908) an exact hit found — needs nothing more.
+        const bool finished = shadow && usable && (blocked || (qy.mode == Q_DIR && obj != 0));
+        const float4 ball = __ldg(&P.clusters[base >> 5]);
+        const bool ball_missed = finished || (usable && trt_cert_cluster_miss(&qy.rf, ball.x, ball.y, ball.z, ball.w, qy.far_limit));
+        if (__all_sync(lanes, ball_missed)) {
+            // once every lane's answer is known the remaining chunks cannot change anything
+            if (__all_sync(lanes, finished)) break;
+            continue;
         }
-        // pass 1 (float, warp-uniform record addresses): classify the candidate spheres of this chunk — all of them,
-        // or, for the first-generation hits of a patch tile, the few the patch certificate left (use_patch, n <= 32)
-        // (small scenes: the mask of existing spheres is a per-scene constant, host-evaluated)
-        const unsigned int valid = CONST_RECORDS ? c_scene.sphere_mask : (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u));
-        const unsigned int candidates = use_patch ? (patch_mask & valid) : (valid & reachable);
-        unsigned int survivors = PRE ? pre.survivors : 0u;
-        if (PRE) blocked = pre.blocked;
-        // two spheres per trip: the arithmetic of trt_cert_sphere2 (same operations, same rounding) on float pairs
-#pragma unroll 1
-        for (unsigned int m = PRE ? 0u : ((candidates | (candidates >> 1)) & 0x55555555u); m; m &= m - 1) {
-            const int j = __ffs(m) - 1;             // even: spheres base + j and base + j + 1
-            CullPair g;
-            if (CONST_RECORDS) {
-                const float4 lo = s_pairs[j], hi = s_pairs[j + 1];      // pair j / 2 = float4 j and j + 1 (j is even)
-                g.cx = make_float2(lo.x, lo.y); g.cy = make_float2(lo.z, lo.w);
-                g.cz = make_float2(hi.x, hi.y); g.r = make_float2(hi.z, hi.w);
-            } else {
-                g = ldg_pair(P.cull_pairs, (base + j) >> 1);
-            }
+        unsigned int groups = 0u;      // this lane's: groups of 8 its ray may still hit
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const CullPair g = ldg_pair(P.subballs, 2 * (base >> 5) + half);
             const float2 ocx = __fadd2_rn(g.cx, rp.nox), ocy = __fadd2_rn(g.cy, rp.noy), ocz = __fadd2_rn(g.cz, rp.noz);
             const float2 tc = __ffma2_rn(ocz, rp.dz, __ffma2_rn(ocy, rp.dy, __fmul2_rn(ocx, rp.dx)));
             const float2 ntc = __fmul2_rn(tc, neg1);
@@ -469,33 +519,25 @@ __device__ __forceinline__ bool query_clustered(const RenderParams &P, const Que
             const float2 h2 = __ffma2_rn(wz, wz, __ffma2_rn(wy, wy, __fmul2_rn(wx, wx)));
             const float2 outer = __fadd2_rn(g.r, slack2);
             const float2 outer_sq = __fmul2_rn(outer, outer);
-            const float2 front = __ffma2_rn(g.r, neg1, tc);
-            const bool miss0 = (h2.x > outer_sq.x) || (tc.x < -slack) || (front.x > qy.far_limit);
-            const bool miss1 = (h2.y > outer_sq.y) || (tc.y < -slack) || (front.y > qy.far_limit);
-            if (!miss0) survivors |= 1u << j;
-            if (!miss1) survivors |= 2u << j;
-            if (shadow) {
-                const float2 inner = __ffma2_rn(g.r, shrink2, nslack2);
-                const float2 inner_sq = __fmul2_rn(inner, inner);
-                const bool blocks0 = (inner.x > 0.0f) && (h2.x < inner_sq.x) && (front.x > slack) && (tc.x < qy.near_limit);
-                const bool blocks1 = (inner.y > 0.0f) && (h2.y < inner_sq.y) && (front.y > slack) && (tc.y < qy.near_limit);
-                // a pad sphere (r = 0) has inner < 0 and cannot block; a non-candidate of a patch tile that "blocks" is
-                // impossible as well: the patch certificate proved that none of the tile's rays can reach it
-                blocked = blocked || blocks0 || blocks1;
-            }
+            const float2 front = __ffma2_rn(g.r, neg1, tc), back = __fadd2_rn(g.r, tc);
+            const bool m0 = usable && ((h2.x > outer_sq.x) || (back.x < -slack) || (front.x > qy.far_limit));
+            const bool m1 = usable && ((h2.y > outer_sq.y) || (back.y < -slack) || (front.y > qy.far_limit));
+            if (!m0 && !ball_missed) groups |= 1u << (2 * half);
+            if (!m1 && !ball_missed) groups |= 2u << (2 * half);
         }
-        survivors &= candidates;
-        if (!usable) survivors = candidates;
-        survivors &= own;
+        if (__all_sync(lanes, groups == 0u)) continue;
+        // pass 1 (float): the spheres of the groups this ray still needs, classified by whichever lanes are free (classify_chunk);
+        // a ray without a usable certificate keeps everything
+        const unsigned int valid = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+        const uint2 cls = classify_chunk(P.cull_pairs, cs, base, cnt, usable ? groups : 0u, shadow, lanes);
+        unsigned int survivors = cls.x & valid;
+        if (cls.y) blocked = true;
+        if (!usable) survivors = groups ? valid : 0u;
         if (shadow && usable && blocked) survivors = 0;
-        // many-sphere scenes: once every lane's light is proven blocked the remaining chunks cannot change anything
-        if (!CONST_RECORDS && shadow && n > 32 && __all_sync(__activemask(), usable && blocked)) break;
         if (exact_tests) *exact_tests += (unsigned int)__popc(survivors);
-        // pass 2 (double, exact): each lane walks its own survivors in index order
+        // pass 2 (double, exact): each lane walks its own survivors (out of line: the kernel's hot code has to fit the instruction cache)
         if (TRT_UNLIKELY(survivors != 0)) {
-            // out of line: three unrolled queries would each carry a copy of the exact test, and the kernel's hot code
-            // has to fit the instruction cache (no_instruction was 20 % of the stall samples with the copies inline)
-            const ClosestHit h = walk_survivors<clustered>(P.sphere_geom, P.sphere_orig, survivors, base, o, d, ClosestHit{closest, t_hit, obj, index, best_oi});
+            const ClosestHit h = walk_survivors<true>(P.sphere_geom, P.sphere_orig, survivors, base, o, d, ClosestHit{closest, t_hit, obj, index, best_oi});
             closest = h.closest;
             t_hit = h.t_hit;
             obj = h.obj;
@@ -504,21 +546,7 @@ __device__ __forceinline__ bool query_clustered(const RenderParams &P, const Que
         }
     }
     blocked = blocked && usable && shadow;
-    if (qy.mode == Q_CLOSEST) {
-        // (num_g is the reference's own numerator for this origin: only the denominator's sign is left to the float certificate)
-        if (!(usable && trt_cert_plane_miss_num(&qy.rf, num_g, c_scene.ground_normal_f[0], c_scene.ground_normal_f[1], c_scene.ground_normal_f[2])))
-            plane_exact_num<false>(num_g, o, d, closest, obj, t_hit, no_tally);
-    } else if (qy.mode == Q_DIR) {
-        // any hit blocks.  The ground (TRT.c:677-695): numerator and denominator are the reference's own doubles
-        // (the denominator is a per-light constant); opposite signs or a zero numerator give t <= 0, a miss,
-        // without the division.
-        if (TRT_UNLIKELY(!blocked && obj == 0 && fabs(qy.plane_denom) > 0.00001 && num_g != 0.0 && ((num_g < 0.0) == (qy.plane_denom < 0.0)))) {
-            const double t = ieee_div(num_g, qy.plane_denom);
-            if (t > 0.00001) obj = 2;
-        }
-    } else {
-        if (TRT_UNLIKELY(!blocked && qy.ground_candidate)) plane_exact_num<false>(num_g, o, d, closest, obj, t_hit, no_tally);
-    }
+    finish_query(qy, o, num_g, blocked, closest, obj, t_hit);
     return blocked;
 }
 
@@ -527,10 +555,10 @@ __device__ __forceinline__ bool query_clustered(const RenderParams &P, const Que
 template <bool CONST_RECORDS, bool PRE = false>
 __device__ __forceinline__ bool query_certified(const RenderParams &P, const float4 *s_pairs, const Query &qy, const d3 &o, double num_g, bool use_patch,
                                                 unsigned int patch_mask, int &obj, int &index, double &t_hit, unsigned int *exact_tests,
-                                                const Classified pre = Classified{0u, false})
+                                                const Classified pre = Classified{0u, false}, ClusterScratch *cs = nullptr, unsigned int lanes = 0u)
 {
     static_assert(!PRE || CONST_RECORDS, "a precomputed classification covers the single chunk of a small scene");
-    if (!CONST_RECORDS) return query_clustered(P, qy, o, num_g, obj, index, t_hit, exact_tests);
+    if (!CONST_RECORDS) return query_clustered(P, cs, lanes, qy, o, num_g, obj, index, t_hit, exact_tests);
     const d3 d = qy.d;
     double closest = INFINITY;
     obj = 0;
@@ -775,6 +803,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     WarpShared &W = reinterpret_cast<WarpShared *>(smem_raw + SMEM_TABLE_BYTES)[warp];
+    ClusterScratch *const cs = CULL == 2 ? reinterpret_cast<ClusterScratch *>(smem_raw + SMEM_BYTES) + warp : nullptr;
     if (P.ansi) stage_fill(reinterpret_cast<unsigned char *>(W.ansi_stage), lane);
     // finished samples of the current tile, [channel][k * 32 + pixel lane]: written once, read once at the end of
     // the tile by the pixel's lane -> parked in an L2-resident per-warp slice of global memory, not in shared memory
@@ -1138,6 +1167,9 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                         int obj2 = 0, index2 = -1;
                         double t2 = 0.0;
                         bool blocked = false;
+                        // many-sphere scenes: the lanes of this step that run the query, named explicitly (they share per-warp scratch)
+                        unsigned int qlanes = 0u;
+                        if (CULL == 2) qlanes = __ballot_sync(n_rec >= 32 ? 0xffffffffu : ((1u << n_rec) - 1u), run);
                         if (run) {
                             if (COUNT || CULL == 0) {
                                 tally.add(CTR_TRACE_CALLS);
@@ -1153,7 +1185,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TRT_MIN_CTAS_PER_SM) k_render(con
                                                                            COUNT ? &exact : nullptr, q == 0 ? pre_dir : pre_point);
                                 else
                                     blocked3 = query_certified<CULL == 1>(P, s_pairs, qy, at, num_g, use_patch, use_patch ? W.pmask[q] : 0u, obj3, index3, t3,
-                                                                          COUNT ? &exact : nullptr);
+                                                                          COUNT ? &exact : nullptr, Classified{0u, false}, cs, qlanes);
                                 if (COUNT) {
                                     // the audit: both paths must lead to the same decision / the same hit
                                     tally.add(CTR_EXACT_SPHERE_TESTS, exact);
@@ -1391,10 +1423,12 @@ __global__ void __launch_bounds__(128) k_tile_certs(const RenderParams P, uint4 
 // out: 11 doubles per ray = kind, point[3], normal[3], colour[3], reflectivity
 __global__ void k_probe_trace(const RenderParams P, const double *__restrict__ rays, int n, double *__restrict__ out)
 {
+    __shared__ ClusterScratch s_cs[4];           // (128 threads per CTA)
     __shared__ double s_byte_to_unit[256];
     for (int k = threadIdx.x; k < 256; k += blockDim.x) s_byte_to_unit[k] = P.byte_to_unit[k];
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int probe_lanes = __ballot_sync(0xffffffffu, i < n);   // the lanes that run a query together (query_clustered)
     if (i >= n) return;
     const d3 o = mk3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]);
     const d3 d = mk3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
@@ -1405,7 +1439,7 @@ __global__ void k_probe_trace(const RenderParams P, const double *__restrict__ r
         Query qy;
         setup_closest_query(qy, o, d, fabsf((float)o.x) + fabsf((float)o.y) + fabsf((float)o.z) + c_scene.filter_centre_l1);
         if (!c_scene.clustered) query_certified<true>(P, reinterpret_cast<const float4 *>(P.cull_pairs), qy, o, plane_numerator(o), false, 0u, obj, index, t_hit, nullptr);
-        else query_certified<false>(P, nullptr, qy, o, plane_numerator(o), false, 0u, obj, index, t_hit, nullptr);
+        else query_certified<false>(P, nullptr, qy, o, plane_numerator(o), false, 0u, obj, index, t_hit, nullptr, Classified{0u, false}, &s_cs[threadIdx.x >> 5], probe_lanes);
     } else {
         query_reference<false>(P, o, d, obj, index, t_hit, tally);
     }
@@ -1442,6 +1476,7 @@ __global__ void k_probe_trace(const RenderParams P, const double *__restrict__ r
 __global__ void k_probe_sphere(const double *__restrict__ rays, const double *__restrict__ geom, int n, double *__restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int probe_lanes = __ballot_sync(0xffffffffu, i < n);   // the lanes that run a query together (query_clustered)
     if (i >= n) return;
     const d3 o = mk3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]);
     const d3 d = mk3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
@@ -1463,6 +1498,7 @@ __global__ void k_probe_sphere(const double *__restrict__ rays, const double *__
 __global__ void k_probe_plane(const double *__restrict__ rays, int n, double *__restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int probe_lanes = __ballot_sync(0xffffffffu, i < n);   // the lanes that run a query together (query_clustered)
     if (i >= n) return;
     const d3 o = mk3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]);
     const d3 d = mk3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
@@ -1482,7 +1518,9 @@ __global__ void k_probe_plane(const double *__restrict__ rays, int n, double *__
 // (certificate-guided shadow queries when the scene allows them, push_back, unit, the shared-reciprocal division).
 __global__ void k_probe_lighting(const RenderParams P, const double *__restrict__ in, int n, double *__restrict__ out)
 {
+    __shared__ ClusterScratch s_cs[4];           // (128 threads per CTA)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int probe_lanes = __ballot_sync(0xffffffffu, i < n);   // the lanes that run a query together (query_clustered)
     if (i >= n) return;
     const d3 at = mk3(in[i * 9 + 0], in[i * 9 + 1], in[i * 9 + 2]);
     const d3 nrm = mk3(in[i * 9 + 3], in[i * 9 + 4], in[i * 9 + 5]);
@@ -1525,7 +1563,7 @@ __global__ void k_probe_lighting(const RenderParams P, const double *__restrict_
         bool blocked = false;
         if (!cert) query_reference<false>(P, at, qy.d, obj2, index2, t2, no_tally);
         else if (!c_scene.clustered) blocked = query_certified<true>(P, reinterpret_cast<const float4 *>(P.cull_pairs), qy, at, num_g, false, 0u, obj2, index2, t2, nullptr);
-        else blocked = query_certified<false>(P, nullptr, qy, at, num_g, false, 0u, obj2, index2, t2, nullptr);
+        else blocked = query_certified<false>(P, nullptr, qy, at, num_g, false, 0u, obj2, index2, t2, nullptr, Classified{0u, false}, &s_cs[threadIdx.x >> 5], probe_lanes);
         bool open = !blocked && obj2 == 0;
         double f = 1.0;
         const double *lc;
@@ -1674,8 +1712,8 @@ template <bool COUNT, int CULL>
 static void prepare_kernel()
 {
     // dynamic shared memory per CTA (the rings of 4 warps) may exceed the 48 KB default
-    CK(cudaFuncSetAttribute(k_render<COUNT, CULL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    CK(cudaFuncSetAttribute(k_render<COUNT, CULL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_render<COUNT, CULL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_of<CULL>()));
+    CK(cudaFuncSetAttribute(k_render<COUNT, CULL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_of<CULL>()));
 }
 
 int render_ctas_per_sm()
@@ -1724,8 +1762,8 @@ void launch_render(const RenderParams &p, bool count, int cull, bool one_plus_on
     // 12 flavours: counting or not, certificates off / small scene / clustered scene, generic lights or exactly 1 + 1
 #define TRT_LAUNCH(COUNT, CULL) \
     do { \
-        if (one_plus_one) k_render<COUNT, CULL, 1><<<g, b, SMEM_BYTES, stream>>>(p); \
-        else k_render<COUNT, CULL, 0><<<g, b, SMEM_BYTES, stream>>>(p); \
+        if (one_plus_one) k_render<COUNT, CULL, 1><<<g, b, smem_bytes_of<CULL>(), stream>>>(p); \
+        else k_render<COUNT, CULL, 0><<<g, b, smem_bytes_of<CULL>(), stream>>>(p); \
     } while (0)
     if (count) {
         if (cull == 1) TRT_LAUNCH(true, 1);

@@ -100,8 +100,9 @@ class FramePipeline:
     and stores its bytes directly at their place in the destination stream (trt_render_rows_ansi_device), rank 0's memory
     over NVLink or the shared host buffer over PCIe: one kernel launch per rank and frame, the transfer rides along tile by
     tile.
-    `direct=True` (with peer): K1 writes quantised cells locally and K2 — one launch per band — stores the encoded bytes straight
-    into rank 0's stream through the peer mapping (its bulk copies target the peer address); no copy engine, no K1 epilogue.
+    `direct=True` (with peer): K1 writes quantised cells locally and K2 — one launch per piece of the band — stores the encoded
+    bytes straight into rank 0's stream through the peer mapping (its bulk copies target the peer address); no copy engine, no K1
+    epilogue.
     `adapt=True` (with peer or host_stream): the collective that ends a step carries every rank's measured K1 time, and the
     bands of the next step follow from it (sharding.reweight): the picture changes slowly from frame to frame, so after a
     few frames the ranks finish together.  Bands only decide who renders which rows: the stream is byte-identical for any
@@ -124,7 +125,7 @@ class FramePipeline:
         self.adapt = bool(adapt) and world_size > 1 and self.async_pieces
         self.fused = bool(fused) and self.async_pieces
         self.direct = self.direct and self.peer and not self.fused
-        self.piece_fractions = pieces if (self.async_pieces and not self.fused and not self.direct) else 1
+        self.piece_fractions = pieces if (self.async_pieces and not self.fused) else 1
         self.weights = None if row_weights is None else [float(x) for x in row_weights]
         if self.adapt and self.weights is None:
             self.weights = [1.0] * height
@@ -228,7 +229,9 @@ class FramePipeline:
             elif self.direct:
                 # K2's bulk stores (cp.async.bulk shared -> global) go through the peer mapping: the band's bytes cross NVLink
                 # as they are encoded, no copy engine, no second pass over them
-                if self.step_no > 0:
+                # (piece by piece: the first pieces cross while the next one renders; all ranks' last pieces arrive at rank 0
+                # together, so the exposed part is the LAST piece's share of the frame over rank 0's NVLink ingest rate)
+                if self.step_no > 0 and i == 0:
                     self.r.L.trt_wait_steps(self.peer_base + self.flags_offset + 4 * 40, 1, self.step_no, 0)
                 self.r.encode_rows_quant(q, self.width, r1 - r0, self.peer_base, abi.HOME_BYTES + r0 * rb)
             else:
