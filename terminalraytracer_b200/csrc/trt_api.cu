@@ -334,7 +334,7 @@ void upload_scene(const trt_Scene *scene, bool wait = true)
     std::vector<int> orig((size_t)(n > 0 ? n : 1)), pos((size_t)(n > 0 ? n : 1));
     for (int i = 0; i < n; i++) orig[i] = pos[i] = i;
     const int num_clusters = (n + 31) / 32;
-    std::vector<float4> clusters((size_t)(num_clusters > 0 ? num_clusters : 1), make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<float4> clusters((size_t)(num_clusters > 0 ? num_clusters : 1) + 1, make_float4(0.f, 0.f, 0.f, 0.f));   // (+1: read in pairs)
     std::vector<CullPair> subballs((size_t)(num_clusters > 0 ? 2 * num_clusters : 2));
     memset(subballs.data(), 0, sizeof(CullPair) * subballs.size());
     s.clustered = n > TRT_CLUSTER_MIN_SPHERES ? 1 : 0;

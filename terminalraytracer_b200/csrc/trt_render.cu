@@ -413,8 +413,9 @@ static __device__ __noinline__ uint2 classify_chunk(const CullPair *__restrict__
     __syncwarp(lanes);
     // the lanes of a QUAD share an item, each takes one pair of its 8 spheres (the 4 pair records are one 128-byte line); with
     // fewer than 4 active lanes one "quad" of n_act lanes takes the pairs in turns
-    const int width = min(4, n_act), quads = n_act / width;
-    const int quad = my_rank / width, first = my_rank - quad * width;
+    const bool full = n_act >= 4;
+    const int width = full ? 4 : n_act, quads = full ? n_act >> 2 : 1;
+    const int quad = full ? my_rank >> 2 : 0, first = full ? my_rank & 3 : my_rank;
     const float2 neg1 = make_float2(-1.0f, -1.0f), shrink2 = make_float2(0.99999237060546875f, 0.99999237060546875f);
     if (quad < quads) {
         for (int it = quad; it < total; it += quads) {
@@ -495,17 +496,43 @@ __device__ __forceinline__ bool query_clustered(const RenderParams &P, ClusterSc
         cs->ray[lane][1] = make_float4(qy.rf.dx, qy.rf.dy, qy.rf.dz, qy.far_limit);
         cs->near_limit[lane] = qy.near_limit;
     }
-    for (int base = 0; base < n; base += 32) {
+    const int nchunks = (n + 31) >> 5;
+    const float2 far2 = make_float2(qy.far_limit, qy.far_limit);
+    bool all_finished = false;
+    for (int c0 = 0; c0 < nchunks && !all_finished; c0 += 2) {
+        // two chunk balls per trip (trt_cert_cluster_miss's arithmetic on float pairs; the array ends in a spare record)
+        bool miss0, miss1;
+        {
+            const float4 b0 = __ldg(&P.clusters[c0]), b1 = __ldg(&P.clusters[c0 + 1]);
+            const float2 R = make_float2(b0.w, b1.w);
+            const float2 ocx = __fadd2_rn(make_float2(b0.x, b1.x), rp.nox), ocy = __fadd2_rn(make_float2(b0.y, b1.y), rp.noy),
+                         ocz = __fadd2_rn(make_float2(b0.z, b1.z), rp.noz);
+            const float2 tc = __ffma2_rn(ocz, rp.dz, __ffma2_rn(ocy, rp.dy, __fmul2_rn(ocx, rp.dx)));
+            const float2 ntc = __fmul2_rn(tc, neg1);
+            const float2 wx = __ffma2_rn(ntc, rp.dx, ocx), wy = __ffma2_rn(ntc, rp.dy, ocy), wz = __ffma2_rn(ntc, rp.dz, ocz);
+            const float2 h2 = __ffma2_rn(wz, wz, __ffma2_rn(wy, wy, __fmul2_rn(wx, wx)));
+            const float2 outer = __fadd2_rn(R, slack2);
+            const float2 outer_sq = __fmul2_rn(outer, outer);
+            const float2 back = __fadd2_rn(tc, R), front = __ffma2_rn(R, neg1, tc);
+            miss0 = (h2.x > outer_sq.x) || (back.x < -slack) || (front.x > far2.x);
+            miss1 = (h2.y > outer_sq.y) || (back.y < -slack) || (front.y > far2.y);
+        }
+#pragma unroll 1
+        for (int half_c = 0; half_c < 2; half_c++) {
+        if (c0 + half_c >= nchunks) break;
+        const int base = (c0 + half_c) << 5;
         const int cnt = min(32, n - base);
-        // the chunk is a cluster of the k-d order with a bounding ball, and four balls of 8 inside it (trt_cert_cluster_miss):
-        // skip what no lane's ray can reach, and let every lane drop what its own ray cannot.  A shadow ray whose answer is known —
-        // certainly blocked, or (directional light: any hit blocks, TRT.c:907-908) an exact hit found — needs nothing more.
+        // the chunk is a cluster of the k-d order with a bounding ball, and four balls of 8 inside it: skip what no lane's ray can
+        // reach, and let every lane drop what its own ray cannot.  A shadow ray whose answer is known — certainly blocked, or
+        // (directional light: any hit blocks, TRT.c:907-908) an exact hit found — needs nothing more.
         const bool finished = shadow && usable && (blocked || (qy.mode == Q_DIR && obj != 0));
-        const float4 ball = __ldg(&P.clusters[base >> 5]);
-        const bool ball_missed = finished || (usable && trt_cert_cluster_miss(&qy.rf, ball.x, ball.y, ball.z, ball.w, qy.far_limit));
+        const bool ball_missed = finished || (usable && (half_c ? miss1 : miss0));
         if (__all_sync(lanes, ball_missed)) {
             // once every lane's answer is known the remaining chunks cannot change anything
-            if (__all_sync(lanes, finished)) break;
+            if (__all_sync(lanes, finished)) {
+                all_finished = true;
+                break;
+            }
             continue;
         }
         unsigned int groups = 0u;      // this lane's: groups of 8 its ray may still hit
@@ -543,6 +570,7 @@ __device__ __forceinline__ bool query_clustered(const RenderParams &P, ClusterSc
             obj = h.obj;
             index = h.index;
             best_oi = h.best_oi;
+        }
         }
     }
     blocked = blocked && usable && shadow;
