@@ -26,8 +26,9 @@
 //     hits have their own ring because a tile's ground hits share tile-level ("patch") certificates;
 //   * finished samples are parked in an L2-resident per-warp slice of global memory and summed per pixel in sample
 //     order at the end of the tile (TRT.c:1063 adds them in that order; floating-point addition is not associative);
-//   * scenes of more than 64 spheres are ordered along a k-d tree with bounding balls per 32 and per 8 spheres
-//     (CULL == 2): whole chunks of the query loop are skipped when no lane's ray can reach their ball.
+//   * scenes of more than 32 spheres are ordered along a k-d tree with bounding balls per 32 and per 8 spheres
+//     (CULL == 2): whole chunks of the query loop are skipped when no lane's ray can reach their ball, and inside a
+//     chunk the float classification is dealt across the warp per (ray, group of 8) — query_clustered, classify_chunk.
 // Compared with one-ray-per-trip state machines, no lane ever executes another lane's phase under predication:
 // the rings keep full warps of like work together however the bounce counts diverge.  DESIGN.md 4.2 has the
 // measurements and the list of variants that were tried.
@@ -460,12 +461,11 @@ static __device__ __noinline__ uint2 classify_chunk(const CullPair *__restrict__
 }
 
 // Many-sphere scenes (CULL == 2): the spheres are in k-d order, every 32 consecutive ones — one chunk of this loop — under a bounding
-// ball and every 8 under a ball inside it (trt_cert_cluster_miss).  The WARP walks the chunks together: record addresses stay
-// warp-uniform (one transaction per load), a chunk no lane's ray can reach is skipped by all, and every lane drops what its own ray
-// cannot reach.  (A per-lane stackless walk of a bounding-ball tree over the same order, leaves of 8 — 50 ball tests and 7 leaves per
-// query on the CPU model instead of 32 + 64 balls and ~60 spheres — was measured twice: 61.7 ms with the leaf work inside the walk
-// loop, 68.4 ms as a while-while traversal, against 60.4 ms for this form at 1920x1080: every lane then loads its own nodes and
-// records, 32 transactions per load instead of one.)
+// ball and every 8 under a ball inside it (trt_cert_cluster_miss).  The WARP walks the chunks together (ball records at warp-uniform
+// addresses, two chunk balls per trip): a chunk no lane's ray can reach is skipped by all, every lane tests the chunk's four group
+// balls for its own ray, and the spheres of the groups it still needs are classified by classify_chunk — per ray, dealt across the
+// warp.  (A per-lane stackless walk of a bounding-ball tree over the same order, chunks taken nearest first with a shrinking reach,
+// and a lane = sphere form were measured and lost; DESIGN.md 4.4 has the numbers.)
 __device__ __forceinline__ bool query_clustered(const RenderParams &P, ClusterScratch *cs, const unsigned int lanes, const Query &qy, const d3 &o, double num_g,
                                                 int &obj, int &index, double &t_hit, unsigned int *exact_tests)
 {
@@ -1504,7 +1504,6 @@ __global__ void k_probe_trace(const RenderParams P, const double *__restrict__ r
 __global__ void k_probe_sphere(const double *__restrict__ rays, const double *__restrict__ geom, int n, double *__restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned int probe_lanes = __ballot_sync(0xffffffffu, i < n);   // the lanes that run a query together (query_clustered)
     if (i >= n) return;
     const d3 o = mk3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]);
     const d3 d = mk3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
@@ -1526,7 +1525,6 @@ __global__ void k_probe_sphere(const double *__restrict__ rays, const double *__
 __global__ void k_probe_plane(const double *__restrict__ rays, int n, double *__restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned int probe_lanes = __ballot_sync(0xffffffffu, i < n);   // the lanes that run a query together (query_clustered)
     if (i >= n) return;
     const d3 o = mk3(rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2]);
     const d3 d = mk3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
