@@ -2,7 +2,8 @@
 """bench.py — headline benchmark of the render path (BASELINE.json: Mrays/s on the default demo scene
 at 7680x4320, reference bounce depth, milky_way skybox, row-band sharded over 1/2/4/8 GPUs).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config demo8k|demo4k|stress|orbit]
+                    [--fused -1|0|1|2] [--pieces 0.7,0.3]        (gather form and piece fractions at N > 1, see --help)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One step = one frame through the hot path: K1 (render band, persistent FP64 kernel) -> K2 (ANSI
@@ -67,8 +68,9 @@ def workload_config(cfg, n_gpus):
     else:
         pose = f"orbit pose t={cfg['t']}s"
         shard = (f"cost-weighted contiguous row-bands x{n_gpus} (1/8-resolution cost pre-pass, then feedback from the ranks' measured K1 "
-                 f"times); every rank's encoded bytes go into rank 0's stream over NVLink peer memory (see 'gather'); one small NCCL "
-                 f"all-gather (the K1 times) ends the step") if n_gpus > 1 else "single GPU"
+                 f"times); every rank's encoded bytes go into rank 0's stream over NVLink peer memory (see 'gather'); a step ends on the device "
+                 f"(per-rank flag words behind rank 0's stream, no host synchronisation); a small NCCL all-gather of the K1 times runs only on "
+                 f"the feedback steps (the first five, then every 32nd)") if n_gpus > 1 else "single GPU"
     return {
         "workload": f"{cfg['label']}: {what}, {w}x{h} cells, 10 samples/pixel, bounce limit 10, skybox {sky}, {pose}",
         "width": w, "height": h, "samples_per_pixel": 10, "bounce_limit": 10, "skybox": cfg["skybox"],

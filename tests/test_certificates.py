@@ -92,3 +92,40 @@ def test_certificates_random_lights_tilted_ground_scaled_scene(cc):
                 sc.pls[i].position = abi.Vector(q.x * scale, q.y * scale, q.z * scale)
         bad, _ = U.cert_check(cc, sc)
         assert bad == 0, (trial, scale)
+
+
+def test_work_deal_of_a_chunk_covers_every_item_once():
+    """classify_chunk (trt_render.cu) deals the (ray, group of 8) items of a chunk to quads of the lanes that run the query.  A
+    restatement of its index arithmetic — the work list by group then ray, quads over the RANKS of the active lanes, a short
+    "quad" when fewer than four lanes are active, the pair loop cut at the chunk's sphere count — for arbitrary lane masks:
+    every pair of every needed group is classified by exactly one lane, for exactly its ray, and nothing else is touched."""
+    rng = np.random.default_rng(11)
+    masks = [0xffffffff, 0x1, 0x80000000, 0x7, 0xf, 0x1f, 0xaaaaaaaa, 0x0000ffff] + [int(rng.integers(1, 1 << 32)) for _ in range(40)]
+    for lanes in masks:
+        active = [l for l in range(32) if (lanes >> l) & 1]
+        n_act = len(active)
+        rank = {l: i for i, l in enumerate(active)}
+        cnt = int(rng.choice([32, 31, 24, 17, 9, 8, 2, 1]))
+        groups = {l: int(rng.integers(0, 16)) for l in active}
+        # the work list: four ballots, position = items of the lower groups + lower lanes with the same group
+        items = []
+        for g in range(4):
+            items += [(l << 2) | g for l in active if (groups[l] >> g) & 1]
+        assert len(items) <= 128 and all(0 <= it < 128 for it in items)
+        full = n_act >= 4
+        width, quads = (4, n_act >> 2) if full else (n_act, 1)
+        seen = {}
+        for l in active:
+            quad, first = (rank[l] >> 2, rank[l] & 3) if full else (0, rank[l])
+            if quad >= quads:
+                continue
+            for it in range(quad, len(items), quads):
+                r, g = items[it] >> 2, items[it] & 3
+                for pp in range(first, 4, width):
+                    j = 8 * g + 2 * pp
+                    if j >= cnt:
+                        break
+                    assert (r, j) not in seen
+                    seen[(r, j)] = l
+        want = {(l, 8 * g + 2 * pp) for l in active for g in range(4) if (groups[l] >> g) & 1 for pp in range(4) if 8 * g + 2 * pp < cnt}
+        assert set(seen) == want
