@@ -40,9 +40,9 @@ src = open(source, errors="replace").read().splitlines()
 heads = []
 for i, text in enumerate(src, 1):
     if re.match(r"^(static |template|__device__|__global__|TRT_HD|inline)", text) and "(" in text and not text.rstrip().endswith(";"):
-        m = re.search(r"([A-Za-z_][A-Za-z0-9_<>]*)\s*\(", text)
+        m = re.search(r"\b(k_[A-Za-z0-9_]+)\s*\(", text) if "__global__" in text else re.search(r"([A-Za-z_][A-Za-z0-9_<>]*)\s*\(", text)
         if m:
-            heads.append((i, m.group(1)))
+            heads.append((i, m.group(1) + (" (kernel body)" if "__global__" in text else "")))
 
 
 def other_text(k):
