@@ -144,7 +144,6 @@ class FramePipeline:
         if rank == 0 and not self.host_stream:
             if self.peer:
                 # cudaMalloc'ed by the library (an IPC handle needs the base of an allocation), viewed as a torch tensor
-                # + 64 flag words behind the stream: every rank's completed step number (trt_signal_step / trt_wait_steps)
                 # + 128 flag words behind the stream (trt_signal_step / trt_wait_steps): word r = rank r's completed step,
                 # word 32 = a wait timed out, word 40 = the last frame rank 0 has consumed
                 self.flags_offset = (total + 16 + 255) & ~255
